@@ -1,0 +1,207 @@
+"""Layer table of the YOLOv2 detector, darknet ``.weights`` IO and seeded synthetic weights.
+
+Host-side only (numpy).  What it mirrors in the reference:
+
+* layer table            -- models_detection/KerasYOLO.py:277-400 (conv_1..conv_23, the five
+                            MaxPooling2D, the conv_21 skip + space_to_depth + concatenate)
+* ``read_darknet_weights`` -- utility/utils.py:138-148 (WeightReader) +
+                            models_detection/KerasYOLO.py:244-274 (init_weights) and the file
+                            header rules of darknet/src/parser.c:1214-1226
+* ``write_darknet_weights`` -- inverse of the above (darknet/src/parser.c:1149-1198 order:
+                            biases, [scales, rolling_mean, rolling_variance], weights)
+
+No weights ship with the reference, so benches and tests use
+``synthetic_yolo_weights`` -- random-init weights of the same architecture.
+"""
+from __future__ import annotations
+
+import struct
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import numpy as np
+
+ANCHORS = [0.57273, 0.677385, 1.87446, 2.06253, 3.33843, 5.47434, 7.88282, 3.52778, 9.77052, 9.16828]
+N_BOX = 5
+BN_EPS_KERAS = 1e-3          # keras BatchNormalization default epsilon
+
+
+@dataclass(frozen=True)
+class ConvSpec:
+    """One conv_k of KerasYOLO.load_model (index = Keras name conv_<index>)."""
+    index: int
+    ksize: int
+    cin: int
+    cout: int
+    bn: bool            # BatchNormalization + LeakyReLU(0.1) follow; else bias + linear
+    pool: bool          # MaxPooling2D(2,2) follows
+    src: str            # "prev" | "skip" (conv_13 pre-pool output) | "concat" ([s2d(conv_21), conv_20])
+
+
+def yolo_layer_table(n_class: int = 80) -> List[ConvSpec]:
+    """conv_1..conv_23 in weight-file order (KerasYOLO.py:277-400)."""
+    out_ch = N_BOX * (4 + 1 + n_class)
+    t = [
+        (3, 3, 32, True), (3, 32, 64, True), (3, 64, 128, False), (1, 128, 64, False),
+        (3, 64, 128, True), (3, 128, 256, False), (1, 256, 128, False), (3, 128, 256, True),
+        (3, 256, 512, False), (1, 512, 256, False), (3, 256, 512, False), (1, 512, 256, False),
+        (3, 256, 512, True), (3, 512, 1024, False), (1, 1024, 512, False), (3, 512, 1024, False),
+        (1, 1024, 512, False), (3, 512, 1024, False), (3, 1024, 1024, False), (3, 1024, 1024, False),
+    ]
+    specs = [ConvSpec(i + 1, k, ci, co, True, p, "prev") for i, (k, ci, co, p) in enumerate(t)]
+    specs.append(ConvSpec(21, 1, 512, 64, True, False, "skip"))
+    specs.append(ConvSpec(22, 3, 1280, 1024, True, False, "concat"))
+    specs.append(ConvSpec(23, 1, 1024, out_ch, False, False, "prev"))
+    return specs
+
+
+def n_params(n_class: int = 80) -> int:
+    n = 0
+    for s in yolo_layer_table(n_class):
+        n += s.ksize * s.ksize * s.cin * s.cout + (4 * s.cout if s.bn else s.cout)
+    return n
+
+
+# --------------------------------------------------------------------------------------
+# synthetic weights
+# --------------------------------------------------------------------------------------
+
+def synthetic_yolo_weights(n_class: int = 80, seed: int = 0, head_obj_bias: float = -2.0,
+                           head_gains=(0.13, 0.05, 0.40, 0.80)) -> Dict[str, np.ndarray]:
+    """Random-init weights of the KerasYOLO architecture, Keras layouts.
+
+    kernel_k : (kh, kw, Cin, Cout) float32   gamma_k/beta_k/mean_k/var_k : (Cout,)   bias_23 : (Cout,)
+    He-scaled kernels keep activations O(1..10) through 22 layers; the head (conv_23) columns are
+    scaled per entry type (``head_gains`` = xy, wh, objectness, class; conv_feat has rms ~7 on
+    random frames) and the objectness bias shifted so that t_xy ~ N(0,1), t_wh ~ N(0,0.4) and a few
+    dozen anchors pass the 0.5 threshold on random frames.
+    """
+    rng = np.random.default_rng(seed)
+    w: Dict[str, np.ndarray] = {}
+    for s in yolo_layer_table(n_class):
+        fan_in = s.ksize * s.ksize * s.cin
+        # gain for LeakyReLU(0.1): sqrt(2/(1+0.01))
+        std = np.sqrt(2.0 / 1.01 / fan_in) if s.bn else np.sqrt(1.0 / fan_in)
+        ker = rng.standard_normal((s.ksize, s.ksize, s.cin, s.cout), dtype=np.float32) * np.float32(std)
+        if not s.bn:
+            d = 5 + n_class
+            col = np.empty(d, np.float32)
+            col[0:2], col[2:4], col[4], col[5:] = head_gains
+            ker *= np.tile(col, N_BOX)[None, None, None, :]
+        w[f"kernel_{s.index}"] = ker
+        if s.bn:
+            w[f"gamma_{s.index}"] = rng.uniform(0.5, 1.5, s.cout).astype(np.float32)
+            w[f"beta_{s.index}"] = (0.1 * rng.standard_normal(s.cout)).astype(np.float32)
+            w[f"mean_{s.index}"] = (0.1 * rng.standard_normal(s.cout)).astype(np.float32)
+            w[f"var_{s.index}"] = rng.uniform(0.5, 1.5, s.cout).astype(np.float32)
+        else:
+            b = (0.1 * rng.standard_normal(s.cout)).astype(np.float32)
+            d = 5 + n_class
+            b.reshape(N_BOX, d)[:, 4] += np.float32(head_obj_bias)
+            w[f"bias_{s.index}"] = b
+    return w
+
+
+# --------------------------------------------------------------------------------------
+# darknet .weights file
+# --------------------------------------------------------------------------------------
+
+def write_darknet_weights(path: str, w: Dict[str, np.ndarray], n_class: int = 80,
+                          major: int = 0, minor: int = 1, revision: int = 0, seen: int = 0) -> None:
+    """Emit a darknet weights file: header (3 x int32 + seen), then per conv
+    biases(beta) [scales(gamma) rolling_mean rolling_variance] weights[Cout][Cin][kh][kw]."""
+    with open(path, "wb") as f:
+        f.write(struct.pack("<iii", major, minor, revision))
+        if major * 10 + minor >= 2 and major < 1000 and minor < 1000:
+            f.write(struct.pack("<Q", seen))
+        else:
+            f.write(struct.pack("<i", seen))
+        for s in yolo_layer_table(n_class):
+            if s.bn:
+                for k in ("beta", "gamma", "mean", "var"):
+                    f.write(np.ascontiguousarray(w[f"{k}_{s.index}"], dtype="<f4").tobytes())
+            else:
+                f.write(np.ascontiguousarray(w[f"bias_{s.index}"], dtype="<f4").tobytes())
+            k_oihw = np.transpose(w[f"kernel_{s.index}"], (3, 2, 0, 1))
+            f.write(np.ascontiguousarray(k_oihw, dtype="<f4").tobytes())
+
+
+def read_darknet_weights(path: str, n_class: int = 80, strict: bool = True) -> Dict[str, np.ndarray]:
+    """Parse a darknet weights file into Keras-layout arrays.
+
+    Header handling follows darknet/src/parser.c:1214-1226 (``seen`` is int32 for v0.1 files and
+    size_t from v0.2 on); the reference's own WeightReader (utils.py:138-148) always skips 16
+    bytes, i.e. it is only right for v0.1 files -- both give the same result there.
+    """
+    raw = np.fromfile(path, dtype=np.uint8)
+    if raw.size < 16:
+        raise ValueError(f"{path}: too short to be a darknet weights file")
+    major, minor, _rev = struct.unpack("<iii", raw[:12].tobytes())
+    off = 12 + (8 if (major * 10 + minor >= 2 and major < 1000 and minor < 1000) else 4)
+    body = raw[off:]
+    if body.size % 4:
+        raise ValueError(f"{path}: payload is not a whole number of float32")
+    flt = body.view("<f4")
+    pos = 0
+
+    def take(n: int) -> np.ndarray:
+        nonlocal pos
+        if pos + n > flt.size:
+            raise ValueError(f"{path}: truncated (need {pos + n} floats, file holds {flt.size})")
+        a = flt[pos:pos + n]
+        pos += n
+        return np.array(a, dtype=np.float32)
+
+    w: Dict[str, np.ndarray] = {}
+    for s in yolo_layer_table(n_class):
+        if s.bn:
+            w[f"beta_{s.index}"] = take(s.cout)
+            w[f"gamma_{s.index}"] = take(s.cout)
+            w[f"mean_{s.index}"] = take(s.cout)
+            w[f"var_{s.index}"] = take(s.cout)
+        else:
+            w[f"bias_{s.index}"] = take(s.cout)
+        k = take(s.cout * s.cin * s.ksize * s.ksize).reshape(s.cout, s.cin, s.ksize, s.ksize)
+        w[f"kernel_{s.index}"] = np.ascontiguousarray(np.transpose(k, (2, 3, 1, 0)))
+    if strict and pos != flt.size:
+        raise ValueError(f"{path}: {flt.size - pos} trailing floats (wrong class count?)")
+    return w
+
+
+# --------------------------------------------------------------------------------------
+# tracker heads
+# --------------------------------------------------------------------------------------
+
+def synthetic_lstm_weights(n_in: int, units: int, n_out: int, seed: int = 1) -> Dict[str, np.ndarray]:
+    """Keras-2 LSTM + Dense weights: kernel (n_in,4u), recurrent_kernel (u,4u), bias (4u,) in gate
+    order i,f,c,o; dense_kernel (u,n_out), dense_bias (n_out,)  (TinyTracker.py:36-37)."""
+    rng = np.random.default_rng(seed)
+    g = lambda *s, sc: (rng.standard_normal(s) * sc).astype(np.float32)
+    b = np.zeros(4 * units, np.float32)
+    b[units:2 * units] = 1.0                      # keras unit_forget_bias
+    b += g(4 * units, sc=0.05)
+    return {
+        "kernel": g(n_in, 4 * units, sc=1.0 / np.sqrt(n_in)),
+        "recurrent_kernel": g(units, 4 * units, sc=1.0 / np.sqrt(units)),
+        "bias": b,
+        "dense_kernel": g(units, n_out, sc=2.0 / np.sqrt(units)),
+        "dense_bias": g(n_out, sc=0.1),
+    }
+
+
+def synthetic_convlstm_weights(cin: int, units: int, n_out: int, seed: int = 2) -> Dict[str, np.ndarray]:
+    """Keras-2 ConvLSTM2D(units,3x3,same) + 1x1 head: kernel (3,3,cin,4u), recurrent_kernel
+    (3,3,u,4u), bias (4u,), gate order i,f,c,o; head_kernel (1,1,u,n_out), head_bias
+    (MultiObjDetTracker.py:176-183)."""
+    rng = np.random.default_rng(seed)
+    g = lambda *s, sc: (rng.standard_normal(s, dtype=np.float32) * np.float32(sc))
+    b = np.zeros(4 * units, np.float32)
+    b[units:2 * units] = 1.0
+    b += g(4 * units, sc=0.05)
+    return {
+        "kernel": g(3, 3, cin, 4 * units, sc=1.0 / np.sqrt(9 * cin)),
+        "recurrent_kernel": g(3, 3, units, 4 * units, sc=1.0 / np.sqrt(9 * units)),
+        "bias": b,
+        "head_kernel": g(1, 1, units, n_out, sc=2.0 / np.sqrt(units)),
+        "head_bias": g(n_out, sc=0.1),
+    }
