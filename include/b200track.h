@@ -1,0 +1,153 @@
+/*
+ * b200track.h -- C-ABI of libb200track.so: the per-frame detect-and-track hot path of
+ * ktzsh/object-tracking on one B200 (sm_100a).
+ *
+ * Plain C: opaque handle, int status (0 = ok, <0 = error; text in b2t_last_error()), plain
+ * pointers and sizes, no torch types.  The library never calls exit().  Device pointers are
+ * raw CUDA addresses (e.g. torch.Tensor.data_ptr()); "stream" is a cudaStream_t passed as void*
+ * (NULL = the legacy default stream).  One context per GPU; a context is not thread-safe.
+ *
+ * The reference has no FFI for its Keras path (it calls into a TensorFlow session); every
+ * entry point below names the reference code it replaces.  The reference's *existing* FFI
+ * (models_detection/YOLO.py:58-119 -> libdarknet.so) is declared in darknet_compat.h.
+ */
+#ifndef B200TRACK_H
+#define B200TRACK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b2t_ctx b2t_ctx;
+
+/* semantics of BatchNorm / space-to-depth, which differ between the two reference detectors */
+enum { B2T_SEM_KERAS = 0,     /* gamma*(x-mean)/sqrt(var+eps)+beta, tf.space_to_depth  (KerasYOLO.py:257-262,241) */
+       B2T_SEM_DARKNET = 1 }; /* (x-mean)/(sqrt(var)+1e-6)*gamma+beta, reorg_cpu        (blas.c:147-158, :9-30)    */
+
+/* which contraction kernel runs the convolutions */
+enum { B2T_ENGINE_TCGEN05 = 0,   /* tcgen05.mma, bf16 hi/lo split operands, 3 MMAs per product, fp32 accumulate in TMEM */
+       B2T_ENGINE_SIMT = 1 };    /* fp32 FMA on the same operands: on-device cross-check only (slow)                    */
+
+enum { B2T_FRAME_U8 = 0,      /* HWC uint8, divided by 255 on load (utils.py:150-153 normalize) */
+       B2T_FRAME_F32 = 1 };   /* HWC float32, already normalised                                 */
+
+typedef struct {
+    int image_h, image_w;     /* KerasYOLO.IMAGE_H/W (416) ; multiples of 32                     */
+    int n_class;              /* KerasYOLO.CLASS                                                 */
+    int max_batch;            /* frames per b2t_yolo_forward call                                */
+    int semantics;            /* B2T_SEM_*                                                       */
+    float bn_eps;             /* keras epsilon (1e-3); ignored for B2T_SEM_DARKNET               */
+    int engine;               /* B2T_ENGINE_*                                                    */
+    int device;               /* CUDA device ordinal                                             */
+    int convlstm_units;       /* 0 = no MultiObjDetTracker head; else ConvLSTM2D filters (512)   */
+    int reserved[7];          /* reserved[0] = 1: also keep the pre-pool outputs of conv_1,2,5,8 (KerasYOLO.extract) */
+} b2t_config;
+
+const char *b2t_last_error(void);
+int  b2t_version(void);
+
+/* ---- lifetime ---------------------------------------------------------------------------- */
+int  b2t_create(const b2t_config *cfg, b2t_ctx **out);
+void b2t_destroy(b2t_ctx *ctx);
+
+/* Device memory is the caller's (a torch tensor): ask for the sizes, allocate, bind.  If
+ * b2t_bind_memory is never called the context cudaMalloc's its own at b2t_finalize. */
+size_t b2t_weight_bytes(const b2t_ctx *ctx);      /* packed weight blob (what a weight broadcast moves)      */
+size_t b2t_workspace_bytes(const b2t_ctx *ctx);   /* activations + split-K partials + decode scratch          */
+int    b2t_bind_memory(b2t_ctx *ctx, void *weight_blob_dev, void *workspace_dev);
+
+/* ---- weights: replaces KerasYOLO.init_weights (KerasYOLO.py:244-274) + WeightReader (utils.py:138-148) ---- */
+/* conv_index 1..23.  kernel: Keras layout (kh,kw,Cin,Cout) float32.  BN layers pass gamma/beta/mean/var,
+ * conv_23 passes bias (others NULL).  Host pointers; packed into a host staging copy of the blob. */
+int  b2t_set_conv_weights(b2t_ctx *ctx, int conv_index, const float *kernel_hwio,
+                          const float *gamma, const float *beta, const float *mean, const float *var,
+                          const float *bias);
+/* darknet .weights file (darknet/src/parser.c:1149-1230; v0.1 int32 and v0.2 size_t "seen" headers) */
+int  b2t_load_darknet_weights(b2t_ctx *ctx, const char *path);
+/* ConvLSTM2D + 1x1 head of MultiObjDetTracker (MultiObjDetTracker.py:176-183), Keras layouts:
+ * kernel (3,3,Cz,4u) with Cz = 5*(5+C)+1024, recurrent (3,3,u,4u), bias (4u), head (1,1,u,5*(5+C)), head_bias */
+int  b2t_set_convlstm_weights(b2t_ctx *ctx, const float *kernel, const float *recurrent, const float *bias,
+                              const float *head_kernel, const float *head_bias);
+/* upload the staged blob to the device, build TMA descriptors.  Call once after all weights are set
+ * (or after a broadcast wrote the device blob: pass upload=0 to keep the device copy). */
+int  b2t_finalize(b2t_ctx *ctx, int upload, void *stream);
+
+/* ---- detector forward: replaces model.predict in KerasYOLO.predict (KerasYOLO.py:531) and
+ *      forward_network in darknet (network.c:198-221) ---------------------------------------- */
+/* frames_dev: (B,H,W,3) uint8 or float32 on the device.  logits_dev: (B,G,G,5,5+C) float32 or NULL
+ * (the context keeps its own copy, see b2t_logits).  Asynchronous on `stream`. */
+int  b2t_yolo_forward(b2t_ctx *ctx, const void *frames_dev, int frame_dtype, int batch,
+                      float *logits_dev, void *stream);
+const float *b2t_logits(const b2t_ctx *ctx);          /* device (max_batch,G,G,5*(5+C)) of the last forward */
+/* KerasYOLO.extract (KerasYOLO.py:509-520) / network_extract_feat (network.c:589-598): copy a layer's
+ * post-activation output (pre-pool), NHWC float32, into out_dev.  name: "norm_1".."norm_22", "conv_23",
+ * "conv_feat" (= norm_22), "concat".  Returns the number of floats per frame, <0 on error. */
+long b2t_extract(b2t_ctx *ctx, const char *name, int batch, float *out_dev, void *stream);
+int  b2t_layer_dims(const b2t_ctx *ctx, const char *name, int *h, int *w, int *c);
+
+/* ---- anchor decode + threshold + per-class NMS: replaces decode_netout (utils.py:208-257) ---- */
+/* logits_dev (B,G,G,A,5+C) fp32 -> boxes_dev (B,max_boxes,8) rows [x,y,w,h,conf,score,label,anchor_id]
+ * in row-major anchor order, counts_dev (B) int32.  anchors: host, 2*A floats. */
+int  b2t_decode_nms(b2t_ctx *ctx, const float *logits_dev, int batch, int grid_h, int grid_w, int n_box,
+                    int n_class, float obj_threshold, float nms_threshold, const float *anchors,
+                    float *boxes_dev, int *counts_dev, int max_boxes, void *stream);
+/* darknet flavour: forward_region_layer + get_region_detections + do_nms_obj (region_layer.c:158-185,
+ * :364-437; box.c:21-55) incl. letterbox un-mapping (correct_region_boxes :336-362, relative=0).
+ * rows [cx,cy,w,h (pixels of the orig_w x orig_h frame), objectness, best prob, best class, anchor_id],
+ * sorted by -best prob (YOLO.py:159), only rows with some prob > 0 after NMS. */
+int  b2t_region_detect(b2t_ctx *ctx, const float *logits_dev, int batch, int grid_h, int grid_w, int n_box,
+                       int n_class, float thresh, float nms_threshold, const float *anchors,
+                       int orig_w, int orig_h, int net_w, int net_h,
+                       float *dets_dev, int *counts_dev, int max_dets, void *stream);
+
+/* ---- recurrent trackers ------------------------------------------------------------------- */
+/* TinyTracker / TinyHeatmapTracker (TinyTracker.py:25-41, TinyHeatmapTracker.py:26-48): an opaque
+ * LSTM head bound to the context.  pool: 0 = Global max (F = C_feat), 1 = MaxPooling2D(4,4)+Flatten. */
+typedef struct b2t_lstm b2t_lstm;
+int  b2t_lstm_create(b2t_ctx *ctx, int n_feat, int n_det, int units, int n_out, int max_streams,
+                     b2t_lstm **out);
+void b2t_lstm_destroy(b2t_lstm *l);
+/* Keras layouts: kernel (n_feat+n_det, 4u), recurrent (u,4u), bias (4u) gate order i,f,c,o;
+ * dense_kernel (u,n_out), dense_bias (n_out).  Host pointers. */
+int  b2t_lstm_set_weights(b2t_lstm *l, const float *kernel, const float *recurrent, const float *bias,
+                          const float *dense_kernel, const float *dense_bias, void *stream);
+int  b2t_lstm_reset(b2t_lstm *l, int stream_index /* -1 = all */, void *stream);
+/* fv_dev (S,n_feat) fp32 pooled features, det_dev (S,n_det) fp32 -> y_dev (S,n_out) fp32; state persists */
+int  b2t_lstm_step(b2t_lstm *l, const float *fv_dev, const float *det_dev, int n_streams,
+                   float *y_dev, int hard_sigmoid, void *stream);
+/* pooled feature of the last forward's conv layer `name` for frames [0,batch): Global -> (B,C);
+ * Max -> (B,(H/4)*(W/4)*C).  chw_view=1 reproduces preprocessing.py:419 (CHW buffer viewed as HWC). */
+int  b2t_pool_features(b2t_ctx *ctx, const char *name, int batch, int pool_mode, int chw_view,
+                       float *fv_dev, void *stream);
+/* generate_heatmap_feat / generate_rectangle_from_heatmap (utils.py:53-79) on the device */
+int  b2t_heatmap_from_box(b2t_ctx *ctx, const float *xywh_dev /* (S,4) top-left x,y,w,h rel. */, int n,
+                          int size, float *heat_dev /* (S,size*size) */, void *stream);
+/* preprocessing.py:434-456 + YOLO.py:177-180: first (highest-prob) row of b2t_region_detect whose class is
+ * allowed -> LSTM bbox input [cx/w,cy/h,bw/w,bh/h] (zeros if none), optionally its heat-map, chosen row or -1 */
+int  b2t_select_detection(b2t_ctx *ctx, const float *dets_dev, const int *counts_dev, int max_dets, int batch,
+                          const unsigned char *class_mask_dev /* n_class bytes or NULL */, int frame_w, int frame_h,
+                          float *det_in_dev /* (B,4) */, int heat_size, float *heat_dev /* or NULL */,
+                          int *chosen_dev /* or NULL */, void *stream);
+int  b2t_box_from_heatmap(b2t_ctx *ctx, const float *heat_dev, int n, int size, float thresh,
+                          int *rect_dev /* (S,4) x1,y1,x2,y2 */, void *stream);
+
+/* MultiObjDetTracker (MultiObjDetTracker.py:160-189): ConvLSTM2D over concat[conv_23 logits, conv_feat]
+ * of the last b2t_yolo_forward, frames [0,batch) taken as consecutive time steps of ONE stream
+ * (TimeDistributed, :162-171), then the 1x1 head.  trk_logits_dev (batch,G,G,5*(5+C)) fp32. */
+int  b2t_convlstm_reset(b2t_ctx *ctx, void *stream);
+int  b2t_convlstm_window(b2t_ctx *ctx, int batch, float *trk_logits_dev, int hard_sigmoid, void *stream);
+
+/* ---- introspection for bench.py ------------------------------------------------------------ */
+long b2t_launch_count(const b2t_ctx *ctx);            /* kernels launched by this context so far */
+/* per-conv timing with CUDA events: runs the forward once, fills ms[23] and (optional) the algorithmic
+ * bytes[23] of each conv (weights + input + output, fp32-equivalent 4 B/element) */
+int  b2t_profile_forward(b2t_ctx *ctx, const void *frames_dev, int frame_dtype, int batch, float *ms,
+                         double *bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200TRACK_H */

@@ -1,0 +1,913 @@
+// C-ABI of libb200track.so (include/b200track.h): context, weight packing, TMA descriptors, launch plan.
+// Host code only orchestrates; every numeric step runs in the kernels of conv_umma.cu / decode_nms.cu /
+// tracker.cu.  There is no CPU fallback: without a device every compute entry point fails with an error.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/b200track.h"
+#include "kernels.cuh"
+
+using namespace b2t;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CK(expr)                                                                                           \
+    do {                                                                                                   \
+        cudaError_t e__ = (cudaError_t)(expr);                                                             \
+        if (e__ != cudaSuccess) return fail(-2, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+    } while (0)
+
+extern "C" const char *b2t_last_error(void) { return g_err; }
+extern "C" int b2t_version(void) { return 100; }
+
+// ------------------------------------------------------------------------------------------------ plan
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
+
+struct ActBuf {              // split-plane activation tensor sized for max_batch frames
+    size_t off = 0;          // byte offset of the hi plane inside the workspace
+    int H = 0, W = 0, C = 0; // C = channels per pixel (pix_stride)
+    long long plane = 0;     // elements between hi and lo plane
+    __nv_bfloat16 *hi = nullptr;
+};
+
+struct ConvLayer {
+    int index = 0, k = 1, cin = 0, cin_pad = 0, cout = 0;
+    bool act = true, pool = false;
+    int H = 0, W = 0;
+    int in_buf = -1, in_ch_off = 0;               // input view
+    int out_buf = -1, out_ch_off = 0, out_mode = DEST_PLAIN;   // full-res bf16 destination (-1 none)
+    int pout_buf = -1;                            // pooled bf16 destination
+    int f32_out = 0;                              // 1 = logits, 2 = convlstm gates, 3 = tracker logits
+    int f32_accumulate = 0;
+    size_t off_whi = 0, off_wlo = 0, off_scale = 0, off_bias = 0;
+    int ldw = 0;
+    int TW = 16, TH = 8, BN = 128;
+    CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
+    bool have_weights = false;
+};
+
+struct b2t_ctx {
+    b2t_config cfg;
+    int G = 0, A = 5, D = 0;
+    int keep_prepool = 0;
+    std::vector<ActBuf> bufs;
+    std::map<std::string, int> buf_by_name;       // "norm_k" -> buffer
+    std::map<std::string, int> cout_by_name;      // true channel count of that tensor
+    std::map<std::string, int> choff_by_name;
+    std::vector<ConvLayer> conv;                  // [0] unused, 1..23, then convlstm layers
+    int L_CIN = 0, L_CREC = 0, L_HEAD = 0;        // indices of the ConvLSTM layers (0 = absent)
+    // conv_1
+    size_t off_w1 = 0, off_s1 = 0, off_b1 = 0, off_lut = 0;
+    // memory
+    size_t weight_bytes = 0, ws_bytes = 0;
+    std::vector<uint8_t> host_blob;
+    uint8_t *d_blob = nullptr, *d_ws = nullptr;
+    bool own_blob = false, own_ws = false;
+    size_t off_logits = 0, off_partial = 0, partial_bytes = 0;
+    size_t off_gates = 0, off_cstate = 0;
+    int buf_hrec = -1, buf_hseq = -1, buf_z = -1;
+    bool finalized = false;
+    long launches = 0;
+    int n_sm = 148;
+    PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+};
+
+static int add_buf(b2t_ctx *c, const std::string &name, int H, int W, int C) {
+    ActBuf b;
+    b.H = H; b.W = W; b.C = C;
+    b.plane = (long long)c->cfg.max_batch * H * W * C;
+    c->bufs.push_back(b);
+    const int id = (int)c->bufs.size() - 1;
+    if (!name.empty()) c->buf_by_name[name] = id;
+    return id;
+}
+
+static void choose_tile(int H, int W, bool pool, int &TW, int &TH) {
+    double best = -1;
+    for (int tw = 4; tw <= 128; tw *= 2) {
+        const int th = 128 / tw;
+        if (pool && (tw > 16 || (th & 1))) continue;
+        const double eff = (double)H * W / ((double)((W + tw - 1) / tw * tw) * ((H + th - 1) / th * th));
+        if (eff > best + 1e-9 || (fabs(eff - best) <= 1e-9 && tw > TW)) { best = eff; TW = tw; TH = th; }
+    }
+}
+
+static int choose_splits(int tiles, int chunks, int n_sm) {
+    const char *env = getenv("B2T_SPLITS");
+    if (env && atoi(env) > 0) {
+        int s = atoi(env) < chunks ? atoi(env) : chunks;
+        const int per = (chunks + s - 1) / s;
+        return (chunks + per - 1) / per;
+    }
+    int best_s = 1;
+    double best_cost = 1e30;
+    const int max_s = chunks / 2 < 1 ? 1 : (chunks / 2 > 32 ? 32 : chunks / 2);
+    for (int s = 1; s <= max_s; ++s) {
+        const int per = (chunks + s - 1) / s;
+        const int s_eff = (chunks + per - 1) / per;
+        if (s_eff != s) continue;
+        const long ctas = (long)tiles * s;
+        const long waves = (ctas + n_sm - 1) / n_sm;
+        const double cost = (double)waves * (per + 8.0) + (s > 1 ? 2.0 * s : 0.0);   // + split-K reduce traffic
+        if (cost < best_cost - 1e-9) { best_cost = cost; best_s = s; }
+    }
+    return best_s;
+}
+
+// ------------------------------------------------------------------------------------------------ create
+static ConvLayer &new_conv(b2t_ctx *c, int index, int k, int cin, int cout, bool act, bool pool, int H, int W) {
+    ConvLayer l;
+    l.index = index; l.k = k; l.cin = cin; l.cin_pad = round_up(cin, 64); l.cout = cout;
+    l.act = act; l.pool = pool; l.H = H; l.W = W;
+    l.ldw = k * k * l.cin_pad;
+    l.BN = cout >= 128 ? 128 : 64;
+    choose_tile(H, W, pool, l.TW, l.TH);
+    if ((int)c->conv.size() <= index) c->conv.resize(index + 1);
+    c->conv[index] = l;
+    return c->conv[index];
+}
+
+static void blob_reserve(b2t_ctx *c, ConvLayer &l) {
+    size_t o = c->weight_bytes;
+    l.off_whi = o;  o += align_up((size_t)l.cout * l.ldw * 2, 256);
+    l.off_wlo = o;  o += align_up((size_t)l.cout * l.ldw * 2, 256);
+    l.off_scale = o;  o += align_up((size_t)l.cout * 4, 256);
+    l.off_bias = o;  o += align_up((size_t)l.cout * 4, 256);
+    c->weight_bytes = o;
+}
+
+extern "C" int b2t_create(const b2t_config *cfg, b2t_ctx **out) {
+    if (!cfg || !out) return fail(-1, "b2t_create: null argument");
+    if (cfg->image_h % 32 || cfg->image_w % 32 || cfg->image_h <= 0 || cfg->image_w <= 0)
+        return fail(-1, "b2t_create: image size %dx%d must be a positive multiple of 32", cfg->image_h, cfg->image_w);
+    if (cfg->image_h != cfg->image_w) return fail(-1, "b2t_create: square input expected (GRID_H == GRID_W)");
+    if (cfg->n_class < 1 || cfg->max_batch < 1) return fail(-1, "b2t_create: bad n_class/max_batch");
+    b2t_ctx *c = new b2t_ctx();
+    c->cfg = *cfg;
+    c->keep_prepool = cfg->reserved[0];
+    c->G = cfg->image_h / 32;
+    c->D = 5 + cfg->n_class;
+    const int AD = c->A * c->D;
+    const int H0 = cfg->image_h;
+    c->conv.resize(24);
+
+    // conv_k table (KerasYOLO.py:277-400): k, cin, cout, pool-after
+    static const int T[20][4] = {{3, 3, 32, 1},     {3, 32, 64, 1},    {3, 64, 128, 0},    {1, 128, 64, 0},
+                                 {3, 64, 128, 1},   {3, 128, 256, 0},  {1, 256, 128, 0},   {3, 128, 256, 1},
+                                 {3, 256, 512, 0},  {1, 512, 256, 0},  {3, 256, 512, 0},   {1, 512, 256, 0},
+                                 {3, 256, 512, 1},  {3, 512, 1024, 0}, {1, 1024, 512, 0},  {3, 512, 1024, 0},
+                                 {1, 1024, 512, 0}, {3, 512, 1024, 0}, {3, 1024, 1024, 0}, {3, 1024, 1024, 0}};
+    // conv_1 blob: fp32 [27][32], scale, bias, LUT
+    c->off_w1 = 0;
+    c->off_s1 = align_up(27 * 32 * 4, 256);
+    c->off_b1 = c->off_s1 + 256;
+    c->off_lut = c->off_b1 + 256;
+    c->weight_bytes = c->off_lut + 1024;
+
+    const int Gs = c->G;
+    const bool lstm = cfg->convlstm_units > 0;
+    const int zc = lstm ? 1024 + round_up(AD, 64) : 1024;        // channels of the conv_22 output buffer
+    const int concat = add_buf(c, "concat", Gs, Gs, 1280);
+    const int featz = add_buf(c, "norm_22", Gs, Gs, zc);
+    c->buf_z = featz;
+
+    int H = H0, prev = -1;
+    int skip_buf = -1;
+    for (int i = 1; i <= 20; ++i) {
+        const int *t = T[i - 1];
+        char nm[32];
+        snprintf(nm, sizeof nm, "norm_%d", i);
+        ConvLayer &l = new_conv(c, i, t[0], t[1], t[2], true, t[3] != 0, H, H);
+        l.in_buf = prev;
+        if (i == 20) {                         // writes straight into the concat buffer (route 27,24)
+            l.out_buf = concat; l.out_ch_off = 256;
+            c->buf_by_name[nm] = concat; c->choff_by_name[nm] = 256;
+        } else if (l.pool) {
+            if (c->keep_prepool || i == 13) {
+                l.out_buf = add_buf(c, nm, H, H, round_up(l.cout, 64));
+                if (i == 13) skip_buf = l.out_buf;
+            }
+            l.pout_buf = add_buf(c, std::string("pool_") + std::to_string(i), H / 2, H / 2, round_up(l.cout, 64));
+        } else {
+            l.out_buf = add_buf(c, nm, H, H, round_up(l.cout, 64));
+        }
+        c->cout_by_name[nm] = l.cout;
+        if (i > 1) blob_reserve(c, l);
+        prev = l.pool ? l.pout_buf : l.out_buf;
+        if (l.pool) H /= 2;
+    }
+    {   // conv_21 on the 26x26 skip, space_to_depth into concat[0:256]
+        ConvLayer &l = new_conv(c, 21, 1, 512, 64, true, false, 2 * Gs, 2 * Gs);
+        l.in_buf = skip_buf;
+        l.out_buf = concat; l.out_ch_off = 0;
+        l.out_mode = cfg->semantics == B2T_SEM_DARKNET ? DEST_REORG_DARKNET : DEST_S2D_TF;
+        blob_reserve(c, l);
+        c->cout_by_name["norm_21"] = 64;
+    }
+    {
+        ConvLayer &l = new_conv(c, 22, 3, 1280, 1024, true, false, Gs, Gs);
+        l.in_buf = concat;
+        l.out_buf = featz;
+        blob_reserve(c, l);
+        c->cout_by_name["norm_22"] = 1024;
+        c->buf_by_name["conv_feat"] = featz; c->cout_by_name["conv_feat"] = 1024;
+        c->cout_by_name["concat"] = 1280;
+    }
+    {
+        ConvLayer &l = new_conv(c, 23, 1, 1024, AD, false, false, Gs, Gs);
+        l.in_buf = featz;
+        l.f32_out = 1;
+        if (lstm) { l.out_buf = featz; l.out_ch_off = 1024; }
+        blob_reserve(c, l);
+    }
+    if (lstm) {
+        const int u = cfg->convlstm_units;
+        if (u % 64) { delete c; return fail(-1, "convlstm_units must be a multiple of 64"); }
+        c->buf_hrec = add_buf(c, "", Gs, Gs, u);
+        c->buf_hseq = add_buf(c, "", Gs, Gs, u);
+        c->bufs[c->buf_hrec].plane = (long long)Gs * Gs * u;        // one stream only
+        c->L_CIN = 24; c->L_CREC = 25; c->L_HEAD = 26;
+        ConvLayer &a = new_conv(c, 24, 3, zc, 4 * u, false, false, Gs, Gs);
+        a.in_buf = featz; a.f32_out = 2;
+        blob_reserve(c, a);
+        ConvLayer &r = new_conv(c, 25, 3, u, 4 * u, false, false, Gs, Gs);
+        r.in_buf = c->buf_hrec; r.f32_out = 2; r.f32_accumulate = 1;
+        blob_reserve(c, r);
+        ConvLayer &h = new_conv(c, 26, 1, u, AD, false, false, Gs, Gs);
+        h.in_buf = c->buf_hseq; h.f32_out = 3;
+        blob_reserve(c, h);
+    }
+    c->host_blob.assign(c->weight_bytes, 0);
+    {   // LUT[u] = float(u / 255.)  (utils.py:150-153: numpy true division in float64, cast to fp32 by Keras)
+        float *lut = reinterpret_cast<float *>(c->host_blob.data() + c->off_lut);
+        for (int i = 0; i < 256; ++i) lut[i] = (float)((double)i / 255.0);
+    }
+
+    // ---- workspace layout
+    size_t o = 0;
+    const int MB = cfg->max_batch;
+    for (size_t i = 0; i < c->bufs.size(); ++i) {
+        ActBuf &b = c->bufs[i];
+        b.off = o;
+        o += align_up((size_t)b.plane * 2 * 2, 1024);
+    }
+    c->off_logits = o;  o += align_up((size_t)MB * Gs * Gs * AD * 4, 1024);
+    // split-K / SIMT partials: worst case over layers and batch sizes
+    size_t pb = 0;
+    for (size_t i = 2; i < c->conv.size(); ++i) {
+        const ConvLayer &l = c->conv[i];
+        if (!l.index) continue;
+        const size_t ldp = round_up(l.cout, 32);
+        const int tiles1 = ((l.W + l.TW - 1) / l.TW) * ((l.H + l.TH - 1) / l.TH) * ((l.cout + l.BN - 1) / l.BN);
+        for (int bsz = 1; bsz <= MB; ++bsz) {
+            size_t s = 1;
+            if (cfg->engine != B2T_ENGINE_SIMT) {
+                s = choose_splits(tiles1 * bsz, l.k * l.k * l.cin_pad / 64, 148);
+                if (s == 1) continue;
+            }
+            const size_t need = s * (size_t)bsz * l.H * l.W * ldp * 4;
+            if (need > pb) pb = need;
+        }
+    }
+    c->off_partial = o;  c->partial_bytes = pb;  o += align_up(pb, 1024);
+    if (lstm) {
+        const int u = cfg->convlstm_units;
+        c->off_gates = o;   o += align_up((size_t)MB * Gs * Gs * 4 * u * 4, 1024);
+        c->off_cstate = o;  o += align_up((size_t)Gs * Gs * u * 4, 1024);
+    }
+    c->ws_bytes = o;
+    *out = c;
+    return 0;
+}
+
+extern "C" void b2t_destroy(b2t_ctx *c) {
+    if (!c) return;
+    if (c->own_blob && c->d_blob) cudaFree(c->d_blob);
+    if (c->own_ws && c->d_ws) cudaFree(c->d_ws);
+    delete c;
+}
+
+extern "C" size_t b2t_weight_bytes(const b2t_ctx *c) { return c ? c->weight_bytes : 0; }
+extern "C" size_t b2t_workspace_bytes(const b2t_ctx *c) { return c ? c->ws_bytes : 0; }
+extern "C" long b2t_launch_count(const b2t_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int b2t_bind_memory(b2t_ctx *c, void *blob, void *ws) {
+    if (!c) return fail(-1, "null ctx");
+    if (c->finalized) return fail(-1, "b2t_bind_memory after b2t_finalize");
+    if (((uintptr_t)blob & 1023) || ((uintptr_t)ws & 1023)) return fail(-1, "device pointers must be 1024-byte aligned");
+    c->d_blob = (uint8_t *)blob;
+    c->d_ws = (uint8_t *)ws;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ weights
+static inline uint16_t f32_to_bf16_rn(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);   // NaN
+    u += 0x7fffu + ((u >> 16) & 1);
+    return (uint16_t)(u >> 16);
+}
+static inline float bf16_to_f32(uint16_t h) {
+    uint32_t u = (uint32_t)h << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+// kernel_hwio (k,k,cin_src,cout) -> [cout][tap][cin_pad] hi/lo; perm[c_dst] = c_src or -1 (NULL = identity)
+static void pack_conv(b2t_ctx *c, const ConvLayer &l, const float *ker, int cin_src, const int *perm) {
+    uint16_t *hi = reinterpret_cast<uint16_t *>(c->host_blob.data() + l.off_whi);
+    uint16_t *lo = reinterpret_cast<uint16_t *>(c->host_blob.data() + l.off_wlo);
+    const int taps = l.k * l.k;
+    for (int co = 0; co < l.cout; ++co)
+        for (int t = 0; t < taps; ++t)
+            for (int ci = 0; ci < l.cin_pad; ++ci) {
+                const int src = perm ? perm[ci] : (ci < cin_src ? ci : -1);
+                float w = 0.f;
+                if (src >= 0) w = ker[((size_t)t * cin_src + src) * l.cout + co];
+                const uint16_t h = f32_to_bf16_rn(w);
+                const uint16_t q = f32_to_bf16_rn(w - bf16_to_f32(h));
+                const size_t d = (size_t)co * l.ldw + (size_t)t * l.cin_pad + ci;
+                hi[d] = h;
+                lo[d] = q;
+            }
+}
+
+static void fold_bn(const b2t_ctx *c, int n, const float *gamma, const float *beta, const float *mean, const float *var,
+                    float *scale, float *bias) {
+    for (int i = 0; i < n; ++i) {
+        double s;
+        if (c->cfg.semantics == B2T_SEM_DARKNET)
+            s = (double)gamma[i] / (sqrt((double)var[i]) + 1e-6);                 // blas.c:156 normalize_cpu
+        else
+            s = (double)gamma[i] / sqrt((double)var[i] + (double)c->cfg.bn_eps);  // keras BN inference
+        scale[i] = (float)s;
+        bias[i] = (float)((double)beta[i] - (double)mean[i] * s);
+    }
+}
+
+extern "C" int b2t_set_conv_weights(b2t_ctx *c, int idx, const float *ker, const float *gamma, const float *beta,
+                                    const float *mean, const float *var, const float *bias) {
+    if (!c || idx < 1 || idx > 23 || !ker) return fail(-1, "b2t_set_conv_weights: bad arguments (conv_%d)", idx);
+    ConvLayer &l = c->conv[idx];
+    const bool bn = idx != 23;
+    if (bn && !(gamma && beta && mean && var)) return fail(-1, "conv_%d needs gamma/beta/mean/var", idx);
+    if (!bn && !bias) return fail(-1, "conv_23 needs a bias");
+    if (idx == 1) {
+        float *w = reinterpret_cast<float *>(c->host_blob.data() + c->off_w1);
+        memcpy(w, ker, 27 * 32 * 4);   // (kh,kw,cin,cout) is already [tap*3+cin][32]
+        fold_bn(c, 32, gamma, beta, mean, var, reinterpret_cast<float *>(c->host_blob.data() + c->off_s1),
+                reinterpret_cast<float *>(c->host_blob.data() + c->off_b1));
+    } else {
+        pack_conv(c, l, ker, l.cin, nullptr);
+        float *s = reinterpret_cast<float *>(c->host_blob.data() + l.off_scale);
+        float *b = reinterpret_cast<float *>(c->host_blob.data() + l.off_bias);
+        if (bn) {
+            fold_bn(c, l.cout, gamma, beta, mean, var, s, b);
+        } else {
+            for (int i = 0; i < l.cout; ++i) { s[i] = 1.f; b[i] = bias[i]; }
+        }
+    }
+    l.have_weights = true;
+    return 0;
+}
+
+extern "C" int b2t_load_darknet_weights(b2t_ctx *c, const char *path) {
+    if (!c || !path) return fail(-1, "null argument");
+    FILE *f = fopen(path, "rb");
+    if (!f) return fail(-3, "cannot open %s", path);
+    int32_t hdr[3];
+    if (fread(hdr, 4, 3, f) != 3) { fclose(f); return fail(-3, "%s: truncated header", path); }
+    // parser.c:1220-1226: "seen" is size_t from v0.2 on, int32 before
+    const bool wide = (hdr[0] * 10 + hdr[1] >= 2) && hdr[0] < 1000 && hdr[1] < 1000;
+    if (fseek(f, wide ? 8 : 4, SEEK_CUR)) { fclose(f); return fail(-3, "%s: truncated header", path); }
+    static const int order[23] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23};
+    std::vector<float> bn, raw, hwio;
+    for (int oi = 0; oi < 23; ++oi) {
+        const int idx = order[oi];
+        const ConvLayer &l = c->conv[idx];
+        const bool isbn = idx != 23;
+        const size_t nb = isbn ? 4 * (size_t)l.cout : (size_t)l.cout, nw = (size_t)l.cout * l.cin * l.k * l.k;
+        bn.resize(nb);
+        raw.resize(nw);
+        hwio.resize(nw);
+        if (fread(bn.data(), 4, nb, f) != nb || fread(raw.data(), 4, nw, f) != nw) {
+            fclose(f);
+            return fail(-3, "%s: truncated at conv_%d (wrong class count?)", path, idx);
+        }
+        // [Cout][Cin][kh][kw] -> (kh,kw,Cin,Cout)   (KerasYOLO.py:270-272)
+        const int kk = l.k * l.k;
+        for (int co = 0; co < l.cout; ++co)
+            for (int ci = 0; ci < l.cin; ++ci)
+                for (int t = 0; t < kk; ++t) hwio[((size_t)t * l.cin + ci) * l.cout + co] = raw[((size_t)co * l.cin + ci) * kk + t];
+        int rc;
+        if (isbn)   // file order: biases(beta), scales(gamma), rolling_mean, rolling_variance (parser.c:1165-1171)
+            rc = b2t_set_conv_weights(c, idx, hwio.data(), bn.data() + l.cout, bn.data(), bn.data() + 2 * l.cout,
+                                      bn.data() + 3 * l.cout, nullptr);
+        else
+            rc = b2t_set_conv_weights(c, idx, hwio.data(), nullptr, nullptr, nullptr, nullptr, bn.data());
+        if (rc) { fclose(f); return rc; }
+    }
+    float extra;
+    const bool trailing = fread(&extra, 4, 1, f) == 1;
+    fclose(f);
+    if (trailing) return fail(-3, "%s: trailing data after conv_23 (wrong class count?)", path);
+    return 0;
+}
+
+extern "C" int b2t_set_convlstm_weights(b2t_ctx *c, const float *kernel, const float *recurrent, const float *bias,
+                                        const float *head_kernel, const float *head_bias) {
+    if (!c || !c->L_CIN) return fail(-1, "context was created without convlstm_units");
+    if (!kernel || !recurrent || !bias || !head_kernel || !head_bias) return fail(-1, "null weight pointer");
+    const int AD = c->A * c->D, u = c->cfg.convlstm_units;
+    ConvLayer &a = c->conv[c->L_CIN], &r = c->conv[c->L_CREC], &h = c->conv[c->L_HEAD];
+    // keras channel order of z: [x_bbox (A*D), x_vis (1024)]  (MultiObjDetTracker.py:175); ours: [feat | logits | pad]
+    std::vector<int> perm(a.cin_pad, -1);
+    for (int i = 0; i < 1024; ++i) perm[i] = AD + i;
+    for (int i = 0; i < AD; ++i) perm[1024 + i] = i;
+    pack_conv(c, a, kernel, AD + 1024, perm.data());
+    pack_conv(c, r, recurrent, u, nullptr);
+    pack_conv(c, h, head_kernel, u, nullptr);
+    auto fill = [&](ConvLayer &l, const float *b) {
+        float *s = reinterpret_cast<float *>(c->host_blob.data() + l.off_scale);
+        float *bb = reinterpret_cast<float *>(c->host_blob.data() + l.off_bias);
+        for (int i = 0; i < l.cout; ++i) { s[i] = 1.f; bb[i] = b ? b[i] : 0.f; }
+        l.have_weights = true;
+    };
+    fill(a, bias);
+    fill(r, nullptr);
+    fill(h, head_bias);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ finalize
+static int make_tmap(b2t_ctx *c, CUtensorMap *tm, void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides,
+                     const cuuint32_t *box) {
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = c->encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, base, dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(-2, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return 0;
+}
+
+extern "C" int b2t_finalize(b2t_ctx *c, int upload, void *stream) {
+    if (!c) return fail(-1, "null ctx");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(c->cfg.device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, c->cfg.device));
+    if (prop.major != 10) return fail(-2, "device %d is sm_%d%d; this library contains sm_100a code only", c->cfg.device,
+                                      prop.major, prop.minor);
+    c->n_sm = prop.multiProcessorCount;
+    if (upload)
+        for (size_t i = 1; i < c->conv.size(); ++i)
+            if (c->conv[i].index && !c->conv[i].have_weights) return fail(-1, "conv layer %zu has no weights", i);
+    if (!c->d_blob) { CK(cudaMalloc(&c->d_blob, c->weight_bytes)); c->own_blob = true; }
+    if (!c->d_ws) { CK(cudaMalloc(&c->d_ws, c->ws_bytes)); c->own_ws = true; }
+    if (!c->encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (!fn || q != cudaDriverEntryPointSuccess) return fail(-2, "cuTensorMapEncodeTiled not available in this driver");
+        c->encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+    }
+    int rc = conv_umma_init();
+    if (rc) return fail(-2, "cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString((cudaError_t)rc));
+    if (upload) CK(cudaMemcpyAsync(c->d_blob, c->host_blob.data(), c->weight_bytes, cudaMemcpyHostToDevice, st));
+    // pad channels / never-written halo must be finite zeros
+    CK(cudaMemsetAsync(c->d_ws, 0, c->ws_bytes, st));
+    for (auto &b : c->bufs) b.hi = reinterpret_cast<__nv_bfloat16 *>(c->d_ws + b.off);
+    const int MB = c->cfg.max_batch;
+    for (size_t i = 2; i < c->conv.size(); ++i) {
+        ConvLayer &l = c->conv[i];
+        if (!l.index) continue;
+        const ActBuf &in = c->bufs[l.in_buf];
+        const int nb = (l.in_buf == c->buf_hrec) ? 1 : MB;
+        cuuint64_t dims[4] = {(cuuint64_t)l.cin_pad, (cuuint64_t)l.W, (cuuint64_t)l.H, (cuuint64_t)nb};
+        cuuint64_t strides[3] = {(cuuint64_t)in.C * 2, (cuuint64_t)in.C * 2 * l.W, (cuuint64_t)in.C * 2 * l.W * l.H};
+        cuuint32_t box[4] = {64, (cuuint32_t)l.TW, (cuuint32_t)l.TH, 1};
+        if ((rc = make_tmap(c, &l.tmA_hi, in.hi + l.in_ch_off, 4, dims, strides, box))) return rc;
+        if ((rc = make_tmap(c, &l.tmA_lo, in.hi + in.plane + l.in_ch_off, 4, dims, strides, box))) return rc;
+        cuuint64_t wd[2] = {(cuuint64_t)l.ldw, (cuuint64_t)l.cout};
+        cuuint64_t wst[1] = {(cuuint64_t)l.ldw * 2};
+        cuuint32_t wbox[2] = {64, (cuuint32_t)l.BN};
+        if ((rc = make_tmap(c, &l.tmB_hi, c->d_blob + l.off_whi, 2, wd, wst, wbox))) return rc;
+        if ((rc = make_tmap(c, &l.tmB_lo, c->d_blob + l.off_wlo, 2, wd, wst, wbox))) return rc;
+    }
+    c->finalized = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+static Dest dest_bf16(const b2t_ctx *c, int buf, int ch_off, int srcH, int srcW, int mode) {
+    Dest d;
+    memset(&d, 0, sizeof d);
+    if (buf >= 0) {
+        const ActBuf &b = c->bufs[buf];
+        d.hi = b.hi;
+        d.plane_stride = b.plane;
+        d.pix_stride_b = b.C;
+        d.ch_off_b = ch_off;
+    }
+    d.H = srcH; d.W = srcW; d.mode = mode;
+    return d;
+}
+
+static int run_conv(b2t_ctx *c, ConvLayer &l, int B, float *f32_dst, cudaStream_t st) {
+    ConvParams p;
+    memset(&p, 0, sizeof p);
+    p.B = B; p.H = l.H; p.W = l.W; p.ksize = l.k; p.cin_chunks = l.cin_pad / 64; p.Cout = l.cout;
+    p.TW = l.TW; p.TH = l.TH;
+    p.tiles_x = (l.W + l.TW - 1) / l.TW; p.tiles_y = (l.H + l.TH - 1) / l.TH;
+    p.chunks_total = l.k * l.k * p.cin_chunks;
+    p.ldp = round_up(l.cout, 32);
+    p.act = l.act; p.pool = l.pool;
+    p.scale = reinterpret_cast<const float *>(c->d_blob + l.off_scale);
+    p.bias = reinterpret_cast<const float *>(c->d_blob + l.off_bias);
+    p.partial = reinterpret_cast<float *>(c->d_ws + c->off_partial);
+    p.out = dest_bf16(c, l.out_buf, l.out_ch_off, l.H, l.W, l.out_mode);
+    p.pout = dest_bf16(c, l.pout_buf, 0, l.H / 2, l.W / 2, DEST_PLAIN);
+    if (f32_dst) {
+        p.out.f32 = f32_dst;
+        p.out.pix_stride_f = l.cout;
+        p.out.ch_off_f = 0;
+        p.out.accumulate_f = l.f32_accumulate;
+    }
+    int rc;
+    if (c->cfg.engine == B2T_ENGINE_SIMT) {
+        p.splits = 1;
+        const ActBuf &in = c->bufs[l.in_buf];
+        SimtView v;
+        v.a_hi = in.hi + l.in_ch_off; v.a_plane = in.plane; v.a_pix_stride = in.C;
+        v.w_hi = reinterpret_cast<const __nv_bfloat16 *>(c->d_blob + l.off_whi);
+        v.w_plane = (long long)(l.off_wlo - l.off_whi) / 2; v.w_ld = l.ldw;
+        if ((rc = launch_conv_simt(v, p, st))) return fail(-2, "conv_simt launch: %s", cudaGetErrorString((cudaError_t)rc));
+        if ((rc = launch_splitk_epilogue(p, st))) return fail(-2, "epilogue launch: %s", cudaGetErrorString((cudaError_t)rc));
+        c->launches += 2;
+        return 0;
+    }
+    const int tiles = B * p.tiles_x * p.tiles_y * ((l.cout + l.BN - 1) / l.BN);
+    p.splits = choose_splits(tiles, p.chunks_total, c->n_sm);
+    if (p.splits > 1 && (size_t)p.splits * B * l.H * l.W * p.ldp * 4 > c->partial_bytes)
+        return fail(-2, "internal: split-K workspace too small for conv %d", l.index);
+    if ((rc = launch_conv_umma(l.BN, l.tmA_hi, l.tmA_lo, l.tmB_hi, l.tmB_lo, p, st)))
+        return fail(-2, "conv_umma launch (conv %d): %s", l.index, cudaGetErrorString((cudaError_t)rc));
+    c->launches += 1;
+    if (p.splits > 1) {
+        if ((rc = launch_splitk_epilogue(p, st))) return fail(-2, "epilogue launch: %s", cudaGetErrorString((cudaError_t)rc));
+        c->launches += 1;
+    }
+    return 0;
+}
+
+static int run_conv1(b2t_ctx *c, const void *frames, int dtype, int B, cudaStream_t st) {
+    ConvLayer &l = c->conv[1];
+    Conv1Params p;
+    memset(&p, 0, sizeof p);
+    p.frames = frames; p.dtype = dtype; p.B = B; p.H = l.H; p.W = l.W;
+    p.w = reinterpret_cast<const float *>(c->d_blob + c->off_w1);
+    p.scale = reinterpret_cast<const float *>(c->d_blob + c->off_s1);
+    p.bias = reinterpret_cast<const float *>(c->d_blob + c->off_b1);
+    p.lut = reinterpret_cast<const float *>(c->d_blob + c->off_lut);
+    p.out = dest_bf16(c, l.out_buf, 0, l.H, l.W, DEST_PLAIN);
+    p.pout = dest_bf16(c, l.pout_buf, 0, l.H / 2, l.W / 2, DEST_PLAIN);
+    const int rc = launch_conv1(p, st);
+    if (rc) return fail(-2, "conv1 launch: %s", cudaGetErrorString((cudaError_t)rc));
+    c->launches += 1;
+    return 0;
+}
+
+static int forward_impl(b2t_ctx *c, const void *frames, int dtype, int B, float *logits_user, cudaStream_t st,
+                        cudaEvent_t *ev /* 24 events or NULL */) {
+    if (!c || !c->finalized) return fail(-1, "b2t_yolo_forward: context not finalized");
+    if (!frames) return fail(-1, "b2t_yolo_forward: null frames");
+    if (B < 1 || B > c->cfg.max_batch) return fail(-1, "batch %d outside [1, max_batch=%d]", B, c->cfg.max_batch);
+    if (dtype != B2T_FRAME_U8 && dtype != B2T_FRAME_F32) return fail(-1, "bad frame dtype %d", dtype);
+    int rc;
+    if (ev) cudaEventRecord(ev[0], st);
+    if ((rc = run_conv1(c, frames, dtype, B, st))) return rc;
+    if (ev) cudaEventRecord(ev[1], st);
+    float *logits = reinterpret_cast<float *>(c->d_ws + c->off_logits);
+    for (int i = 2; i <= 23; ++i) {
+        if ((rc = run_conv(c, c->conv[i], B, i == 23 ? logits : nullptr, st))) return rc;
+        if (ev) cudaEventRecord(ev[i], st);
+    }
+    if (logits_user && logits_user != logits)
+        CK(cudaMemcpyAsync(logits_user, logits, (size_t)B * c->G * c->G * c->A * c->D * 4, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+extern "C" int b2t_yolo_forward(b2t_ctx *c, const void *frames, int dtype, int B, float *logits_dev, void *stream) {
+    return forward_impl(c, frames, dtype, B, logits_dev, (cudaStream_t)stream, nullptr);
+}
+
+extern "C" const float *b2t_logits(const b2t_ctx *c) {
+    return (c && c->d_ws) ? reinterpret_cast<const float *>(c->d_ws + c->off_logits) : nullptr;
+}
+
+extern "C" int b2t_profile_forward(b2t_ctx *c, const void *frames, int dtype, int B, float *ms, double *bytes,
+                                   void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaEvent_t ev[24];
+    for (auto &e : ev) CK(cudaEventCreate(&e));
+    int rc = forward_impl(c, frames, dtype, B, nullptr, st, ev);
+    if (!rc) {
+        CK(cudaStreamSynchronize(st));
+        for (int i = 1; i <= 23; ++i) {
+            CK(cudaEventElapsedTime(&ms[i - 1], ev[i - 1], ev[i]));
+            if (bytes) {
+                const ConvLayer &l = c->conv[i];
+                const double px = (double)B * l.H * l.W;
+                const double w = (double)l.k * l.k * l.cin * l.cout;
+                const double in = px * l.cin, out = px * l.cout * (l.pool ? (i == 13 ? 1.25 : 0.25) : 1.0);
+                bytes[i - 1] = 4.0 * (w + out) + (i == 1 ? (dtype == B2T_FRAME_U8 ? 1.0 : 4.0) : 4.0) * in;
+            }
+        }
+    }
+    for (auto &e : ev) cudaEventDestroy(e);
+    return rc;
+}
+
+static int lookup(const b2t_ctx *c, const char *name, int *buf, int *choff, int *C) {
+    if (!c || !name) return fail(-1, "null argument");
+    auto it = c->buf_by_name.find(name);
+    if (it == c->buf_by_name.end())
+        return fail(-1, "layer '%s' is not kept by this context (pre-pool outputs need config.reserved[0]=1)", name);
+    *buf = it->second;
+    auto jt = c->choff_by_name.find(name);
+    *choff = jt == c->choff_by_name.end() ? 0 : jt->second;
+    auto kt = c->cout_by_name.find(name);
+    *C = kt == c->cout_by_name.end() ? c->bufs[*buf].C : kt->second;
+    return 0;
+}
+
+extern "C" int b2t_layer_dims(const b2t_ctx *c, const char *name, int *h, int *w, int *ch) {
+    if (name && !strcmp(name, "conv_23")) {
+        if (h) *h = c->G; if (w) *w = c->G; if (ch) *ch = c->A * c->D;
+        return 0;
+    }
+    int buf, off, C;
+    const int rc = lookup(c, name, &buf, &off, &C);
+    if (rc) return rc;
+    if (h) *h = c->bufs[buf].H;
+    if (w) *w = c->bufs[buf].W;
+    if (ch) *ch = C;
+    return 0;
+}
+
+extern "C" long b2t_extract(b2t_ctx *c, const char *name, int B, float *out, void *stream) {
+    if (!c || !c->finalized || !out) return fail(-1, "b2t_extract: bad arguments");
+    if (B < 1 || B > c->cfg.max_batch) return fail(-1, "bad batch");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!strcmp(name, "conv_23")) {
+        const size_t n = (size_t)c->G * c->G * c->A * c->D;
+        CK(cudaMemcpyAsync(out, c->d_ws + c->off_logits, n * B * 4, cudaMemcpyDeviceToDevice, st));
+        return (long)n;
+    }
+    int buf, off, C;
+    const int rc = lookup(c, name, &buf, &off, &C);
+    if (rc) return rc;
+    const ActBuf &b = c->bufs[buf];
+    const long long npix = (long long)B * b.H * b.W;
+    const int e = launch_planes_to_f32(b.hi, b.plane, b.C, off, C, npix, out, st);
+    if (e) return fail(-2, "planes_to_f32 launch: %s", cudaGetErrorString((cudaError_t)e));
+    c->launches += 1;
+    return (long)b.H * b.W * C;
+}
+
+// ------------------------------------------------------------------------------------------------ decode
+static int fill_decode(DecodeParams &p, const float *logits, int B, int gh, int gw, int nb, int nc, float t1, float t2,
+                       const float *anchors, float *boxes, int *counts, int maxb) {
+    if (!logits || !boxes || !counts || !anchors) return fail(-1, "decode: null pointer");
+    if (nb < 1 || nb > 16) return fail(-1, "decode: n_box %d outside [1,16]", nb);
+    if (gh * gw * nb > 32767) return fail(-1, "decode: more than 32767 anchors per frame");
+    if (B < 1 || nc < 1 || maxb < 1) return fail(-1, "decode: bad sizes");
+    memset(&p, 0, sizeof p);
+    p.logits = logits; p.B = B; p.GH = gh; p.GW = gw; p.A = nb; p.C = nc;
+    p.obj_thr = t1; p.nms_thr = t2;
+    for (int i = 0; i < 2 * nb; ++i) p.anchors[i] = anchors[i];
+    p.boxes = boxes; p.counts = counts; p.max_boxes = maxb;
+    return 0;
+}
+
+extern "C" int b2t_decode_nms(b2t_ctx *c, const float *logits, int B, int gh, int gw, int nb, int nc, float obj_thr,
+                              float nms_thr, const float *anchors, float *boxes, int *counts, int maxb, void *stream) {
+    DecodeParams p;
+    int rc = fill_decode(p, logits, B, gh, gw, nb, nc, obj_thr, nms_thr, anchors, boxes, counts, maxb);
+    if (rc) return rc;
+    if ((rc = launch_decode(false, p, (cudaStream_t)stream))) return fail(-2, "decode launch: %s", cudaGetErrorString((cudaError_t)rc));
+    if (c) c->launches += 1;
+    return 0;
+}
+
+extern "C" int b2t_region_detect(b2t_ctx *c, const float *logits, int B, int gh, int gw, int nb, int nc, float thresh,
+                                 float nms_thr, const float *anchors, int ow, int oh, int nw, int nh, float *dets,
+                                 int *counts, int maxd, void *stream) {
+    DecodeParams p;
+    int rc = fill_decode(p, logits, B, gh, gw, nb, nc, thresh, nms_thr, anchors, dets, counts, maxd);
+    if (rc) return rc;
+    if (ow < 1 || oh < 1 || nw < 1 || nh < 1) return fail(-1, "region_detect: bad frame size");
+    p.orig_w = ow; p.orig_h = oh; p.net_w = nw; p.net_h = nh;
+    if ((rc = launch_decode(true, p, (cudaStream_t)stream))) return fail(-2, "decode launch: %s", cudaGetErrorString((cudaError_t)rc));
+    if (c) c->launches += 1;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ LSTM head
+struct b2t_lstm {
+    b2t_ctx *ctx;
+    int n_feat, n_det, units, n_out, max_streams;
+    float *d_wp = nullptr, *d_bias = nullptr, *d_wd = nullptr, *d_bd = nullptr;
+    float *d_h[2] = {nullptr, nullptr}, *d_c = nullptr;
+    int cur = 0;
+    bool have = false;
+};
+
+extern "C" int b2t_lstm_create(b2t_ctx *ctx, int n_feat, int n_det, int units, int n_out, int max_streams, b2t_lstm **out) {
+    if (!out || n_feat < 1 || n_det < 0 || units < 4 || units % 4 || n_out < 1 || max_streams < 1)
+        return fail(-1, "b2t_lstm_create: bad arguments");
+    b2t_lstm *l = new b2t_lstm();
+    l->ctx = ctx; l->n_feat = n_feat; l->n_det = n_det; l->units = units; l->n_out = n_out; l->max_streams = max_streams;
+    const size_t rows = (size_t)n_feat + n_det + units;
+    if (cudaMalloc(&l->d_wp, rows * 4 * units * 4) || cudaMalloc(&l->d_bias, 4 * units * 4) ||
+        cudaMalloc(&l->d_wd, (size_t)units * n_out * 4) || cudaMalloc(&l->d_bd, n_out * 4) ||
+        cudaMalloc(&l->d_h[0], (size_t)max_streams * units * 4) || cudaMalloc(&l->d_h[1], (size_t)max_streams * units * 4) ||
+        cudaMalloc(&l->d_c, (size_t)max_streams * units * 4)) {
+        b2t_lstm_destroy(l);
+        return fail(-2, "b2t_lstm_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    cudaMemset(l->d_h[0], 0, (size_t)max_streams * units * 4);
+    cudaMemset(l->d_h[1], 0, (size_t)max_streams * units * 4);
+    cudaMemset(l->d_c, 0, (size_t)max_streams * units * 4);
+    *out = l;
+    return 0;
+}
+
+extern "C" void b2t_lstm_destroy(b2t_lstm *l) {
+    if (!l) return;
+    cudaFree(l->d_wp); cudaFree(l->d_bias); cudaFree(l->d_wd); cudaFree(l->d_bd);
+    cudaFree(l->d_h[0]); cudaFree(l->d_h[1]); cudaFree(l->d_c);
+    delete l;
+}
+
+extern "C" int b2t_lstm_set_weights(b2t_lstm *l, const float *kernel, const float *recurrent, const float *bias,
+                                    const float *dk, const float *db, void *stream) {
+    if (!l || !kernel || !recurrent || !bias || !dk || !db) return fail(-1, "b2t_lstm_set_weights: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int u = l->units, nx = l->n_feat + l->n_det, rows = nx + u;
+    // [units/4][rows][gate][4]: the 16 columns one CTA needs are contiguous per input row
+    std::vector<float> wp((size_t)rows * 4 * u);
+    for (int ub = 0; ub < u / 4; ++ub)
+        for (int k = 0; k < rows; ++k)
+            for (int g = 0; g < 4; ++g)
+                for (int uu = 0; uu < 4; ++uu) {
+                    const int col = g * u + ub * 4 + uu;
+                    const float v = k < nx ? kernel[(size_t)k * 4 * u + col] : recurrent[(size_t)(k - nx) * 4 * u + col];
+                    wp[(((size_t)ub * rows + k) * 4 + g) * 4 + uu] = v;
+                }
+    CK(cudaMemcpyAsync(l->d_wp, wp.data(), wp.size() * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(l->d_bias, bias, 4 * u * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(l->d_wd, dk, (size_t)u * l->n_out * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(l->d_bd, db, l->n_out * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));   // wp is a host temporary
+    l->have = true;
+    return 0;
+}
+
+extern "C" int b2t_lstm_reset(b2t_lstm *l, int s, void *stream) {
+    if (!l) return fail(-1, "null lstm");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (s >= l->max_streams) return fail(-1, "stream index %d >= max_streams %d", s, l->max_streams);
+    const size_t off = s < 0 ? 0 : (size_t)s * l->units, n = (s < 0 ? (size_t)l->max_streams : 1) * l->units;
+    CK(cudaMemsetAsync(l->d_h[0] + off, 0, n * 4, st));
+    CK(cudaMemsetAsync(l->d_h[1] + off, 0, n * 4, st));
+    CK(cudaMemsetAsync(l->d_c + off, 0, n * 4, st));
+    return 0;
+}
+
+extern "C" int b2t_lstm_step(b2t_lstm *l, const float *fv, const float *det, int S, float *y, int hard_sigmoid, void *stream) {
+    if (!l || !l->have) return fail(-1, "b2t_lstm_step: weights not set");
+    if (!fv || (!det && l->n_det) || !y) return fail(-1, "b2t_lstm_step: null pointer");
+    if (S < 1 || S > l->max_streams) return fail(-1, "n_streams %d outside [1,%d]", S, l->max_streams);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nxt = l->cur ^ 1;
+    for (int s0 = 0; s0 < S; s0 += 8) {
+        LstmParams p;
+        p.wp = l->d_wp; p.bias = l->d_bias;
+        p.fv = fv + (size_t)s0 * l->n_feat; p.det = det ? det + (size_t)s0 * l->n_det : nullptr;
+        p.h_in = l->d_h[l->cur] + (size_t)s0 * l->units; p.h_out = l->d_h[nxt] + (size_t)s0 * l->units;
+        p.c = l->d_c + (size_t)s0 * l->units;
+        p.n_feat = l->n_feat; p.n_det = l->n_det; p.units = l->units; p.S = S - s0 < 8 ? S - s0 : 8;
+        p.hard_sigmoid = hard_sigmoid;
+        const int rc = launch_lstm_gates(p, st);
+        if (rc) return fail(-2, "lstm launch: %s", cudaGetErrorString((cudaError_t)rc));
+        if (l->ctx) l->ctx->launches += 1;
+    }
+    // streams not stepped keep their state: copy them across the double buffer
+    if (S < l->max_streams)
+        CK(cudaMemcpyAsync(l->d_h[nxt] + (size_t)S * l->units, l->d_h[l->cur] + (size_t)S * l->units,
+                           (size_t)(l->max_streams - S) * l->units * 4, cudaMemcpyDeviceToDevice, st));
+    l->cur = nxt;
+    const int rc = launch_dense_sigmoid(l->d_h[l->cur], l->d_wd, l->d_bd, l->units, l->n_out, S, y, st);
+    if (rc) return fail(-2, "dense launch: %s", cudaGetErrorString((cudaError_t)rc));
+    if (l->ctx) l->ctx->launches += 1;
+    return 0;
+}
+
+extern "C" int b2t_pool_features(b2t_ctx *c, const char *name, int B, int mode, int chw_view, float *fv, void *stream) {
+    if (!c || !c->finalized || !fv) return fail(-1, "b2t_pool_features: bad arguments");
+    if (B < 1 || B > c->cfg.max_batch) return fail(-1, "bad batch");
+    int buf, off, C;
+    int rc = lookup(c, name, &buf, &off, &C);
+    if (rc) return rc;
+    const ActBuf &b = c->bufs[buf];
+    PoolParams p;
+    p.hi = b.hi; p.plane = b.plane; p.pix_stride = b.C; p.ch_off = off;
+    p.B = B; p.H = b.H; p.W = b.W; p.C = C; p.mode = mode; p.chw_view = chw_view; p.out = fv;
+    if ((rc = launch_pool_features(p, (cudaStream_t)stream))) return fail(-2, "pool launch: %s", cudaGetErrorString((cudaError_t)rc));
+    c->launches += 1;
+    return 0;
+}
+
+extern "C" int b2t_heatmap_from_box(b2t_ctx *c, const float *xywh, int n, int size, float *heat, void *stream) {
+    if (!xywh || !heat || n < 1 || size < 1) return fail(-1, "b2t_heatmap_from_box: bad arguments");
+    const int rc = launch_heatmap_from_box(xywh, n, size, heat, (cudaStream_t)stream);
+    if (rc) return fail(-2, "heatmap launch: %s", cudaGetErrorString((cudaError_t)rc));
+    if (c) c->launches += 1;
+    return 0;
+}
+
+extern "C" int b2t_box_from_heatmap(b2t_ctx *c, const float *heat, int n, int size, float thresh, int *rect, void *stream) {
+    if (!heat || !rect || n < 1 || size < 1) return fail(-1, "b2t_box_from_heatmap: bad arguments");
+    const int rc = launch_box_from_heatmap(heat, n, size, thresh, rect, (cudaStream_t)stream);
+    if (rc) return fail(-2, "heatmap launch: %s", cudaGetErrorString((cudaError_t)rc));
+    if (c) c->launches += 1;
+    return 0;
+}
+
+extern "C" int b2t_select_detection(b2t_ctx *c, const float *dets, const int *counts, int max_dets, int B,
+                                    const unsigned char *class_mask_dev, int frame_w, int frame_h, float *det_in,
+                                    int heat_size, float *heat, int *chosen, void *stream) {
+    if (!dets || !counts || B < 1 || frame_w < 1 || frame_h < 1) return fail(-1, "b2t_select_detection: bad arguments");
+    SelectParams p;
+    p.dets = dets; p.counts = counts; p.max_dets = max_dets; p.B = B; p.class_mask = class_mask_dev;
+    p.frame_w = frame_w; p.frame_h = frame_h; p.det_in = det_in; p.heat_size = heat_size; p.heat = heat; p.chosen = chosen;
+    const int rc = launch_select_detection(p, (cudaStream_t)stream);
+    if (rc) return fail(-2, "select launch: %s", cudaGetErrorString((cudaError_t)rc));
+    if (c) c->launches += 1;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ ConvLSTM
+extern "C" int b2t_convlstm_reset(b2t_ctx *c, void *stream) {
+    if (!c || !c->L_CIN || !c->finalized) return fail(-1, "convlstm not configured");
+    cudaStream_t st = (cudaStream_t)stream;
+    const ActBuf &h = c->bufs[c->buf_hrec];
+    CK(cudaMemsetAsync(h.hi, 0, (size_t)h.plane * 2 * 2, st));
+    CK(cudaMemsetAsync(c->d_ws + c->off_cstate, 0, (size_t)c->G * c->G * c->cfg.convlstm_units * 4, st));
+    return 0;
+}
+
+extern "C" int b2t_convlstm_window(b2t_ctx *c, int B, float *trk_logits, int hard_sigmoid, void *stream) {
+    if (!c || !c->L_CIN || !c->finalized) return fail(-1, "convlstm not configured");
+    if (B < 1 || B > c->cfg.max_batch || !trk_logits) return fail(-1, "b2t_convlstm_window: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int u = c->cfg.convlstm_units, M = c->G * c->G;
+    float *gates = reinterpret_cast<float *>(c->d_ws + c->off_gates);
+    int rc;
+    // input convolution for all T steps at once (does not depend on h)
+    if ((rc = run_conv(c, c->conv[c->L_CIN], B, gates, st))) return rc;
+    for (int t = 0; t < B; ++t) {
+        float *g = gates + (size_t)t * M * 4 * u;
+        if ((rc = run_conv(c, c->conv[c->L_CREC], 1, g, st))) return rc;       // += U * h_{t-1}
+        ConvLstmGateParams p;
+        memset(&p, 0, sizeof p);
+        p.g = g; p.c = reinterpret_cast<float *>(c->d_ws + c->off_cstate);
+        p.h_rec = dest_bf16(c, c->buf_hrec, 0, c->G, c->G, DEST_PLAIN);
+        p.h_seq = dest_bf16(c, c->buf_hseq, 0, c->G, c->G, DEST_PLAIN);
+        p.M = M; p.units = u; p.G = c->G; p.t = t; p.hard_sigmoid = hard_sigmoid;
+        if ((rc = launch_convlstm_gates(p, st))) return fail(-2, "gates launch: %s", cudaGetErrorString((cudaError_t)rc));
+        c->launches += 1;
+    }
+    return run_conv(c, c->conv[c->L_HEAD], B, trk_logits, st);
+}

@@ -1,0 +1,115 @@
+// Shared parameter blocks and the output "emit" routine used by every conv epilogue.
+//
+// Activation layout in HBM ("split planes"): an activation tensor is two bf16 NHWC planes, hi and lo,
+// with value = hi + lo (16 significant bits).  hi plane at `hi`, lo plane at `hi + plane_stride`.
+// A destination may be a channel slice of a wider buffer (pix_stride > C, ch_off > 0): this is how the
+// route/concat layers (KerasYOLO.py:391, MultiObjDetTracker.py:175) are written in place.
+#pragma once
+#include "ptx.cuh"
+
+namespace b2t {
+
+enum { DEST_PLAIN = 0, DEST_S2D_TF = 1, DEST_REORG_DARKNET = 2 };
+
+struct Dest {
+    __nv_bfloat16 *hi;      // bf16 hi plane base (NULL = none)
+    long long plane_stride; // elements between the hi and lo plane
+    int pix_stride_b;       // channels per pixel of the bf16 buffer
+    int ch_off_b;           // first channel of this tensor inside the bf16 buffer
+    float *f32;             // fp32 NHWC base (NULL = none)
+    int pix_stride_f;
+    int ch_off_f;
+    int accumulate_f;       // fp32 dest: add to what is there (ConvLSTM recurrent term)
+    int H, W;               // spatial dims of the SOURCE tensor the coordinates refer to
+    int mode;               // DEST_*
+};
+
+struct ConvParams {
+    int B, H, W;            // output (= input) spatial size, stride-1 'same' conv
+    int ksize;              // 1 or 3
+    int cin_chunks;         // padded Cin / 64
+    int Cout;
+    int TW, TH;             // M tile = TW x TH pixels (TW*TH = 128)
+    int tiles_x, tiles_y;
+    int splits;             // split-K factor (gridDim.z)
+    int chunks_total;       // ksize*ksize*cin_chunks
+    int ldp;                // leading dim of the fp32 partial buffer (Cout rounded up to 32)
+    int act;                // 1 = LeakyReLU(0.1), 0 = linear
+    int pool;               // 1 = also emit the 2x2/2 max-pooled tensor to `pout`
+    const float *scale;     // per-Cout multiplier (folded BN) ...
+    const float *bias;      // ... and offset (or conv bias)
+    float *partial;         // [splits][B*H*W][ldp] fp32 raw accumulators (split-K or SIMT engine)
+    Dest out;               // full-resolution destination (hi and/or f32 may be NULL)
+    Dest pout;              // pooled destination
+};
+
+__device__ __forceinline__ float leaky(float v) { return v > 0.f ? v : 0.1f * v; }
+
+// Write up to 8 consecutive channels [c, c+8) of source pixel (b,y,x).  Cout = channels of the source tensor.
+__device__ __forceinline__ void emit8(const Dest &d, int b, int y, int x, int c, int Cout, const float (&v)[8]) {
+    const int nvalid = min(8, Cout - c);
+    if (nvalid <= 0) return;
+    if (d.mode == DEST_REORG_DARKNET) {
+        // darknet/src/blas.c:9-30 reorg_cpu(forward=0) expressed as a scatter of source element (c,y,x):
+        // the CHW source is read as if shaped (C/4, 2H, 2W); see DESIGN.md section 3.
+        const int H = d.H, W = d.W;                 // source dims (26x26), dest is (4C, H/2, W/2)
+        const int Hd = H / 2, Wd = W / 2, out_c = Cout / 4;
+        for (int i = 0; i < nvalid; ++i) {
+            const int s = ((c + i) * H + y) * W + x;          // flat CHW source index
+            const int w2 = s % (2 * W), h2 = (s / (2 * W)) % (2 * H), c2 = s / (4 * W * H);
+            const int k = ((h2 & 1) * 2 + (w2 & 1)) * out_c + c2;
+            const int o = (w2 >> 1) + W * ((h2 >> 1) + H * k);  // flat index in the (C,H,W)-shaped loop space
+            const int cd = o / (Hd * Wd), yd = (o / Wd) % Hd, xd = o % Wd;
+            const long long pix = ((long long)b * Hd + yd) * Wd + xd;
+            if (d.hi) {
+                __nv_bfloat16 h, l;
+                split_bf16(v[i], h, l);
+                __nv_bfloat16 *p = d.hi + pix * d.pix_stride_b + d.ch_off_b + cd;
+                p[0] = h;
+                p[d.plane_stride] = l;
+            }
+            if (d.f32) d.f32[pix * d.pix_stride_f + d.ch_off_f + cd] = v[i];
+        }
+        return;
+    }
+    long long pix;
+    int cc = c;
+    if (d.mode == DEST_S2D_TF) {  // tf.space_to_depth(2): out[b,y/2,x/2,((y&1)*2+(x&1))*C + c]
+        pix = ((long long)b * (d.H / 2) + (y >> 1)) * (d.W / 2) + (x >> 1);
+        cc = ((y & 1) * 2 + (x & 1)) * Cout + c;
+    } else {
+        pix = ((long long)b * d.H + y) * d.W + x;
+    }
+    if (d.hi) {
+        __nv_bfloat16 *p = d.hi + pix * d.pix_stride_b + d.ch_off_b + cc;
+        __align__(16) __nv_bfloat16 h[8], l[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) split_bf16(v[i], h[i], l[i]);
+        if (nvalid == 8 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0) && ((d.plane_stride & 7) == 0)) {
+            *reinterpret_cast<uint4 *>(p) = *reinterpret_cast<const uint4 *>(h);
+            *reinterpret_cast<uint4 *>(p + d.plane_stride) = *reinterpret_cast<const uint4 *>(l);
+        } else {
+            for (int i = 0; i < nvalid; ++i) {
+                p[i] = h[i];
+                p[d.plane_stride + i] = l[i];
+            }
+        }
+    }
+    if (d.f32) {
+        float *p = d.f32 + pix * d.pix_stride_f + d.ch_off_f + cc;
+        if (nvalid == 8 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+            float4 a = make_float4(v[0], v[1], v[2], v[3]), bq = make_float4(v[4], v[5], v[6], v[7]);
+            if (d.accumulate_f) {
+                const float4 o0 = reinterpret_cast<const float4 *>(p)[0], o1 = reinterpret_cast<const float4 *>(p)[1];
+                a.x += o0.x; a.y += o0.y; a.z += o0.z; a.w += o0.w;
+                bq.x += o1.x; bq.y += o1.y; bq.z += o1.z; bq.w += o1.w;
+            }
+            reinterpret_cast<float4 *>(p)[0] = a;
+            reinterpret_cast<float4 *>(p)[1] = bq;
+        } else {
+            for (int i = 0; i < nvalid; ++i) p[i] = d.accumulate_f ? p[i] + v[i] : v[i];
+        }
+    }
+}
+
+}  // namespace b2t

@@ -1,0 +1,469 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05.mma, accumulator in TMEM), operands fed by TMA.
+//
+// Replaces, for every conv_k of the YOLOv2 graph except conv_1 (KerasYOLO.py:277-400; darknet
+// convolutional_layer.c:445-485 = im2col_cpu + gemm_nn + batchnorm + leaky): Conv2D(k in {1,3}, stride 1, 'same')
+// -> BatchNormalization (folded to scale/bias) -> LeakyReLU(0.1) -> optional MaxPooling2D(2,2), and the
+// ConvLSTM2D / 1x1-head contractions of MultiObjDetTracker.py:176-183.
+//
+//   D[pixel, cout] = sum_{tap, c} A[pixel + tap, c] * Wt[cout, tap, c]
+//
+// * M tile  = 128 pixels = a TW x TH patch of one image (TW*TH = 128); one TMA 4-D box {64 ch, TW, TH, 1} per
+//   (tap, 64-channel chunk) with the tap shift in the box coordinates: out-of-image pixels are zero-filled by
+//   the TMA unit, which IS the 'same' padding -- no im2col buffer exists anywhere.
+// * N tile  = BN output channels (64 or 128), weights K-major [Cout][tap][Cin_pad], one 2-D box {64, BN}.
+// * precision: both operands are bf16 hi/lo pairs (x = hi + lo).  Each 64-deep K chunk issues
+//   a_hi*w_hi + a_hi*w_lo + a_lo*w_hi into the same fp32 TMEM accumulator (single-pass
+//   bf16/tf32 miss the 1e-3 bbox bar, this 3-term form is 20x inside it).
+// * warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-5 = epilogue
+//   (TMEM -> registers -> scale/bias/leaky -> 2x2 max via shuffles -> hi/lo split -> 16-byte stores).
+// * split-K (gridDim.z > 1): raw fp32 accumulators go to a partial buffer, splitk_epilogue_kernel finishes
+//   in a fixed order (deterministic).
+#include "kernels.cuh"
+
+namespace b2t {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                       // bf16 elements = one 128-byte swizzle row
+constexpr int kATileBytes = kBlockM * kBlockK * 2; // 16 KB
+constexpr int kUmmaThreads = 192;
+
+template <int BN>
+struct UmmaCfg {
+    static constexpr int kBTileBytes = BN * kBlockK * 2;
+    static constexpr int kStageBytes = 2 * kATileBytes + 2 * kBTileBytes;
+    static constexpr int kStages = (BN == 128) ? 3 : 4;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * BN * 4;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kUmmaThreads, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                 const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                 const ConvParams p) {
+    using Cfg = UmmaCfg<BN>;
+    constexpr int kStages = Cfg::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *tail = smem + kStages * Cfg::kStageBytes;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(tail);
+    uint64_t *empty_bar = full_bar + kStages;
+    uint64_t *accum_bar = empty_bar + kStages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_bar + 1);
+    float *s_scale = reinterpret_cast<float *>(tail + 256);
+    float *s_bias = s_scale + BN;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // ---- tile coordinates
+    int mt = blockIdx.x;
+    const int tx = mt % p.tiles_x;  mt /= p.tiles_x;
+    const int ty = mt % p.tiles_y;
+    const int b = mt / p.tiles_y;
+    const int x0 = tx * p.TW, y0 = ty * p.TH;
+    const int n0 = blockIdx.y * BN;
+    const int per = (p.chunks_total + p.splits - 1) / p.splits;
+    const int k_begin = blockIdx.z * per;
+    const int k_end = min(p.chunks_total, k_begin + per);
+    const int n_iter = k_end - k_begin;              // host guarantees >= 1 for every z
+    const int pad = p.ksize >> 1;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA_hi);
+        tma_prefetch_desc(&tmA_lo);
+        tma_prefetch_desc(&tmB_hi);
+        tma_prefetch_desc(&tmB_lo);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(accum_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<BN>(tmem_slot);
+    if (warp >= 2) {
+        for (int i = threadIdx.x - 64; i < BN; i += 128) {
+            const int c = n0 + i;
+            s_scale[i] = (c < p.Cout) ? p.scale[c] : 0.f;
+            s_bias[i] = (c < p.Cout) ? p.bias[c] : 0.f;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int it = 0; it < n_iter; ++it) {
+                const int kc = k_begin + it;
+                const int tap = kc / p.cin_chunks, cc = kc - tap * p.cin_chunks;
+                const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t *st = smem + stage * Cfg::kStageBytes;
+                mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                tma_load_4d(&tmA_hi, &full_bar[stage], st, cc * kBlockK, x0 + kw - pad, y0 + kh - pad, b, kEvictNormal);
+                tma_load_4d(&tmA_lo, &full_bar[stage], st + kATileBytes, cc * kBlockK, x0 + kw - pad, y0 + kh - pad, b,
+                            kEvictNormal);
+                tma_load_2d(&tmB_hi, &full_bar[stage], st + 2 * kATileBytes, kc * kBlockK, n0, kEvictNormal);
+                tma_load_2d(&tmB_lo, &full_bar[stage], st + 2 * kATileBytes + Cfg::kBTileBytes, kc * kBlockK, n0,
+                            kEvictNormal);
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int it = 0; it < n_iter; ++it) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+                const uint32_t a_hi = sa, a_lo = sa + kATileBytes;
+                const uint32_t b_hi = sa + 2 * kATileBytes, b_lo = b_hi + Cfg::kBTileBytes;
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                    const uint32_t off = k * 32;  // 16 bf16 = 32 bytes inside the 128-byte swizzle row
+                    const uint64_t dah = umma_desc_sw128(a_hi + off), dal = umma_desc_sw128(a_lo + off);
+                    const uint64_t dbh = umma_desc_sw128(b_hi + off), dbl = umma_desc_sw128(b_lo + off);
+                    umma_bf16(tmem_acc, dal, dbh, idesc, (it | k) ? 1u : 0u);
+                    umma_bf16(tmem_acc, dah, dbl, idesc, 1u);
+                    umma_bf16(tmem_acc, dah, dbh, idesc, 1u);
+                }
+                umma_commit(&empty_bar[stage]);               // frees the smem slot when these MMAs retire
+                if (it == n_iter - 1) umma_commit(accum_bar); // accumulator complete
+            }
+            __syncwarp();
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+    } else {
+        // ===================== epilogue =====================
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        const int q = warp & 3;                 // TMEM lane quarter this warp may read
+        const int r = q * 32 + lane;            // accumulator row = pixel inside the tile
+        const int ly = r / p.TW, lx = r - ly * p.TW;
+        const int y = y0 + ly, x = x0 + lx;
+        const bool valid = (y < p.H) && (x < p.W);
+        const long long pix = ((long long)b * p.H + y) * p.W + x;
+        const long long mtot = (long long)p.B * p.H * p.W;
+#pragma unroll 1
+        for (int j = 0; j < BN / 32; ++j) {
+            uint32_t acc[32];
+            tmem_ld32(tmem_acc + (uint32_t(q * 32) << 16) + j * 32, acc);
+            tmem_ld_wait();
+            const int c0 = n0 + j * 32;
+            if (p.splits > 1) {
+                if (valid && c0 < p.ldp) {
+                    float4 *dst = reinterpret_cast<float4 *>(p.partial + ((long long)blockIdx.z * mtot + pix) * p.ldp + c0);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        dst[i] = make_float4(__uint_as_float(acc[4 * i]), __uint_as_float(acc[4 * i + 1]),
+                                             __uint_as_float(acc[4 * i + 2]), __uint_as_float(acc[4 * i + 3]));
+                }
+                continue;
+            }
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                float t = fmaf(__uint_as_float(acc[i]), s_scale[j * 32 + i], s_bias[j * 32 + i]);
+                v[i] = p.act ? leaky(t) : t;
+            }
+            if (valid && (p.out.hi || p.out.f32)) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const float(&v8)[8] = *reinterpret_cast<const float(*)[8]>(&v[8 * g]);
+                    emit8(p.out, b, y, x, c0 + 8 * g, p.Cout, v8);
+                }
+            }
+            if (p.pool) {  // 2x2/2 max: the four pixels sit in lanes l, l^1, l^TW, l^TW^1 (TW <= 16, tiles even-aligned)
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float m = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], 1));
+                    v[i] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, p.TW));
+                }
+                if (valid && !(lx & 1) && !(ly & 1)) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const float(&v8)[8] = *reinterpret_cast<const float(*)[8]>(&v[8 * g]);
+                        emit8(p.pout, b, y >> 1, x >> 1, c0 + 8 * g, p.Cout, v8);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<BN>(tmem_acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Finishes a split-K (or SIMT-engine) convolution: fixed-order sum of the partials, scale/bias/leaky,
+// optional 2x2 max-pool, hi/lo split, same destinations as the fused epilogue.  One thread = 8 channels
+// of one pixel (or of one 2x2 quad when pooling).
+__global__ void __launch_bounds__(256) splitk_epilogue_kernel(const ConvParams p) {
+    const int cgroups = (p.Cout + 7) / 8;
+    const int Hq = p.pool ? p.H / 2 : p.H, Wq = p.pool ? p.W / 2 : p.W;
+    const long long total = (long long)p.B * Hq * Wq * cgroups;
+    const long long mtot = (long long)p.B * p.H * p.W;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int cg = int(t % cgroups);
+        long long q = t / cgroups;
+        const int xq = int(q % Wq);  q /= Wq;
+        const int yq = int(q % Hq);
+        const int b = int(q / Hq);
+        const int c = cg * 8;
+        float s8[8], b8[8], mx[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const bool ok = c + i < p.Cout;
+            s8[i] = ok ? p.scale[c + i] : 0.f;
+            b8[i] = ok ? p.bias[c + i] : 0.f;
+            mx[i] = -INFINITY;
+        }
+        const int npix = p.pool ? 4 : 1;
+        for (int k = 0; k < npix; ++k) {
+            const int y = p.pool ? 2 * yq + (k >> 1) : yq, x = p.pool ? 2 * xq + (k & 1) : xq;
+            const long long pix = ((long long)b * p.H + y) * p.W + x;
+            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int z = 0; z < p.splits; ++z) {  // ldp is a multiple of 32 -> both float4 are in bounds
+                const float4 *src = reinterpret_cast<const float4 *>(p.partial + ((long long)z * mtot + pix) * p.ldp + c);
+                const float4 a = src[0], bq = src[1];
+                v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+                v[4] += bq.x; v[5] += bq.y; v[6] += bq.z; v[7] += bq.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float tt = fmaf(v[i], s8[i], b8[i]);
+                v[i] = p.act ? leaky(tt) : tt;
+                mx[i] = fmaxf(mx[i], v[i]);
+            }
+            if (p.out.hi || p.out.f32) emit8(p.out, b, y, x, c, p.Cout, v);
+        }
+        if (p.pool) emit8(p.pout, b, yq, xq, c, p.Cout, mx);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SIMT cross-check engine: the same contraction with fp32 FMAs on the joined (hi+lo) operands, raw result to
+// p.partial[0]; splitk_epilogue_kernel (splits = 1) finishes it.  Not a product path -- it exists so the
+// tcgen05 kernel can be validated layer by layer on the device.
+
+__global__ void __launch_bounds__(256) conv_simt_kernel(const SimtView v, const ConvParams p) {
+    __shared__ float sA[64][17];
+    __shared__ float sB[64][17];
+    const int tid = threadIdx.x;
+    const long long mtot = (long long)p.B * p.H * p.W;
+    const long long m0 = (long long)blockIdx.x * 64;
+    const int n0 = blockIdx.y * 64;
+    const int lrow = tid >> 2, lk = (tid & 3) * 4;      // loader: row, first of 4 k
+    const int ty = tid >> 4, tx = tid & 15;             // compute: 4 pixels x 4 couts
+    float acc[4][4] = {};
+    // decode the loader's pixel once
+    const long long m = m0 + lrow;
+    const bool m_ok = m < mtot;
+    int pb = 0, py = 0, px = 0;
+    if (m_ok) {
+        px = int(m % p.W);
+        py = int((m / p.W) % p.H);
+        pb = int(m / ((long long)p.W * p.H));
+    }
+    const int pad = p.ksize >> 1;
+    const int cin_pad = p.cin_chunks * 64;
+    for (int tap = 0; tap < p.ksize * p.ksize; ++tap) {
+        const int kh = tap / p.ksize, kw = tap % p.ksize;
+        const int yy = py + kh - pad, xx = px + kw - pad;
+        const bool in_ok = m_ok && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
+        const long long apix = ((long long)pb * p.H + yy) * p.W + xx;
+        for (int c0 = 0; c0 < cin_pad; c0 += 16) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float a = 0.f;
+                if (in_ok) {
+                    const __nv_bfloat16 *q = v.a_hi + apix * v.a_pix_stride + c0 + lk + i;
+                    a = join_bf16(q[0], q[v.a_plane]);
+                }
+                sA[lrow][lk + i] = a;
+                float w = 0.f;
+                if (n0 + lrow < p.Cout) {
+                    const __nv_bfloat16 *q = v.w_hi + (long long)(n0 + lrow) * v.w_ld + tap * cin_pad + c0 + lk + i;
+                    w = join_bf16(q[0], q[v.w_plane]);
+                }
+                sB[lrow][lk + i] = w;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int kk = 0; kk < 16; ++kk) {
+                float a[4], w[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { a[i] = sA[ty * 4 + i][kk]; w[i] = sB[tx * 4 + i][kk]; }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = 0; i < 4; ++i) {
+        const long long mm = m0 + ty * 4 + i;
+        if (mm >= mtot) continue;
+        for (int j = 0; j < 4; ++j) {
+            const int c = n0 + tx * 4 + j;
+            if (c < p.ldp) p.partial[mm * p.ldp + c] = acc[i][j];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv_1 (3 -> 32, 3x3) fused with the input normalisation (image/255, utils.py:150-153), BN, LeakyReLU
+// and the 2x2 max-pool.  K = 27 is no tensor-core shape and the layer is HBM-bound (0.5 MB in, 5.5 MB out
+// per frame), so this is a direct fp32 convolution: one thread = one pooled pixel x 16 output channels.
+
+__global__ void __launch_bounds__(128) conv1_direct_kernel(const Conv1Params p) {
+    __shared__ __align__(16) float sw[27 * 32];
+    __shared__ float sscale[32], sbias[32], slut[256];
+    for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) sw[i] = p.w[i];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) slut[i] = p.lut[i];
+    if (threadIdx.x < 32) { sscale[threadIdx.x] = p.scale[threadIdx.x]; sbias[threadIdx.x] = p.bias[threadIdx.x]; }
+    __syncthreads();
+    const int Hq = p.H / 2, Wq = p.W / 2;
+    const long long total = (long long)p.B * Hq * Wq * 2;
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int half = int(t & 1);
+    long long q = t >> 1;
+    const int xq = int(q % Wq);  q /= Wq;
+    const int yq = int(q % Hq);
+    const int b = int(q / Hq);
+    // 4x4x3 input patch around the 2x2 quad
+    float in[4][4][3];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int yy = 2 * yq - 1 + r;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const int xx = 2 * xq - 1 + s;
+            const bool ok = yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
+            const long long off = (((long long)b * p.H + yy) * p.W + xx) * 3;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float val = 0.f;
+                if (ok) val = p.dtype == 0 ? slut[reinterpret_cast<const uint8_t *>(p.frames)[off + c]]
+                                           : reinterpret_cast<const float *>(p.frames)[off + c];
+                in[r][s][c] = val;
+            }
+        }
+    }
+    float acc[4][16];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[k][i] = 0.f;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float4 *wr = reinterpret_cast<const float4 *>(&sw[((kh * 3 + kw) * 3 + c) * 32 + half * 16]);
+                float w[16];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 f = wr[i];
+                    w[4 * i] = f.x; w[4 * i + 1] = f.y; w[4 * i + 2] = f.z; w[4 * i + 3] = f.w;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float a = in[(k >> 1) + kh][(k & 1) + kw][c];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) acc[k][i] = fmaf(a, w[i], acc[k][i]);
+                }
+            }
+    float mx[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) mx[i] = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            acc[k][i] = leaky(fmaf(acc[k][i], sscale[half * 16 + i], sbias[half * 16 + i]));
+            mx[i] = fmaxf(mx[i], acc[k][i]);
+        }
+        if (p.out.hi || p.out.f32) {
+            const float(&lo8)[8] = *reinterpret_cast<const float(*)[8]>(&acc[k][0]);
+            const float(&hi8)[8] = *reinterpret_cast<const float(*)[8]>(&acc[k][8]);
+            emit8(p.out, b, 2 * yq + (k >> 1), 2 * xq + (k & 1), half * 16, 32, lo8);
+            emit8(p.out, b, 2 * yq + (k >> 1), 2 * xq + (k & 1), half * 16 + 8, 32, hi8);
+        }
+    }
+    const float(&m0)[8] = *reinterpret_cast<const float(*)[8]>(&mx[0]);
+    const float(&m1)[8] = *reinterpret_cast<const float(*)[8]>(&mx[8]);
+    emit8(p.pout, b, yq, xq, half * 16, 32, m0);
+    emit8(p.pout, b, yq, xq, half * 16 + 8, 32, m1);
+}
+
+// split planes -> fp32 NHWC (KerasYOLO.extract / network_extract_feat read-out)
+__global__ void planes_to_f32_kernel(const __nv_bfloat16 *hi, long long plane, int pix_stride, int ch_off, int C,
+                                     long long npix, float *out) {
+    const long long total = npix * C;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const long long pix = t / C;
+        const int c = int(t - pix * C);
+        const __nv_bfloat16 *q = hi + pix * pix_stride + ch_off + c;
+        out[t] = join_bf16(q[0], q[plane]);
+    }
+}
+
+// ---------------------------------------------------------------- host-side launchers (used by api.cu)
+int launch_conv_umma(int BN, const CUtensorMap &a_hi, const CUtensorMap &a_lo, const CUtensorMap &b_hi,
+                     const CUtensorMap &b_lo, const ConvParams &p, cudaStream_t st) {
+    dim3 grid(p.B * p.tiles_x * p.tiles_y, (p.Cout + BN - 1) / BN, p.splits);
+    if (BN == 128) {
+        conv_umma_kernel<128><<<grid, kUmmaThreads, UmmaCfg<128>::kSmemBytes, st>>>(a_hi, a_lo, b_hi, b_lo, p);
+    } else {
+        conv_umma_kernel<64><<<grid, kUmmaThreads, UmmaCfg<64>::kSmemBytes, st>>>(a_hi, a_lo, b_hi, b_lo, p);
+    }
+    return (int)cudaGetLastError();
+}
+int conv_umma_init() {
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         UmmaCfg<128>::kSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(conv_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             UmmaCfg<64>::kSmemBytes);
+    return (int)e;
+}
+int launch_splitk_epilogue(const ConvParams &p, cudaStream_t st) {
+    const int cgroups = (p.Cout + 7) / 8;
+    const long long total = (long long)p.B * (p.pool ? p.H / 2 : p.H) * (p.pool ? p.W / 2 : p.W) * cgroups;
+    const int blocks = (int)min((long long)148 * 16, (total + 255) / 256);
+    splitk_epilogue_kernel<<<blocks, 256, 0, st>>>(p);
+    return (int)cudaGetLastError();
+}
+int launch_conv_simt(const SimtView &v, const ConvParams &p, cudaStream_t st) {
+    const long long mtot = (long long)p.B * p.H * p.W;
+    dim3 grid((unsigned)((mtot + 63) / 64), (p.ldp + 63) / 64);
+    conv_simt_kernel<<<grid, 256, 0, st>>>(v, p);
+    return (int)cudaGetLastError();
+}
+int launch_conv1(const Conv1Params &p, cudaStream_t st) {
+    const long long total = (long long)p.B * (p.H / 2) * (p.W / 2) * 2;
+    conv1_direct_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(p);
+    return (int)cudaGetLastError();
+}
+int launch_planes_to_f32(const __nv_bfloat16 *hi, long long plane, int pix_stride, int ch_off, int C, long long npix,
+                         float *out, cudaStream_t st) {
+    const long long total = npix * C;
+    const int blocks = (int)min((long long)148 * 8, (total + 255) / 256);
+    planes_to_f32_kernel<<<blocks, 256, 0, st>>>(hi, plane, pix_stride, ch_off, C, npix, out);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace b2t

@@ -1,0 +1,94 @@
+// Parameter blocks and host launchers of every kernel in the library (one definition, shared by the kernels'
+// translation units and api.cu).
+#pragma once
+#include <cuda.h>
+
+#include "conv_types.cuh"
+
+namespace b2t {
+
+struct SimtView {
+    const __nv_bfloat16 *a_hi;  long long a_plane;  int a_pix_stride;   // activations (channel offset pre-applied)
+    const __nv_bfloat16 *w_hi;  long long w_plane;  int w_ld;           // weights [Cout][taps*cin_pad]
+};
+
+struct Conv1Params {
+    const void *frames;   // (B,H,W,3) uint8 or float32
+    int dtype;            // 0 = u8, 1 = f32
+    int B, H, W;
+    const float *w;       // [27][32] fp32 (tap-major: (kh*3+kw)*3 + cin)
+    const float *scale, *bias;
+    const float *lut;     // [256] = float(u / 255.0)
+    Dest out;             // full-res (optional)
+    Dest pout;            // pooled
+};
+
+struct DecodeParams {
+    const float *logits;   // (B, G, G, A, D) fp32
+    int B, GH, GW, A, C;
+    float obj_thr, nms_thr;
+    float anchors[32];
+    float *boxes;          // (B, max_boxes, 8)
+    int *counts;           // (B)
+    int max_boxes;
+    int orig_w, orig_h, net_w, net_h;   // darknet flavour only
+};
+
+struct LstmParams {
+    const float *wp;      // [units/4][n_in + units][4 gates][4 units]
+    const float *bias;    // [4*units] keras order
+    const float *fv;      // (S, n_feat)
+    const float *det;     // (S, n_det)
+    const float *h_in;    // (S, units)
+    float *h_out;         // (S, units)
+    float *c;             // (S, units) in place
+    int n_feat, n_det, units, S;
+    int hard_sigmoid;
+};
+
+struct PoolParams {
+    const __nv_bfloat16 *hi;  long long plane;  int pix_stride, ch_off;
+    int B, H, W, C;
+    int mode;       // 0 = global max -> (B,C); 1 = 4x4/4 max + flatten -> (B,(H/4)*(W/4)*C)
+    int chw_view;   // 1 = read the tensor as the reference does: CHW buffer reshaped (H,W,C) without transpose
+    float *out;
+};
+
+struct SelectParams {
+    const float *dets;  const int *counts;  int max_dets, B;
+    const unsigned char *class_mask;   // device, n_class bytes, or NULL = all classes
+    int frame_w, frame_h;
+    float *det_in;      // (B,4)
+    int heat_size;  float *heat;       // (B, size*size) or NULL
+    int *chosen;        // (B) row index or -1
+};
+
+struct ConvLstmGateParams {
+    const float *g;       // (M, 4u) pre-activations (input conv + bias + recurrent conv)
+    float *c;             // (M, u) cell state, in place
+    Dest h_rec;           // h' as split planes for the next recurrent conv
+    Dest h_seq;           // h' as split planes at this time step's slot (input of the 1x1 head)
+    int M, units, G;      // M = G*G pixels of one stream
+    int t;                // time-step slot (batch index in h_seq)
+    int hard_sigmoid;
+};
+
+int launch_conv_umma(int BN, const CUtensorMap &a_hi, const CUtensorMap &a_lo, const CUtensorMap &b_hi,
+                     const CUtensorMap &b_lo, const ConvParams &p, cudaStream_t st);
+int conv_umma_init();
+int launch_splitk_epilogue(const ConvParams &p, cudaStream_t st);
+int launch_conv_simt(const SimtView &v, const ConvParams &p, cudaStream_t st);
+int launch_conv1(const Conv1Params &p, cudaStream_t st);
+int launch_planes_to_f32(const __nv_bfloat16 *hi, long long plane, int pix_stride, int ch_off, int C, long long npix,
+                         float *out, cudaStream_t st);
+int launch_decode(bool darknet, const DecodeParams &p, cudaStream_t st);
+int launch_lstm_gates(const LstmParams &p, cudaStream_t st);
+int launch_dense_sigmoid(const float *h, const float *wd, const float *bd, int units, int n_out, int S, float *y,
+                         cudaStream_t st);
+int launch_pool_features(const PoolParams &p, cudaStream_t st);
+int launch_heatmap_from_box(const float *xywh, int n, int size, float *heat, cudaStream_t st);
+int launch_select_detection(const SelectParams &p, cudaStream_t st);
+int launch_box_from_heatmap(const float *heat, int n, int size, float thresh, int *rect, cudaStream_t st);
+int launch_convlstm_gates(const ConvLstmGateParams &p, cudaStream_t st);
+
+}  // namespace b2t

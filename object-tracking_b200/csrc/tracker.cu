@@ -1,0 +1,255 @@
+// Recurrent tracker steps.
+//
+// lstm_gates_kernel / dense_sigmoid_kernel  = TinyTracker.py:36-37 and TinyHeatmapTracker.py:43-44:
+//     LSTM(units, implementation=2) -> Dense(n_out, sigmoid), Keras-2 gate order i,f,c,o,
+//     z = [x,h]·[W;U] + b, i,f,o = hard_sigmoid(z) (or sigmoid), c' = f*c + i*tanh(z_c), h' = o*tanh(c').
+// pool_features_kernel                      = TinyTracker.py:29-33 GlobalMaxPooling2D | MaxPooling2D(4,4)+Flatten
+//                                             (optionally through the CHW-viewed-as-HWC reinterpretation of
+//                                             preprocessing.py:419).
+// heatmap kernels                           = utils.py:53-58 / :61-79.
+// convlstm_gates_kernel                     = gate maths of ConvLSTM2D (MultiObjDetTracker.py:176).
+//
+// The LSTM is a latency-bound GEMV (12.6 MB of fp32 weights, a few streams): the weights are packed at load
+// time so that the [4 gates x 4 units] columns one CTA owns are contiguous per input row (64-byte rows, fully
+// coalesced), 128 CTAs stream disjoint slabs once per step for all S streams, and the reduction order is fixed.
+#include "kernels.cuh"
+
+namespace b2t {
+
+constexpr int kUnitsPerBlock = 4;
+constexpr int kLstmThreads = 256;
+constexpr int kMaxStreams = 8;      // streams per launch group
+
+
+__device__ __forceinline__ float hard_sigmoid_f(float x) { return fminf(fmaxf(fmaf(0.2f, x, 0.5f), 0.f), 1.f); }
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void __launch_bounds__(kLstmThreads) lstm_gates_kernel(const LstmParams p) {
+    __shared__ float red[16][16][kMaxStreams];
+    const int ub = blockIdx.x;
+    const int col = threadIdx.x & 15, ks = threadIdx.x >> 4;   // 16 columns x 16 row groups
+    const int n_x = p.n_feat + p.n_det, n_rows = n_x + p.units;
+    const float *w = p.wp + (long long)ub * n_rows * 16;
+    float acc[kMaxStreams];
+#pragma unroll
+    for (int s = 0; s < kMaxStreams; ++s) acc[s] = 0.f;
+    for (int k = ks; k < n_rows; k += 16) {
+        const float wv = __ldg(w + (long long)k * 16 + col);
+#pragma unroll
+        for (int s = 0; s < kMaxStreams; ++s) {
+            if (s < p.S) {
+                float xv;
+                if (k < p.n_feat) xv = __ldg(p.fv + (long long)s * p.n_feat + k);
+                else if (k < n_x) xv = __ldg(p.det + (long long)s * p.n_det + (k - p.n_feat));
+                else xv = __ldg(p.h_in + (long long)s * p.units + (k - n_x));
+                acc[s] = fmaf(xv, wv, acc[s]);
+            }
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < kMaxStreams; ++s) red[ks][col][s] = acc[s];
+    __syncthreads();
+    // 4 units x S streams finish
+    if (threadIdx.x < kUnitsPerBlock * p.S) {
+        const int uu = threadIdx.x % kUnitsPerBlock, s = threadIdx.x / kUnitsPerBlock;
+        const int unit = ub * kUnitsPerBlock + uu;
+        float z[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            float t = 0.f;
+            for (int r = 0; r < 16; ++r) t += red[r][g * 4 + uu][s];
+            z[g] = t + p.bias[g * p.units + unit];
+        }
+        const float i = p.hard_sigmoid ? hard_sigmoid_f(z[0]) : sigmoid_f(z[0]);
+        const float f = p.hard_sigmoid ? hard_sigmoid_f(z[1]) : sigmoid_f(z[1]);
+        const float o = p.hard_sigmoid ? hard_sigmoid_f(z[3]) : sigmoid_f(z[3]);
+        const float cn = fmaf(f, p.c[(long long)s * p.units + unit], i * tanhf(z[2]));
+        p.c[(long long)s * p.units + unit] = cn;
+        p.h_out[(long long)s * p.units + unit] = o * tanhf(cn);
+    }
+}
+
+// y[s][j] = sigmoid(sum_k h[s][k] * Wd[k][j] + bd[j]); one warp per output, lanes over k
+__global__ void dense_sigmoid_kernel(const float *h, const float *wd, const float *bd, int units, int n_out, int S,
+                                     float *y) {
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (gw >= S * n_out) return;
+    const int s = gw / n_out, j = gw - s * n_out;
+    float acc = 0.f;
+    for (int k = lane; k < units; k += 32) acc = fmaf(h[(long long)s * units + k], __ldg(wd + (long long)k * n_out + j), acc);
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) y[(long long)s * n_out + j] = sigmoid_f(acc + bd[j]);
+}
+
+// ---------------------------------------------------------------- feature pooling
+
+__device__ __forceinline__ float pool_read(const PoolParams &p, int b, int h, int w, int c) {
+    int yy = h, xx = w, cc = c;
+    if (p.chw_view) {   // viewed[h][w][c] = flat_chw[(h*W + w)*C + c]
+        const int f = (h * p.W + w) * p.C + c;
+        cc = f / (p.H * p.W);
+        yy = (f / p.W) % p.H;
+        xx = f % p.W;
+    }
+    const __nv_bfloat16 *q = p.hi + (((long long)b * p.H + yy) * p.W + xx) * p.pix_stride + p.ch_off + cc;
+    return join_bf16(q[0], q[p.plane]);
+}
+
+__global__ void pool_features_kernel(const PoolParams p) {
+    const int PH = p.H / 4, PW = p.W / 4;
+    const int per = p.mode == 0 ? p.C : PH * PW * p.C;
+    const long long total = (long long)p.B * per;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int b = int(t / per), r = int(t - (long long)b * per);
+        float m = -INFINITY;
+        if (p.mode == 0) {
+            for (int h = 0; h < p.H; ++h)
+                for (int w = 0; w < p.W; ++w) m = fmaxf(m, pool_read(p, b, h, w, r));
+        } else {
+            const int c = r % p.C, pw = (r / p.C) % PW, ph = r / (p.C * PW);
+            for (int i = 0; i < 4; ++i)
+                for (int j = 0; j < 4; ++j) m = fmaxf(m, pool_read(p, b, ph * 4 + i, pw * 4 + j, c));
+        }
+        p.out[t] = m;
+    }
+}
+
+// ---------------------------------------------------------------- heat maps (utils.py:53-79)
+__device__ __forceinline__ void heatmap_fill(double x, double y, double w, double h, int size, float *heat) {
+    // python int() truncates toward zero; numpy slices wrap negative bounds once and clamp to the array
+    const int sx = (int)(x * size), sy = (int)(y * size), sh = (int)(h * size), sw = (int)(w * size);
+    auto norm = [size](int v) { int t = v < 0 ? v + size : v; return t < 0 ? 0 : (t > size ? size : t); };
+    const int y0 = norm(sy), y1 = norm(sy + sh + 1), x0 = norm(sx), x1 = norm(sx + sw + 1);
+    for (int i = threadIdx.x; i < size * size; i += blockDim.x) {
+        const int r = i / size, c = i % size;
+        heat[i] = (r >= y0 && r < y1 && c >= x0 && c < x1) ? 1.f : 0.f;
+    }
+}
+
+// utils.py:53-58 generate_heatmap_feat on (S,4) rows [x, y, w, h] = top-left corner and size, image-relative
+__global__ void heatmap_from_box_kernel(const float *xywh, int n, int size, float *heat) {
+    const int s = blockIdx.x;
+    if (s >= n) return;
+    heatmap_fill(xywh[4 * s], xywh[4 * s + 1], xywh[4 * s + 2], xywh[4 * s + 3], size,
+                 heat + (long long)s * size * size);
+}
+
+// preprocessing.py:434-456 + YOLO.py:177-180: take the highest-probability detection whose class is allowed
+// (rows are already sorted by -prob), normalise by the frame size in double like the python code, emit the
+// LSTM's bbox input [cx/w, cy/h, bw/w, bh/h] (zeros if none) and, optionally, its heat-map.
+__global__ void select_detection_kernel(const SelectParams p) {
+    const int b = blockIdx.x;
+    __shared__ int pick;
+    if (threadIdx.x == 0) {
+        pick = -1;
+        const int n = max(0, min(p.counts[b], p.max_dets));
+        for (int i = 0; i < n; ++i) {
+            const int cls = (int)p.dets[((long long)b * p.max_dets + i) * 8 + 6];
+            if (!p.class_mask || p.class_mask[cls]) { pick = i; break; }
+        }
+        if (p.chosen) p.chosen[b] = pick;
+    }
+    __syncthreads();
+    double x = 0, y = 0, w = 0, h = 0;
+    if (pick >= 0) {
+        const float *d = p.dets + ((long long)b * p.max_dets + pick) * 8;
+        x = (double)d[0] / p.frame_w;  y = (double)d[1] / p.frame_h;
+        w = (double)d[2] / p.frame_w;  h = (double)d[3] / p.frame_h;
+    }
+    if (threadIdx.x == 0 && p.det_in) {
+        float *o = p.det_in + 4 * b;
+        o[0] = (float)x; o[1] = (float)y; o[2] = (float)w; o[3] = (float)h;
+    }
+    if (p.heat) heatmap_fill(x - w / 2.0, y - h / 2.0, w, h, p.heat_size, p.heat + (long long)b * p.heat_size * p.heat_size);
+}
+
+__global__ void box_from_heatmap_kernel(const float *heat, int n, int size, float thresh, int *rect) {
+    const int s = blockIdx.x;
+    if (s >= n) return;
+    __shared__ int sm[4];
+    if (threadIdx.x == 0) { sm[0] = size; sm[1] = size; sm[2] = -1; sm[3] = -1; }
+    __syncthreads();
+    int x1 = size, y1 = size, x2 = -1, y2 = -1;
+    for (int i = threadIdx.x; i < size * size; i += blockDim.x) {
+        if (heat[(long long)s * size * size + i] >= thresh) {
+            const int r = i / size, c = i % size;
+            x1 = min(x1, c); y1 = min(y1, r); x2 = max(x2, c); y2 = max(y2, r);
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        x1 = min(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+        y1 = min(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+        x2 = max(x2, __shfl_xor_sync(0xffffffffu, x2, o));
+        y2 = max(y2, __shfl_xor_sync(0xffffffffu, y2, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&sm[0], x1); atomicMin(&sm[1], y1); atomicMax(&sm[2], x2); atomicMax(&sm[3], y2);
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) rect[4 * s + threadIdx.x] = sm[threadIdx.x];
+}
+
+// ---------------------------------------------------------------- ConvLSTM2D gates
+
+__global__ void convlstm_gates_kernel(const ConvLstmGateParams p) {
+    const int groups = p.units / 8;
+    const long long total = (long long)p.M * groups;
+    for (long long tt = blockIdx.x * (long long)blockDim.x + threadIdx.x; tt < total;
+         tt += (long long)gridDim.x * blockDim.x) {
+        const int m = int(tt / groups), u0 = int(tt - (long long)m * groups) * 8;
+        const float *g = p.g + (long long)m * 4 * p.units;
+        float h8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int u = u0 + i;
+            const float zi = g[u], zf = g[p.units + u], zc = g[2 * p.units + u], zo = g[3 * p.units + u];
+            const float ig = p.hard_sigmoid ? hard_sigmoid_f(zi) : sigmoid_f(zi);
+            const float fg = p.hard_sigmoid ? hard_sigmoid_f(zf) : sigmoid_f(zf);
+            const float og = p.hard_sigmoid ? hard_sigmoid_f(zo) : sigmoid_f(zo);
+            const float cn = fmaf(fg, p.c[(long long)m * p.units + u], ig * tanhf(zc));
+            p.c[(long long)m * p.units + u] = cn;
+            h8[i] = og * tanhf(cn);
+        }
+        const int y = m / p.G, x = m - y * p.G;
+        emit8(p.h_rec, 0, y, x, u0, p.units, h8);
+        emit8(p.h_seq, p.t, y, x, u0, p.units, h8);
+    }
+}
+
+// ---------------------------------------------------------------- launchers
+int launch_lstm_gates(const LstmParams &p, cudaStream_t st) {
+    lstm_gates_kernel<<<p.units / kUnitsPerBlock, kLstmThreads, 0, st>>>(p);
+    return (int)cudaGetLastError();
+}
+int launch_dense_sigmoid(const float *h, const float *wd, const float *bd, int units, int n_out, int S, float *y,
+                         cudaStream_t st) {
+    const long long warps = (long long)S * n_out;
+    dense_sigmoid_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(h, wd, bd, units, n_out, S, y);
+    return (int)cudaGetLastError();
+}
+int launch_pool_features(const PoolParams &p, cudaStream_t st) {
+    const int per = p.mode == 0 ? p.C : (p.H / 4) * (p.W / 4) * p.C;
+    const long long total = (long long)p.B * per;
+    pool_features_kernel<<<(unsigned)min((long long)148 * 8, (total + 127) / 128), 128, 0, st>>>(p);
+    return (int)cudaGetLastError();
+}
+int launch_heatmap_from_box(const float *xywh, int n, int size, float *heat, cudaStream_t st) {
+    heatmap_from_box_kernel<<<n, 256, 0, st>>>(xywh, n, size, heat);
+    return (int)cudaGetLastError();
+}
+int launch_select_detection(const SelectParams &p, cudaStream_t st) {
+    select_detection_kernel<<<p.B, 256, 0, st>>>(p);
+    return (int)cudaGetLastError();
+}
+int launch_box_from_heatmap(const float *heat, int n, int size, float thresh, int *rect, cudaStream_t st) {
+    box_from_heatmap_kernel<<<n, 256, 0, st>>>(heat, n, size, thresh, rect);
+    return (int)cudaGetLastError();
+}
+int launch_convlstm_gates(const ConvLstmGateParams &p, cudaStream_t st) {
+    const long long total = (long long)p.M * (p.units / 8);
+    convlstm_gates_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(p);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace b2t
