@@ -115,9 +115,11 @@ void b2t_lstm_destroy(b2t_lstm *l);
 int  b2t_lstm_set_weights(b2t_lstm *l, const float *kernel, const float *recurrent, const float *bias,
                           const float *dense_kernel, const float *dense_bias, void *stream);
 int  b2t_lstm_reset(b2t_lstm *l, int stream_index /* -1 = all */, void *stream);
-/* fv_dev (S,n_feat) fp32 pooled features, det_dev (S,n_det) fp32 -> y_dev (S,n_out) fp32; state persists */
-int  b2t_lstm_step(b2t_lstm *l, const float *fv_dev, const float *det_dev, int n_streams,
-                   float *y_dev, int hard_sigmoid, void *stream);
+/* fv_dev (S,n_feat) fp32 pooled features, det_dev (S,n_det) fp32 -> y_dev (S,n_out) fp32; state persists.
+ * *_stride = elements between consecutive streams' rows (<= 0: dense), so that time step t of S windows
+ * stored (S,T,F) can be stepped without a gather. */
+int  b2t_lstm_step(b2t_lstm *l, const float *fv_dev, int fv_stride, const float *det_dev, int det_stride,
+                   int n_streams, float *y_dev, int y_stride, int hard_sigmoid, void *stream);
 /* pooled feature of the last forward's conv layer `name` for frames [0,batch): Global -> (B,C);
  * Max -> (B,(H/4)*(W/4)*C).  chw_view=1 reproduces preprocessing.py:419 (CHW buffer viewed as HWC). */
 int  b2t_pool_features(b2t_ctx *ctx, const char *name, int batch, int pool_mode, int chw_view,

@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <cmath>
 #include <map>
 #include <string>
 #include <vector>
@@ -45,7 +46,7 @@ struct ActBuf {              // split-plane activation tensor sized for max_batc
     size_t off = 0;          // byte offset of the hi plane inside the workspace
     int H = 0, W = 0, C = 0; // C = channels per pixel (pix_stride)
     long long plane = 0;     // elements between hi and lo plane
-    __nv_bfloat16 *hi = nullptr;
+    op_t *hi = nullptr;
 };
 
 struct ConvLayer {
@@ -53,8 +54,8 @@ struct ConvLayer {
     bool act = true, pool = false;
     int H = 0, W = 0;
     int in_buf = -1, in_ch_off = 0;               // input view
-    int out_buf = -1, out_ch_off = 0, out_mode = DEST_PLAIN;   // full-res bf16 destination (-1 none)
-    int pout_buf = -1;                            // pooled bf16 destination
+    int out_buf = -1, out_ch_off = 0, out_mode = DEST_PLAIN;   // full-res split-plane destination (-1 none)
+    int pout_buf = -1;                            // pooled split-plane destination
     int f32_out = 0;                              // 1 = logits, 2 = convlstm gates, 3 = tracker logits
     int f32_accumulate = 0;
     size_t off_whi = 0, off_wlo = 0, off_scale = 0, off_bias = 0;
@@ -319,37 +320,39 @@ extern "C" int b2t_bind_memory(b2t_ctx *c, void *blob, void *ws) {
 }
 
 // ------------------------------------------------------------------------------------------------ weights
-static inline uint16_t f32_to_bf16_rn(float f) {
-    uint32_t u;
-    memcpy(&u, &f, 4);
-    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);   // NaN
-    u += 0x7fffu + ((u >> 16) & 1);
-    return (uint16_t)(u >> 16);
-}
-static inline float bf16_to_f32(uint16_t h) {
-    uint32_t u = (uint32_t)h << 16;
-    float f;
-    memcpy(&f, &u, 4);
-    return f;
-}
-
-// kernel_hwio (k,k,cin_src,cout) -> [cout][tap][cin_pad] hi/lo; perm[c_dst] = c_src or -1 (NULL = identity)
-static void pack_conv(b2t_ctx *c, const ConvLayer &l, const float *ker, int cin_src, const int *perm) {
-    uint16_t *hi = reinterpret_cast<uint16_t *>(c->host_blob.data() + l.off_whi);
-    uint16_t *lo = reinterpret_cast<uint16_t *>(c->host_blob.data() + l.off_wlo);
+// kernel_hwio (k,k,cin_src,cout) -> [cout][tap][cin_pad] hi/lo; perm[c_dst] = c_src or -1 (NULL = identity).
+// Every output channel is pre-scaled by a power of two so that its largest |w| lands in [128, 256): small
+// weights (|w| ~ 1e-2 is typical) would otherwise push the lo halves into fp16's subnormal range and lose
+// the pair's 22 bits.  unscale[co] = 2^-shift is folded (exactly) into the epilogue's per-channel scale.
+static void pack_conv(b2t_ctx *c, const ConvLayer &l, const float *ker, int cin_src, const int *perm,
+                      std::vector<float> &unscale) {
+    op_t *hi = reinterpret_cast<op_t *>(c->host_blob.data() + l.off_whi);
+    op_t *lo = reinterpret_cast<op_t *>(c->host_blob.data() + l.off_wlo);
     const int taps = l.k * l.k;
-    for (int co = 0; co < l.cout; ++co)
+    unscale.assign(l.cout, 1.f);
+    for (int co = 0; co < l.cout; ++co) {
+        float m = 0.f;
+        for (int t = 0; t < taps; ++t)
+            for (int ci = 0; ci < cin_src; ++ci) m = fmaxf(m, fabsf(ker[((size_t)t * cin_src + ci) * l.cout + co]));
+        int shift = 0;
+        if (m > 0.f && std::isfinite(m)) {
+            int e;
+            frexpf(m, &e);               // m = f * 2^e, f in [0.5, 1)
+            shift = 8 - e;               // m * 2^shift in [128, 256)
+            if (shift > 40) shift = 40;
+            if (shift < -8) shift = -8;
+        }
+        const float up = ldexpf(1.f, shift);
+        unscale[co] = ldexpf(1.f, -shift);
         for (int t = 0; t < taps; ++t)
             for (int ci = 0; ci < l.cin_pad; ++ci) {
                 const int src = perm ? perm[ci] : (ci < cin_src ? ci : -1);
                 float w = 0.f;
-                if (src >= 0) w = ker[((size_t)t * cin_src + src) * l.cout + co];
-                const uint16_t h = f32_to_bf16_rn(w);
-                const uint16_t q = f32_to_bf16_rn(w - bf16_to_f32(h));
+                if (src >= 0) w = ker[((size_t)t * cin_src + src) * l.cout + co] * up;
                 const size_t d = (size_t)co * l.ldw + (size_t)t * l.cin_pad + ci;
-                hi[d] = h;
-                lo[d] = q;
+                split_f16(w, hi[d], lo[d]);
             }
+    }
 }
 
 static void fold_bn(const b2t_ctx *c, int n, const float *gamma, const float *beta, const float *mean, const float *var,
@@ -378,7 +381,8 @@ extern "C" int b2t_set_conv_weights(b2t_ctx *c, int idx, const float *ker, const
         fold_bn(c, 32, gamma, beta, mean, var, reinterpret_cast<float *>(c->host_blob.data() + c->off_s1),
                 reinterpret_cast<float *>(c->host_blob.data() + c->off_b1));
     } else {
-        pack_conv(c, l, ker, l.cin, nullptr);
+        std::vector<float> un;
+        pack_conv(c, l, ker, l.cin, nullptr, un);
         float *s = reinterpret_cast<float *>(c->host_blob.data() + l.off_scale);
         float *b = reinterpret_cast<float *>(c->host_blob.data() + l.off_bias);
         if (bn) {
@@ -386,6 +390,7 @@ extern "C" int b2t_set_conv_weights(b2t_ctx *c, int idx, const float *ker, const
         } else {
             for (int i = 0; i < l.cout; ++i) { s[i] = 1.f; b[i] = bias[i]; }
         }
+        for (int i = 0; i < l.cout; ++i) s[i] *= un[i];          // exact: power of two
     }
     l.have_weights = true;
     return 0;
@@ -444,18 +449,19 @@ extern "C" int b2t_set_convlstm_weights(b2t_ctx *c, const float *kernel, const f
     std::vector<int> perm(a.cin_pad, -1);
     for (int i = 0; i < 1024; ++i) perm[i] = AD + i;
     for (int i = 0; i < AD; ++i) perm[1024 + i] = i;
-    pack_conv(c, a, kernel, AD + 1024, perm.data());
-    pack_conv(c, r, recurrent, u, nullptr);
-    pack_conv(c, h, head_kernel, u, nullptr);
-    auto fill = [&](ConvLayer &l, const float *b) {
+    std::vector<float> ua, ur, uh;
+    pack_conv(c, a, kernel, AD + 1024, perm.data(), ua);
+    pack_conv(c, r, recurrent, u, nullptr, ur);
+    pack_conv(c, h, head_kernel, u, nullptr, uh);
+    auto fill = [&](ConvLayer &l, const float *b, const std::vector<float> &un) {
         float *s = reinterpret_cast<float *>(c->host_blob.data() + l.off_scale);
         float *bb = reinterpret_cast<float *>(c->host_blob.data() + l.off_bias);
-        for (int i = 0; i < l.cout; ++i) { s[i] = 1.f; bb[i] = b ? b[i] : 0.f; }
+        for (int i = 0; i < l.cout; ++i) { s[i] = un[i]; bb[i] = b ? b[i] : 0.f; }
         l.have_weights = true;
     };
-    fill(a, bias);
-    fill(r, nullptr);
-    fill(h, head_bias);
+    fill(a, bias, ua);
+    fill(r, nullptr, ur);
+    fill(h, head_bias, uh);
     return 0;
 }
 
@@ -463,7 +469,7 @@ extern "C" int b2t_set_convlstm_weights(b2t_ctx *c, const float *kernel, const f
 static int make_tmap(b2t_ctx *c, CUtensorMap *tm, void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides,
                      const cuuint32_t *box) {
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
-    CUresult r = c->encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, base, dims, strides, box, es,
+    CUresult r = c->encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, base, dims, strides, box, es,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(-2, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -496,7 +502,7 @@ extern "C" int b2t_finalize(b2t_ctx *c, int upload, void *stream) {
     if (upload) CK(cudaMemcpyAsync(c->d_blob, c->host_blob.data(), c->weight_bytes, cudaMemcpyHostToDevice, st));
     // pad channels / never-written halo must be finite zeros
     CK(cudaMemsetAsync(c->d_ws, 0, c->ws_bytes, st));
-    for (auto &b : c->bufs) b.hi = reinterpret_cast<__nv_bfloat16 *>(c->d_ws + b.off);
+    for (auto &b : c->bufs) b.hi = reinterpret_cast<op_t *>(c->d_ws + b.off);
     const int MB = c->cfg.max_batch;
     for (size_t i = 2; i < c->conv.size(); ++i) {
         ConvLayer &l = c->conv[i];
@@ -519,7 +525,7 @@ extern "C" int b2t_finalize(b2t_ctx *c, int upload, void *stream) {
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-static Dest dest_bf16(const b2t_ctx *c, int buf, int ch_off, int srcH, int srcW, int mode) {
+static Dest dest_planes(const b2t_ctx *c, int buf, int ch_off, int srcH, int srcW, int mode) {
     Dest d;
     memset(&d, 0, sizeof d);
     if (buf >= 0) {
@@ -542,11 +548,12 @@ static int run_conv(b2t_ctx *c, ConvLayer &l, int B, float *f32_dst, cudaStream_
     p.chunks_total = l.k * l.k * p.cin_chunks;
     p.ldp = round_up(l.cout, 32);
     p.act = l.act; p.pool = l.pool;
+    { const char *e = getenv("B2T_NMAIN"); p.n_main = e ? atoi(e) : 3; if (p.n_main < 1) p.n_main = 1; if (p.n_main > 3) p.n_main = 3; }
     p.scale = reinterpret_cast<const float *>(c->d_blob + l.off_scale);
     p.bias = reinterpret_cast<const float *>(c->d_blob + l.off_bias);
     p.partial = reinterpret_cast<float *>(c->d_ws + c->off_partial);
-    p.out = dest_bf16(c, l.out_buf, l.out_ch_off, l.H, l.W, l.out_mode);
-    p.pout = dest_bf16(c, l.pout_buf, 0, l.H / 2, l.W / 2, DEST_PLAIN);
+    p.out = dest_planes(c, l.out_buf, l.out_ch_off, l.H, l.W, l.out_mode);
+    p.pout = dest_planes(c, l.pout_buf, 0, l.H / 2, l.W / 2, DEST_PLAIN);
     if (f32_dst) {
         p.out.f32 = f32_dst;
         p.out.pix_stride_f = l.cout;
@@ -559,7 +566,7 @@ static int run_conv(b2t_ctx *c, ConvLayer &l, int B, float *f32_dst, cudaStream_
         const ActBuf &in = c->bufs[l.in_buf];
         SimtView v;
         v.a_hi = in.hi + l.in_ch_off; v.a_plane = in.plane; v.a_pix_stride = in.C;
-        v.w_hi = reinterpret_cast<const __nv_bfloat16 *>(c->d_blob + l.off_whi);
+        v.w_hi = reinterpret_cast<const op_t *>(c->d_blob + l.off_whi);
         v.w_plane = (long long)(l.off_wlo - l.off_whi) / 2; v.w_ld = l.ldw;
         if ((rc = launch_conv_simt(v, p, st))) return fail(-2, "conv_simt launch: %s", cudaGetErrorString((cudaError_t)rc));
         if ((rc = launch_splitk_epilogue(p, st))) return fail(-2, "epilogue launch: %s", cudaGetErrorString((cudaError_t)rc));
@@ -589,8 +596,8 @@ static int run_conv1(b2t_ctx *c, const void *frames, int dtype, int B, cudaStrea
     p.scale = reinterpret_cast<const float *>(c->d_blob + c->off_s1);
     p.bias = reinterpret_cast<const float *>(c->d_blob + c->off_b1);
     p.lut = reinterpret_cast<const float *>(c->d_blob + c->off_lut);
-    p.out = dest_bf16(c, l.out_buf, 0, l.H, l.W, DEST_PLAIN);
-    p.pout = dest_bf16(c, l.pout_buf, 0, l.H / 2, l.W / 2, DEST_PLAIN);
+    p.out = dest_planes(c, l.out_buf, 0, l.H, l.W, DEST_PLAIN);
+    p.pout = dest_planes(c, l.pout_buf, 0, l.H / 2, l.W / 2, DEST_PLAIN);
     const int rc = launch_conv1(p, st);
     if (rc) return fail(-2, "conv1 launch: %s", cudaGetErrorString((cudaError_t)rc));
     c->launches += 1;
@@ -805,16 +812,21 @@ extern "C" int b2t_lstm_reset(b2t_lstm *l, int s, void *stream) {
     return 0;
 }
 
-extern "C" int b2t_lstm_step(b2t_lstm *l, const float *fv, const float *det, int S, float *y, int hard_sigmoid, void *stream) {
+extern "C" int b2t_lstm_step(b2t_lstm *l, const float *fv, int fv_stride, const float *det, int det_stride, int S,
+                             float *y, int y_stride, int hard_sigmoid, void *stream) {
     if (!l || !l->have) return fail(-1, "b2t_lstm_step: weights not set");
     if (!fv || (!det && l->n_det) || !y) return fail(-1, "b2t_lstm_step: null pointer");
     if (S < 1 || S > l->max_streams) return fail(-1, "n_streams %d outside [1,%d]", S, l->max_streams);
     cudaStream_t st = (cudaStream_t)stream;
+    if (fv_stride <= 0) fv_stride = l->n_feat;
+    if (det_stride <= 0) det_stride = l->n_det;
+    if (y_stride <= 0) y_stride = l->n_out;
     const int nxt = l->cur ^ 1;
     for (int s0 = 0; s0 < S; s0 += 8) {
         LstmParams p;
         p.wp = l->d_wp; p.bias = l->d_bias;
-        p.fv = fv + (size_t)s0 * l->n_feat; p.det = det ? det + (size_t)s0 * l->n_det : nullptr;
+        p.fv = fv + (size_t)s0 * fv_stride; p.det = det ? det + (size_t)s0 * det_stride : nullptr;
+        p.fv_stride = fv_stride; p.det_stride = det_stride;
         p.h_in = l->d_h[l->cur] + (size_t)s0 * l->units; p.h_out = l->d_h[nxt] + (size_t)s0 * l->units;
         p.c = l->d_c + (size_t)s0 * l->units;
         p.n_feat = l->n_feat; p.n_det = l->n_det; p.units = l->units; p.S = S - s0 < 8 ? S - s0 : 8;
@@ -828,7 +840,7 @@ extern "C" int b2t_lstm_step(b2t_lstm *l, const float *fv, const float *det, int
         CK(cudaMemcpyAsync(l->d_h[nxt] + (size_t)S * l->units, l->d_h[l->cur] + (size_t)S * l->units,
                            (size_t)(l->max_streams - S) * l->units * 4, cudaMemcpyDeviceToDevice, st));
     l->cur = nxt;
-    const int rc = launch_dense_sigmoid(l->d_h[l->cur], l->d_wd, l->d_bd, l->units, l->n_out, S, y, st);
+    const int rc = launch_dense_sigmoid(l->d_h[l->cur], l->d_wd, l->d_bd, l->units, l->n_out, S, y, y_stride, st);
     if (rc) return fail(-2, "dense launch: %s", cudaGetErrorString((cudaError_t)rc));
     if (l->ctx) l->ctx->launches += 1;
     return 0;
@@ -903,8 +915,8 @@ extern "C" int b2t_convlstm_window(b2t_ctx *c, int B, float *trk_logits, int har
         ConvLstmGateParams p;
         memset(&p, 0, sizeof p);
         p.g = g; p.c = reinterpret_cast<float *>(c->d_ws + c->off_cstate);
-        p.h_rec = dest_bf16(c, c->buf_hrec, 0, c->G, c->G, DEST_PLAIN);
-        p.h_seq = dest_bf16(c, c->buf_hseq, 0, c->G, c->G, DEST_PLAIN);
+        p.h_rec = dest_planes(c, c->buf_hrec, 0, c->G, c->G, DEST_PLAIN);
+        p.h_seq = dest_planes(c, c->buf_hseq, 0, c->G, c->G, DEST_PLAIN);
         p.M = M; p.units = u; p.G = c->G; p.t = t; p.hard_sigmoid = hard_sigmoid;
         if ((rc = launch_convlstm_gates(p, st))) return fail(-2, "gates launch: %s", cudaGetErrorString((cudaError_t)rc));
         c->launches += 1;

@@ -1,7 +1,7 @@
 // Shared parameter blocks and the output "emit" routine used by every conv epilogue.
 //
-// Activation layout in HBM ("split planes"): an activation tensor is two bf16 NHWC planes, hi and lo,
-// with value = hi + lo (16 significant bits).  hi plane at `hi`, lo plane at `hi + plane_stride`.
+// Activation layout in HBM ("split planes"): an activation tensor is two fp16 NHWC planes, hi and lo,
+// with value = hi + lo (22 significant bits).  hi plane at `hi`, lo plane at `hi + plane_stride`.
 // A destination may be a channel slice of a wider buffer (pix_stride > C, ch_off > 0): this is how the
 // route/concat layers (KerasYOLO.py:391, MultiObjDetTracker.py:175) are written in place.
 #pragma once
@@ -12,10 +12,10 @@ namespace b2t {
 enum { DEST_PLAIN = 0, DEST_S2D_TF = 1, DEST_REORG_DARKNET = 2 };
 
 struct Dest {
-    __nv_bfloat16 *hi;      // bf16 hi plane base (NULL = none)
+    op_t *hi;      // fp16 hi plane base (NULL = none)
     long long plane_stride; // elements between the hi and lo plane
-    int pix_stride_b;       // channels per pixel of the bf16 buffer
-    int ch_off_b;           // first channel of this tensor inside the bf16 buffer
+    int pix_stride_b;       // channels per pixel of the split-plane buffer
+    int ch_off_b;           // first channel of this tensor inside the split-plane buffer
     float *f32;             // fp32 NHWC base (NULL = none)
     int pix_stride_f;
     int ch_off_f;
@@ -36,6 +36,7 @@ struct ConvParams {
     int ldp;                // leading dim of the fp32 partial buffer (Cout rounded up to 32)
     int act;                // 1 = LeakyReLU(0.1), 0 = linear
     int pool;               // 1 = also emit the 2x2/2 max-pooled tensor to `pout`
+    int n_main;             // TMEM accumulators for the hi*hi products (1..3), + 1 for the corrections
     const float *scale;     // per-Cout multiplier (folded BN) ...
     const float *bias;      // ... and offset (or conv bias)
     float *partial;         // [splits][B*H*W][ldp] fp32 raw accumulators (split-K or SIMT engine)
@@ -62,9 +63,9 @@ __device__ __forceinline__ void emit8(const Dest &d, int b, int y, int x, int c,
             const int cd = o / (Hd * Wd), yd = (o / Wd) % Hd, xd = o % Wd;
             const long long pix = ((long long)b * Hd + yd) * Wd + xd;
             if (d.hi) {
-                __nv_bfloat16 h, l;
-                split_bf16(v[i], h, l);
-                __nv_bfloat16 *p = d.hi + pix * d.pix_stride_b + d.ch_off_b + cd;
+                op_t h, l;
+                split_f16(v[i], h, l);
+                op_t *p = d.hi + pix * d.pix_stride_b + d.ch_off_b + cd;
                 p[0] = h;
                 p[d.plane_stride] = l;
             }
@@ -81,10 +82,10 @@ __device__ __forceinline__ void emit8(const Dest &d, int b, int y, int x, int c,
         pix = ((long long)b * d.H + y) * d.W + x;
     }
     if (d.hi) {
-        __nv_bfloat16 *p = d.hi + pix * d.pix_stride_b + d.ch_off_b + cc;
-        __align__(16) __nv_bfloat16 h[8], l[8];
+        op_t *p = d.hi + pix * d.pix_stride_b + d.ch_off_b + cc;
+        __align__(16) op_t h[8], l[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) split_bf16(v[i], h[i], l[i]);
+        for (int i = 0; i < 8; ++i) split_f16(v[i], h[i], l[i]);
         if (nvalid == 8 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0) && ((d.plane_stride & 7) == 0)) {
             *reinterpret_cast<uint4 *>(p) = *reinterpret_cast<const uint4 *>(h);
             *reinterpret_cast<uint4 *>(p + d.plane_stride) = *reinterpret_cast<const uint4 *>(l);

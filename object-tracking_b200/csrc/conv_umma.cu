@@ -11,9 +11,9 @@
 //   (tap, 64-channel chunk) with the tap shift in the box coordinates: out-of-image pixels are zero-filled by
 //   the TMA unit, which IS the 'same' padding -- no im2col buffer exists anywhere.
 // * N tile  = BN output channels (64 or 128), weights K-major [Cout][tap][Cin_pad], one 2-D box {64, BN}.
-// * precision: both operands are bf16 hi/lo pairs (x = hi + lo).  Each 64-deep K chunk issues
+// * precision: both operands are fp16 hi/lo pairs (x = hi + lo).  Each 64-deep K chunk issues
 //   a_hi*w_hi + a_hi*w_lo + a_lo*w_hi into the same fp32 TMEM accumulator (single-pass
-//   bf16/tf32 miss the 1e-3 bbox bar, this 3-term form is 20x inside it).
+//   bf16/tf32 miss the 1e-3 bbox bar; the 3-term form on fp16 pairs carries ~22 bits per operand).
 // * warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-5 = epilogue
 //   (TMEM -> registers -> scale/bias/leaky -> 2x2 max via shuffles -> hi/lo split -> 16-byte stores).
 // * split-K (gridDim.z > 1): raw fp32 accumulators go to a partial buffer, splitk_epilogue_kernel finishes
@@ -23,7 +23,7 @@
 namespace b2t {
 
 constexpr int kBlockM = 128;
-constexpr int kBlockK = 64;                       // bf16 elements = one 128-byte swizzle row
+constexpr int kBlockK = 64;                       // fp16 elements = one 128-byte swizzle row
 constexpr int kATileBytes = kBlockM * kBlockK * 2; // 16 KB
 constexpr int kUmmaThreads = 192;
 
@@ -65,6 +65,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const int k_begin = blockIdx.z * per;
     const int k_end = min(p.chunks_total, k_begin + per);
     const int n_iter = k_end - k_begin;              // host guarantees >= 1 for every z
+    // TMEM accumulators (BN fp32 columns each): n_main for the hi*hi products, used round-robin over the K
+    // chunks, and one for the small hi*lo + lo*hi corrections.  The tensor core truncates every addend to the
+    // accumulator's exponent, so short accumulation chains and magnitude-matched accumulators keep the
+    // result at fp32 quality; the epilogue adds them up in fp32 round-to-nearest.
+    const int n_main = min(p.n_main, n_iter);
     const int pad = p.ksize >> 1;
 
     if (warp == 0 && lane == 0) {
@@ -79,7 +84,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         mbar_init(accum_bar, 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc<BN>(tmem_slot);
+    if (warp == 1) tmem_alloc<4 * BN>(tmem_slot);
     if (warp >= 2) {
         for (int i = threadIdx.x - 64; i < BN; i += 128) {
             const int c = n0 + i;
@@ -115,7 +120,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN);
+        constexpr uint32_t idesc = umma_idesc_f16(kBlockM, BN);
         int stage = 0;
         uint32_t phase = 0;
         for (int it = 0; it < n_iter; ++it) {
@@ -127,12 +132,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 const uint32_t b_hi = sa + 2 * kATileBytes, b_lo = b_hi + Cfg::kBTileBytes;
 #pragma unroll
                 for (int k = 0; k < kBlockK / 16; ++k) {
-                    const uint32_t off = k * 32;  // 16 bf16 = 32 bytes inside the 128-byte swizzle row
+                    const uint32_t off = k * 32;  // 16 fp16 = 32 bytes inside the 128-byte swizzle row
                     const uint64_t dah = umma_desc_sw128(a_hi + off), dal = umma_desc_sw128(a_lo + off);
                     const uint64_t dbh = umma_desc_sw128(b_hi + off), dbl = umma_desc_sw128(b_lo + off);
-                    umma_bf16(tmem_acc, dal, dbh, idesc, (it | k) ? 1u : 0u);
-                    umma_bf16(tmem_acc, dah, dbl, idesc, 1u);
-                    umma_bf16(tmem_acc, dah, dbh, idesc, 1u);
+                    const uint32_t t_main = tmem_acc + (it % n_main) * BN, t_corr = tmem_acc + n_main * BN;
+                    umma_f16(t_corr, dal, dbh, idesc, (it | k) ? 1u : 0u);
+                    umma_f16(t_corr, dah, dbl, idesc, 1u);
+                    umma_f16(t_main, dah, dbh, idesc, (it >= n_main || k) ? 1u : 0u);
                 }
                 umma_commit(&empty_bar[stage]);               // frees the smem slot when these MMAs retire
                 if (it == n_iter - 1) umma_commit(accum_bar); // accumulator complete
@@ -156,6 +162,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             uint32_t acc[32];
             tmem_ld32(tmem_acc + (uint32_t(q * 32) << 16) + j * 32, acc);
             tmem_ld_wait();
+            for (int a = 1; a <= n_main; ++a) {          // remaining main accumulators, then the corrections
+                uint32_t more[32];
+                tmem_ld32(tmem_acc + (uint32_t(q * 32) << 16) + a * BN + j * 32, more);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) acc[i] = __float_as_uint(__uint_as_float(acc[i]) + __uint_as_float(more[i]));
+            }
             const int c0 = n0 + j * 32;
             if (p.splits > 1) {
                 if (valid && c0 < p.ldp) {
@@ -198,7 +211,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc<BN>(tmem_acc);
+    if (warp == 1) tmem_dealloc<4 * BN>(tmem_acc);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -285,14 +298,14 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const SimtView v, const 
             for (int i = 0; i < 4; ++i) {
                 float a = 0.f;
                 if (in_ok) {
-                    const __nv_bfloat16 *q = v.a_hi + apix * v.a_pix_stride + c0 + lk + i;
-                    a = join_bf16(q[0], q[v.a_plane]);
+                    const op_t *q = v.a_hi + apix * v.a_pix_stride + c0 + lk + i;
+                    a = join_f16(q[0], q[v.a_plane]);
                 }
                 sA[lrow][lk + i] = a;
                 float w = 0.f;
                 if (n0 + lrow < p.Cout) {
-                    const __nv_bfloat16 *q = v.w_hi + (long long)(n0 + lrow) * v.w_ld + tap * cin_pad + c0 + lk + i;
-                    w = join_bf16(q[0], q[v.w_plane]);
+                    const op_t *q = v.w_hi + (long long)(n0 + lrow) * v.w_ld + tap * cin_pad + c0 + lk + i;
+                    w = join_f16(q[0], q[v.w_plane]);
                 }
                 sB[lrow][lk + i] = w;
             }
@@ -409,15 +422,15 @@ __global__ void __launch_bounds__(128) conv1_direct_kernel(const Conv1Params p) 
 }
 
 // split planes -> fp32 NHWC (KerasYOLO.extract / network_extract_feat read-out)
-__global__ void planes_to_f32_kernel(const __nv_bfloat16 *hi, long long plane, int pix_stride, int ch_off, int C,
+__global__ void planes_to_f32_kernel(const op_t *hi, long long plane, int pix_stride, int ch_off, int C,
                                      long long npix, float *out) {
     const long long total = npix * C;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
          t += (long long)gridDim.x * blockDim.x) {
         const long long pix = t / C;
         const int c = int(t - pix * C);
-        const __nv_bfloat16 *q = hi + pix * pix_stride + ch_off + c;
-        out[t] = join_bf16(q[0], q[plane]);
+        const op_t *q = hi + pix * pix_stride + ch_off + c;
+        out[t] = join_f16(q[0], q[plane]);
     }
 }
 
@@ -458,7 +471,7 @@ int launch_conv1(const Conv1Params &p, cudaStream_t st) {
     conv1_direct_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(p);
     return (int)cudaGetLastError();
 }
-int launch_planes_to_f32(const __nv_bfloat16 *hi, long long plane, int pix_stride, int ch_off, int C, long long npix,
+int launch_planes_to_f32(const op_t *hi, long long plane, int pix_stride, int ch_off, int C, long long npix,
                          float *out, cudaStream_t st) {
     const long long total = npix * C;
     const int blocks = (int)min((long long)148 * 8, (total + 255) / 256);

@@ -8,8 +8,8 @@
 namespace b2t {
 
 struct SimtView {
-    const __nv_bfloat16 *a_hi;  long long a_plane;  int a_pix_stride;   // activations (channel offset pre-applied)
-    const __nv_bfloat16 *w_hi;  long long w_plane;  int w_ld;           // weights [Cout][taps*cin_pad]
+    const op_t *a_hi;  long long a_plane;  int a_pix_stride;   // activations (channel offset pre-applied)
+    const op_t *w_hi;  long long w_plane;  int w_ld;           // weights [Cout][taps*cin_pad]
 };
 
 struct Conv1Params {
@@ -43,11 +43,12 @@ struct LstmParams {
     float *h_out;         // (S, units)
     float *c;             // (S, units) in place
     int n_feat, n_det, units, S;
+    int fv_stride, det_stride;   // elements between consecutive streams' rows
     int hard_sigmoid;
 };
 
 struct PoolParams {
-    const __nv_bfloat16 *hi;  long long plane;  int pix_stride, ch_off;
+    const op_t *hi;  long long plane;  int pix_stride, ch_off;
     int B, H, W, C;
     int mode;       // 0 = global max -> (B,C); 1 = 4x4/4 max + flatten -> (B,(H/4)*(W/4)*C)
     int chw_view;   // 1 = read the tensor as the reference does: CHW buffer reshaped (H,W,C) without transpose
@@ -79,12 +80,12 @@ int conv_umma_init();
 int launch_splitk_epilogue(const ConvParams &p, cudaStream_t st);
 int launch_conv_simt(const SimtView &v, const ConvParams &p, cudaStream_t st);
 int launch_conv1(const Conv1Params &p, cudaStream_t st);
-int launch_planes_to_f32(const __nv_bfloat16 *hi, long long plane, int pix_stride, int ch_off, int C, long long npix,
+int launch_planes_to_f32(const op_t *hi, long long plane, int pix_stride, int ch_off, int C, long long npix,
                          float *out, cudaStream_t st);
 int launch_decode(bool darknet, const DecodeParams &p, cudaStream_t st);
 int launch_lstm_gates(const LstmParams &p, cudaStream_t st);
 int launch_dense_sigmoid(const float *h, const float *wd, const float *bd, int units, int n_out, int S, float *y,
-                         cudaStream_t st);
+                         int y_stride, cudaStream_t st);
 int launch_pool_features(const PoolParams &p, cudaStream_t st);
 int launch_heatmap_from_box(const float *xywh, int n, int size, float *heat, cudaStream_t st);
 int launch_select_detection(const SelectParams &p, cudaStream_t st);

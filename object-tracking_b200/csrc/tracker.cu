@@ -39,8 +39,8 @@ __global__ void __launch_bounds__(kLstmThreads) lstm_gates_kernel(const LstmPara
         for (int s = 0; s < kMaxStreams; ++s) {
             if (s < p.S) {
                 float xv;
-                if (k < p.n_feat) xv = __ldg(p.fv + (long long)s * p.n_feat + k);
-                else if (k < n_x) xv = __ldg(p.det + (long long)s * p.n_det + (k - p.n_feat));
+                if (k < p.n_feat) xv = __ldg(p.fv + (long long)s * p.fv_stride + k);
+                else if (k < n_x) xv = __ldg(p.det + (long long)s * p.det_stride + (k - p.n_feat));
                 else xv = __ldg(p.h_in + (long long)s * p.units + (k - n_x));
                 acc[s] = fmaf(xv, wv, acc[s]);
             }
@@ -71,14 +71,14 @@ __global__ void __launch_bounds__(kLstmThreads) lstm_gates_kernel(const LstmPara
 
 // y[s][j] = sigmoid(sum_k h[s][k] * Wd[k][j] + bd[j]); one warp per output, lanes over k
 __global__ void dense_sigmoid_kernel(const float *h, const float *wd, const float *bd, int units, int n_out, int S,
-                                     float *y) {
+                                     float *y, int y_stride) {
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (gw >= S * n_out) return;
     const int s = gw / n_out, j = gw - s * n_out;
     float acc = 0.f;
     for (int k = lane; k < units; k += 32) acc = fmaf(h[(long long)s * units + k], __ldg(wd + (long long)k * n_out + j), acc);
     for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) y[(long long)s * n_out + j] = sigmoid_f(acc + bd[j]);
+    if (lane == 0) y[(long long)s * y_stride + j] = sigmoid_f(acc + bd[j]);
 }
 
 // ---------------------------------------------------------------- feature pooling
@@ -91,8 +91,8 @@ __device__ __forceinline__ float pool_read(const PoolParams &p, int b, int h, in
         yy = (f / p.W) % p.H;
         xx = f % p.W;
     }
-    const __nv_bfloat16 *q = p.hi + (((long long)b * p.H + yy) * p.W + xx) * p.pix_stride + p.ch_off + cc;
-    return join_bf16(q[0], q[p.plane]);
+    const op_t *q = p.hi + (((long long)b * p.H + yy) * p.W + xx) * p.pix_stride + p.ch_off + cc;
+    return join_f16(q[0], q[p.plane]);
 }
 
 __global__ void pool_features_kernel(const PoolParams p) {
@@ -223,9 +223,9 @@ int launch_lstm_gates(const LstmParams &p, cudaStream_t st) {
     return (int)cudaGetLastError();
 }
 int launch_dense_sigmoid(const float *h, const float *wd, const float *bd, int units, int n_out, int S, float *y,
-                         cudaStream_t st) {
+                         int y_stride, cudaStream_t st) {
     const long long warps = (long long)S * n_out;
-    dense_sigmoid_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(h, wd, bd, units, n_out, S, y);
+    dense_sigmoid_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(h, wd, bd, units, n_out, S, y, y_stride);
     return (int)cudaGetLastError();
 }
 int launch_pool_features(const PoolParams &p, cudaStream_t st) {

@@ -65,6 +65,8 @@ class DetectorEngine:
         self.finalized = False
         self._anchors = (C.c_float * (2 * N_BOX))(*ANCHORS)
         self._scratch: Dict[Tuple, torch.Tensor] = {}
+        self._logits_view = None
+        self.forward_events = None
 
     def __del__(self):
         try:
@@ -119,17 +121,24 @@ class DetectorEngine:
         if dt is None:
             raise ValueError("frames must be uint8 or float32")
         B = frames.shape[0]
+        ev = self.forward_events
+        if ev is not None:                      # bench.py: device time of the conv stack, per call
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
         N.check(self.lib.b2t_yolo_forward(self.h, frames.data_ptr(), dt, B, None, _stream()))
+        if ev is not None:
+            b.record()
+            ev.append((a, b))
         return self.logits(B)
 
     def logits(self, B: int) -> torch.Tensor:
-        n = self.grid * self.grid * self.n_box * (5 + self.n_class)
-        out = self._buf(("logits", B), (B, self.grid, self.grid, self.n_box, 5 + self.n_class), torch.float32)
-        N.check(self.lib.b2t_extract(self.h, b"conv_23", B, out.data_ptr(), _stream()))
-        return out
-
-    def logits_ptr(self) -> int:
-        return self.lib.b2t_logits(self.h)
+        """Zero-copy view of the context's logits buffer (it lives inside the torch-owned workspace)."""
+        if self._logits_view is None:
+            off = self.lib.b2t_logits(self.h) - self.workspace.data_ptr()
+            n = self.max_batch * self.grid * self.grid * self.n_box * (5 + self.n_class)
+            self._logits_view = self.workspace[off:off + 4 * n].view(torch.float32).view(
+                self.max_batch, self.grid, self.grid, self.n_box, 5 + self.n_class)
+        return self._logits_view[:B]
 
     def _buf(self, key, shape, dtype) -> torch.Tensor:
         t = self._scratch.get(key)
@@ -257,9 +266,14 @@ class LstmHead:
     def reset(self, stream_index: int = -1) -> None:
         N.check(self.lib.b2t_lstm_reset(self.h, stream_index, _stream()))
 
-    def step(self, fv: torch.Tensor, det: torch.Tensor, hard_sigmoid: bool = True) -> torch.Tensor:
+    def step(self, fv: torch.Tensor, det: torch.Tensor, hard_sigmoid: bool = True,
+             out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """fv (S,n_feat), det (S,n_det): rows may be strided views (e.g. x[:, t] of an (S,T,F) tensor)."""
         S = fv.shape[0]
-        y = torch.empty((S, self.n_out), dtype=torch.float32, device=fv.device)
-        N.check(self.lib.b2t_lstm_step(self.h, fv.data_ptr(), det.data_ptr(), S, y.data_ptr(),
+        if fv.stride(-1) != 1 or det.stride(-1) != 1:
+            raise ValueError("feature rows must be contiguous")
+        y = out if out is not None else torch.empty((S, self.n_out), dtype=torch.float32, device=fv.device)
+        N.check(self.lib.b2t_lstm_step(self.h, fv.data_ptr(), fv.stride(0) if S > 1 else 0, det.data_ptr(),
+                                       det.stride(0) if S > 1 else 0, S, y.data_ptr(), y.stride(0) if S > 1 else 0,
                                        1 if hard_sigmoid else 0, _stream()))
         return y

@@ -1,0 +1,109 @@
+"""Drop-in for the inference-relevant half of ``models_tracking/BaseTracker.py`` (:12-60) plus the per-frame
+``step()/reset()`` the reference lacks: the dataflow of
+``BatchSequenceGenerator2.output_from_instance`` (utility/preprocessing.py:403-477) -- detect, take the
+highest-probability detection of an allowed class, normalise it by the frame size, pool the fv_layer
+feature, feed the recurrent head -- without the JPEG round-trip through disk (:412-415).
+
+Everything numeric runs on the GPU: detector forward, region decode + NMS, detection choice, feature
+pooling, LSTM cell, Dense head.  ``train()`` is out of scope.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from ..models_detection.YOLO import YOLO
+from ..models_detection._common import load_config
+
+
+class BaseTracker(object):
+    def __init__(self, config=None, max_streams: int = 1, detector_kwargs: Optional[dict] = None,
+                 ref_layout_bug: bool = False):
+        self.config = load_config(config)
+        self.detection_model = self.config["model_detector"]["name"]
+        self.detection_fv_layer = self.config["model_detector"]["fv_layer"]
+        self.cpu_mode = self.config["train"]["cpu_only"]
+        self.tgpu_id = self.config["train"]["tgpu_id"]
+        self.dgpu_id = self.config["train"]["dgpu_id"]
+        self.pool = self.config["train"]["pool"]
+        self.batch_size = self.config["train"]["batch_size"]
+        self.max_epochs = self.config["train"]["max_epochs"]
+        self.sequence_length = self.config["model_tracker"]["sequence_length"]
+        self.classes = self.config["train"]["classes"]
+        self.model_name = self.config["model_tracker"]["name"]
+        self.tensorboard_dir = self.config["train"]["tensorboard_dir"]
+        self.saved_model_path = self.config["train"]["saved_model_dir"] + self.model_name
+        self.max_streams = max_streams
+        self.ref_layout_bug = ref_layout_bug          # preprocessing.py:419 CHW-as-HWC reinterpretation (R11)
+        self._detector_kwargs = dict(detector_kwargs or {})
+        self.load_detection_model()
+
+    def load_detection_model(self):
+        if self.detection_model != 'YOLO':
+            raise NotImplementedError("only the YOLO detector plugin is built (FasterRCNN: SURVEY.md 8f rank 4)")
+        kw = dict(self._detector_kwargs)
+        kw.setdefault("max_batch", self.max_streams * self.sequence_length)
+        self.model_detector = YOLO([self.cpu_mode, self.dgpu_id], config=self.config, **kw)
+        self._w, self._h, self._c = self.model_detector.get_layer_dims(self.detection_fv_layer)
+        self._fv_name = self.model_detector._name(self.detection_fv_layer)
+
+    def load_tracker_model(self):
+        raise NotImplementedError
+
+    def load_data_generators(self):
+        raise NotImplementedError("training data generators are out of scope of the B200 hot path")
+
+    def train(self):
+        raise NotImplementedError("training is out of scope of the B200 hot path (SURVEY.md section 2.1)")
+
+    # ------------------------------------------------------------------ feature size of the pooled fv
+    def _n_feat(self) -> int:
+        if self.pool == 'Global':
+            return self._c
+        if self.pool == 'Max':
+            return (self._w // 4) * (self._h // 4) * self._c
+        raise ValueError(f"unknown pool '{self.pool}'")
+
+    # ------------------------------------------------------------------ new per-frame API
+    def reset(self, stream: int = -1):
+        self.head.reset(stream)
+        self._steps = 0
+
+    def _detect_and_pool(self, frames: torch.Tensor, heat_size: int = 0):
+        det = self.model_detector
+        B, H, W = frames.shape[0], frames.shape[1], frames.shape[2]
+        dets, counts = det.detect_batch(frames, W, H)
+        det_in, heat, chosen = det.engine.select_detection(dets, counts, W, H, det.class_mask, heat_size)
+        fv = det.engine.pool_features(self._fv_name, B, self.pool, self.ref_layout_bug)
+        return fv, det_in, heat, chosen
+
+    def track_windows(self, frames: torch.Tensor, reset: bool = True) -> torch.Tensor:
+        """frames (S,T,H,W,3) uint8 on the GPU: S independent streams (or windows), T consecutive frames each.
+        One batched detector pass over S*T frames, then T recurrent steps over the S streams in parallel.
+        reset=True reproduces Keras' stateless windows (state zeroed at the start of every window)."""
+        S, T = frames.shape[0], frames.shape[1]
+        if S > self.max_streams:
+            raise ValueError(f"{S} streams > max_streams {self.max_streams}")
+        fv, xin = self._tracker_inputs(frames.reshape(S * T, *frames.shape[2:]))
+        fv, xin = fv.view(S, T, -1), xin.view(S, T, -1)
+        out = torch.empty((S, T, self.n_out), dtype=torch.float32, device=frames.device)
+        if reset:
+            self.head.reset(-1)
+        for t in range(T):
+            self.head.step(fv[:, t], xin[:, t], out=out[:, t])
+        return out
+
+    def step(self, frame, stream: int = 0) -> np.ndarray:
+        """One frame of one stream (online use).  frame: HWC uint8 array or GPU tensor.  State persists;
+        it is reset every ``sequence_length`` steps like the reference's stateless 4-frame windows."""
+        if self.max_streams != 1 and stream != 0:
+            raise NotImplementedError("per-stream online stepping uses one tracker object per stream")
+        t = torch.as_tensor(np.ascontiguousarray(frame) if isinstance(frame, np.ndarray) else frame)
+        t = t.to(self.model_detector.engine.device)
+        if getattr(self, "_steps", 0) % self.sequence_length == 0:
+            self.head.reset(-1)
+        self._steps = getattr(self, "_steps", 0) + 1
+        fv, xin = self._tracker_inputs(t[None].contiguous())
+        return self.head.step(fv, xin)[0].cpu().numpy()

@@ -62,6 +62,38 @@ def n_params(n_class: int = 80) -> int:
     return n
 
 
+def traffic_model(n_class: int = 80, image_size: int = 416) -> Dict[str, float]:
+    """Algorithmic element counts of one forward pass in fused-minimum form:
+    W = conv weights + conv_23 bias, R = activation elements read (each conv input once, conv_1's input
+    as stored), Wr = activation elements written (pooled where a pool follows; conv_13 both full and
+    pooled; the concat written in place), flops = 2*MACs."""
+    h = image_size
+    w_el = r_el = wr_el = 0
+    flops = 0.0
+    for s in yolo_layer_table(n_class):
+        if s.src == "skip":
+            hh = image_size // 16
+        elif s.src == "concat" or s.index == 23:
+            hh = image_size // 32
+        else:
+            hh = h
+        px = hh * hh
+        w_el += s.ksize * s.ksize * s.cin * s.cout + (0 if s.bn else s.cout)
+        r_el += px * s.cin
+        out = px * s.cout
+        wr_el += (out // 4 if s.pool else out) + (out if s.index == 13 else 0)
+        flops += 2.0 * px * s.ksize * s.ksize * s.cin * s.cout
+        if s.pool and s.src == "prev":
+            h //= 2
+    return {"W": w_el, "R": r_el, "Wr": wr_el, "flops": flops}
+
+
+def forward_bytes(n_class: int = 80, image_size: int = 416, batch: int = 1, elem_bytes: int = 4) -> float:
+    """Algorithmic HBM bytes PER FRAME at `batch` frames per weight pass: s*(W/B + R + Wr)."""
+    t = traffic_model(n_class, image_size)
+    return elem_bytes * (t["W"] / batch + t["R"] + t["Wr"])
+
+
 # --------------------------------------------------------------------------------------
 # synthetic weights
 # --------------------------------------------------------------------------------------

@@ -1,0 +1,247 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path through the C-ABI against the CPU oracle
+and the committed golden vectors.  Tolerances: discrete outputs (keep-set, labels, order, anchor ids)
+bit-exact; box coordinates 1e-3 (north_star) -- asserted much tighter where the arithmetic allows."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import darknet_oracle, decode_oracle, tracker_oracle, yolo_oracle
+from oracle.cases import DECODE_KINDS, DECODE_SPECS, decode_case
+from object_tracking_b200 import weights as W
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _engine(**kw):
+    from object_tracking_b200.engine import DetectorEngine
+    return DetectorEngine(**kw)
+
+
+@pytest.fixture(scope="module")
+def keras_c2():
+    z = np.load(os.path.join(GOLD, "keras_416_c2.npz"))
+    w = W.synthetic_yolo_weights(2, seed=int(z["weight_seed"]))
+    frames = np.random.default_rng(int(z["frame_seed"])).integers(0, 256, (2, 416, 416, 3), dtype=np.uint8)
+    e = _engine(n_class=2, max_batch=2, keep_prepool=True)
+    e.set_weights(w)
+    e.finalize()
+    return z, w, frames, e
+
+
+def test_forward_matches_golden_logits(keras_c2):
+    z, w, frames, e = keras_c2
+    lg = e.forward(torch.from_numpy(frames).cuda()).cpu().numpy()
+    assert lg.shape == z["logits"].shape
+    err = np.abs(lg - z["logits"]).max()
+    assert err < 5e-4, err                                  # fp64 oracle, logits up to |14|
+    fmax = e.pool_features("conv_feat", 2, "Global").cpu().numpy()
+    assert np.abs(fmax - z["feat_globalmax"]).max() < 2e-3
+    feat = e.extract("conv_feat", 2).cpu().numpy()
+    assert np.abs(feat[..., ::32] - z["feat_sub"]).max() < 2e-3
+
+
+def test_every_layer_against_fp64_oracle(keras_c2):
+    z, w, frames, e = keras_c2
+    names = [f"norm_{i}" for i in range(1, 21)] + ["concat"]
+    o = yolo_oracle.yolo_forward(yolo_oracle.normalize(frames), w, 2, dtype=np.float64, want=names)
+    e.forward(torch.from_numpy(frames).cuda())
+    for n in names:
+        got = e.extract(n, 2).cpu().numpy()
+        ref = o[n]
+        assert got.shape == ref.shape, n
+        rel = np.abs(got - ref).max() / np.abs(ref).max()
+        assert rel < 2e-5, (n, rel)
+
+
+def test_batch_one_and_float_frames_agree(keras_c2):
+    z, w, frames, e = keras_c2
+    a = e.forward(torch.from_numpy(frames).cuda()).clone()
+    b = e.forward(torch.from_numpy(frames[:1]).cuda()).clone()         # different split-K plan, same numbers
+    assert (a[0] - b[0]).abs().max().item() < 1e-4
+    xf = torch.from_numpy(yolo_oracle.normalize(frames).astype(np.float32)).cuda()
+    c = e.forward(xf)
+    assert torch.equal(a, c)                                            # u8 LUT path == float32 input path
+
+
+def test_tcgen05_engine_matches_simt_engine(keras_c2):
+    z, w, frames, e = keras_c2
+    s = _engine(n_class=2, max_batch=2, engine="simt")
+    s.set_weights(w)
+    s.finalize()
+    fr = torch.from_numpy(frames).cuda()
+    a, b = e.forward(fr), s.forward(fr)
+    assert (a - b).abs().max().item() < 3e-4
+
+
+def test_forward_errors(keras_c2):
+    from object_tracking_b200._native import B2TError
+    z, w, frames, e = keras_c2
+    with pytest.raises(ValueError):
+        e.forward(torch.zeros((1, 400, 416, 3), dtype=torch.uint8, device="cuda"))
+    with pytest.raises(B2TError):
+        e.forward(torch.zeros((3, 416, 416, 3), dtype=torch.uint8, device="cuda"))   # > max_batch
+    with pytest.raises(B2TError):
+        e.extract("norm_99", 1)
+
+
+def test_darknet_semantics_against_reference_library_golden():
+    """BN eps / reorg ordering of the darknet C library + its .weights loader (golden = libdarknet outputs)."""
+    import tempfile
+    z = np.load(os.path.join(GOLD, "darknet_416.npz"))
+    w = W.synthetic_yolo_weights(80, seed=int(z["weight_seed"]))
+    frame = np.random.default_rng(int(z["frame_seed"])).integers(0, 256, (1, 416, 416, 3), dtype=np.uint8)
+    e = _engine(n_class=80, max_batch=1, semantics="darknet")
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "s.weights")
+        W.write_darknet_weights(p, w, 80)
+        e.load_darknet_weights(p)
+    e.finalize()
+    lg = e.forward(torch.from_numpy(frame).cuda())
+    got = lg.cpu().numpy().reshape(13, 13, 425).transpose(2, 0, 1)
+    assert np.abs(got - z["logits"]).max() < 3e-3            # the library itself is fp32 with its own rounding
+    concat = e.extract("concat", 1).cpu().numpy()[0].transpose(2, 0, 1)
+    assert np.abs(concat[:256][::8] - z["reorg_sub"]).max() < 2e-3
+    fv = e.pool_features("norm_20", 1, "Global").cpu().numpy()[0]
+    assert np.abs(fv - z["feat_globalmax"]).max() < 3e-3
+    # region decode + do_nms_obj on the library's own logits -> the library's detections
+    lt = torch.from_numpy(np.ascontiguousarray(z["logits"].transpose(1, 2, 0)).reshape(1, 13, 13, 5, 85)).cuda()
+    dets, counts = e.region_detect(lt, 0.5, 0.45, 416, 416)
+    n = int(counts.cpu()[0])
+    rows = dets.cpu().numpy()[0, :n]
+    ref_rows = darknet_oracle.yolo_detect_list(z["det_boxes"], z["det_obj"], z["det_prob"], list(range(80)))
+    assert n == len(ref_rows)
+    for r, (cls, prob, box) in zip(rows, ref_rows):
+        assert int(r[6]) == cls
+        assert abs(r[5] - prob) < 1e-5
+        assert np.abs(r[:4] - np.array(box)).max() < 1e-2    # pixels of a 416 frame
+
+
+@pytest.mark.parametrize("spec", DECODE_SPECS)
+def test_decode_nms_matches_oracle(spec):
+    g, c = spec
+    eng = _engine(n_class=2, max_batch=1)
+    nets, refs = [], []
+    for rep in range(4):
+        for kind in DECODE_KINDS:
+            seed = 500000 + 97 * rep + 13 * DECODE_KINDS.index(kind) + g * c
+            net = decode_case(seed, g, c, kind)
+            nets.append(net)
+            refs.append(decode_oracle.boxes_to_array(decode_oracle.decode_netout(net, 0.5, 0.45, W.ANCHORS, c)))
+    batch = torch.from_numpy(np.stack(nets)).cuda()
+    boxes, counts = eng.decode(batch, 0.5, 0.45)
+    boxes, counts = boxes.cpu().numpy(), counts.cpu().numpy()
+    total = 0
+    for i, ref in enumerate(refs):
+        n = int(counts[i])
+        assert n == len(ref), (i, n, len(ref))
+        got = boxes[i, :n].astype(np.float64)
+        assert np.array_equal(got[:, 6:8], ref[:, 6:8])                   # labels + anchor ids, in order
+        assert np.abs(got[:, :6] - ref[:, :6]).max(initial=0) < 2e-6      # coords/conf/score (exp within 2 ulp)
+        total += n
+    assert total > 50
+
+
+def test_decode_golden_reference_outputs():
+    """Committed outputs of the REFERENCE decode_netout (utility/utils.py) -- not of our oracle."""
+    from object_tracking_b200.engine import DetectorEngine
+    eng = DetectorEngine(n_class=2, max_batch=1)
+    z = np.load(os.path.join(GOLD, "decode_cases.npz"))
+    checked = 0
+    for i in range(int(z["n_cases"])):
+        g, c, kind, seed = (int(v) for v in z[f"meta_{i}"])
+        net = decode_case(seed, g, c, DECODE_KINDS[kind])
+        boxes, counts = eng.decode(torch.from_numpy(net[None]).cuda(), 0.5, 0.45)
+        n = int(counts.cpu()[0])
+        ref = z[f"box_{i}"]
+        assert n == len(ref), (i, kind)
+        got = boxes.cpu().numpy()[0, :n].astype(np.float64)
+        assert np.array_equal(got[:, 6:8], ref[:, 6:8])
+        assert np.abs(got[:, :6] - ref[:, :6]).max(initial=0) < 2e-6
+        checked += n
+    assert checked > 500
+
+
+def test_decode_thresholds_and_capacity():
+    from object_tracking_b200.engine import DetectorEngine
+    eng = DetectorEngine(n_class=2, max_batch=1)
+    net = decode_case(7, 13, 20, "crowd")
+    for (ot, nt) in ((0.5, 0.45), (0.6, 0.3), (0.5, 0.9)):
+        ref = decode_oracle.boxes_to_array(decode_oracle.decode_netout(net, ot, nt, W.ANCHORS, 20))
+        boxes, counts = eng.decode(torch.from_numpy(net[None]).cuda(), ot, nt)
+        n = int(counts.cpu()[0])
+        assert n == len(ref)
+        assert np.array_equal(boxes.cpu().numpy()[0, :n, 6:8].astype(np.float64), ref[:, 6:8])
+    # all 845 anchors confident, one class, identical boxes per cell -> stress the sort / suppression
+    net = np.zeros((13, 13, 5, 6), np.float32)
+    net[..., 4] = 6.0
+    net[..., 5] = np.linspace(3, 9, 845, dtype=np.float32).reshape(13, 13, 5)
+    ref = decode_oracle.boxes_to_array(decode_oracle.decode_netout(net, 0.5, 0.45, W.ANCHORS, 1))
+    boxes, counts = eng.decode(torch.from_numpy(net[None]).cuda(), 0.5, 0.45)
+    n = int(counts.cpu()[0])
+    assert n == len(ref) and n > 20
+    assert np.array_equal(boxes.cpu().numpy()[0, :n, 6:8].astype(np.float64), ref[:, 6:8])
+
+
+def test_lstm_heads_match_golden():
+    from object_tracking_b200.engine import DetectorEngine, LstmHead
+    z = np.load(os.path.join(GOLD, "tracker_cases.npz"))
+    eng = DetectorEngine(n_class=2, max_batch=1)
+    for tag, n_det, n_out in (("tiny", 4, 4), ("heat", 1024, 1024)):
+        w = W.synthetic_lstm_weights(1024 + n_det, 512, n_out, seed=11)
+        head = LstmHead(eng, 1024, n_det, 512, n_out, max_streams=3)
+        head.set_weights(w)
+        fv, det, yref = z[f"{tag}_fv"], z[f"{tag}_det"], z[f"{tag}_y"]
+        for t in range(fv.shape[0]):
+            if t % 4 == 0:
+                head.reset()                               # keras LSTMs are stateless across 4-frame windows
+            y = head.step(torch.from_numpy(fv[t]).cuda(), torch.from_numpy(det[t]).cuda())
+            assert np.abs(y.cpu().numpy() - yref[t]).max() < 2e-5, (tag, t)
+
+
+def test_heatmap_kernels():
+    from object_tracking_b200.engine import DetectorEngine
+    eng = DetectorEngine(n_class=2, max_batch=1)
+    rng = np.random.default_rng(5)
+    xywh = np.round(rng.uniform(-0.1, 0.9, (64, 4)) * 256) / 256       # exactly representable -> same int()
+    xywh[:, 2:] = np.abs(xywh[:, 2:]) * 0.5
+    xywh[0] = 0
+    heat = eng.heatmap_from_box(torch.from_numpy(xywh.astype(np.float32)).cuda(), 32).cpu().numpy()
+    for i in range(64):
+        ref = tracker_oracle.generate_heatmap_feat(*xywh[i], hmap_size=32)
+        assert np.array_equal(heat[i], ref.astype(np.float32)), i
+    rect = eng.box_from_heatmap(torch.from_numpy(heat).cuda(), 32, 0.75).cpu().numpy()
+    for i in range(64):
+        assert tuple(rect[i]) == tracker_oracle.generate_rectangle_from_heatmap(heat[i], 0.75, 32), i
+
+
+def test_convlstm_window_matches_oracle():
+    """MultiObjDetTracker: detector (C=2) -> ConvLSTM2D(64) over 3 consecutive frames -> 1x1 head."""
+    from object_tracking_b200.engine import DetectorEngine
+    C, U, T = 2, 64, 3
+    w = W.synthetic_yolo_weights(C, seed=0)
+    wl = W.synthetic_convlstm_weights(5 * (5 + C) + 1024, U, 5 * (5 + C), seed=2)
+    frames = np.random.default_rng(99).integers(0, 256, (T, 416, 416, 3), dtype=np.uint8)
+    e = DetectorEngine(n_class=C, max_batch=T, convlstm_units=U)
+    e.set_weights(w)
+    e.set_convlstm_weights(wl)
+    e.finalize()
+    o = yolo_oracle.yolo_forward(yolo_oracle.normalize(frames), w, C, dtype=np.float64)
+    det = e.forward(torch.from_numpy(frames).cuda()).cpu().numpy()
+    assert np.abs(det - o["logits"]).max() < 5e-4
+    h = np.zeros((13, 13, U)); c = np.zeros((13, 13, U))
+    wl64 = {k: v.astype(np.float64) for k, v in wl.items()}
+    refs = []
+    for t in range(T):
+        out, h, c = tracker_oracle.multiobj_step(o["logits"][t].reshape(13, 13, -1), o["feat"][t], h, c, wl64)
+        refs.append(out)
+    e.convlstm_reset()
+    trk = e.convlstm_window(T).cpu().numpy().reshape(T, 13, 13, -1)
+    for t in range(T):
+        assert np.abs(trk[t] - refs[t]).max() < 1e-3, t
+    # a second window continues from the carried state unless reset
+    e.convlstm_reset()
+    trk2 = e.convlstm_window(T).cpu().numpy().reshape(T, 13, 13, -1)
+    assert np.array_equal(trk, trk2)

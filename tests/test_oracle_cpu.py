@@ -1,0 +1,116 @@
+"""CPU suite, part 1: the oracle against the committed golden vectors (which hold outputs of the
+REFERENCE's own code: utility/utils.py decode_netout exec'd from /root/reference, and the reference's
+darknet C library), plus host-side weight IO."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from oracle import darknet_oracle, decode_oracle, tracker_oracle, yolo_oracle
+from oracle.cases import DECODE_KINDS, decode_case
+from object_tracking_b200 import weights as W
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_decode_oracle_matches_reference_outputs():
+    z = np.load(os.path.join(GOLD, "decode_cases.npz"))
+    n = int(z["n_cases"])
+    assert n >= 80
+    nonempty = 0
+    for i in range(n):
+        g, c, kind, seed = (int(v) for v in z[f"meta_{i}"])
+        net = decode_case(seed, g, c, DECODE_KINDS[kind])
+        assert np.isclose(net.astype(np.float64).sum(), float(z[f"insum_{i}"]), rtol=0, atol=1e-6)
+        got = decode_oracle.boxes_to_array(decode_oracle.decode_netout(net, 0.5, 0.45, W.ANCHORS, c))
+        ref = z[f"box_{i}"]
+        assert got.shape == ref.shape, (i, kind)
+        assert np.array_equal(got, ref), (i, kind)          # bit-exact incl. order, labels, anchor ids
+        nonempty += len(ref) > 0
+    assert nonempty > n // 2
+
+
+def test_decode_edge_cases():
+    # empty, a single confident anchor, two identical boxes of one class (IoU = 1 >= thr -> one survives)
+    net = np.full((13, 13, 5, 7), -20.0, np.float32)
+    assert decode_oracle.decode_netout(net, 0.5, 0.45, W.ANCHORS, 2) == []
+    net[3, 4, 1, 4] = 8.0; net[3, 4, 1, 5] = 9.0; net[3, 4, 1, 0:4] = 0.0
+    out = decode_oracle.decode_netout(net, 0.5, 0.45, W.ANCHORS, 2)
+    assert len(out) == 1 and out[0].get_label() == 0 and out[0].cell == (3 * 13 + 4) * 5 + 1
+    net[3, 4, 2] = net[3, 4, 1]
+    net[3, 4, 2, 2:4] += np.log(np.float32([W.ANCHORS[2] / W.ANCHORS[4], W.ANCHORS[3] / W.ANCHORS[5]]))
+    out = decode_oracle.decode_netout(net, 0.5, 0.45, W.ANCHORS, 2)
+    assert len(out) == 1
+
+
+def test_darknet_oracle_matches_reference_library_outputs():
+    z = np.load(os.path.join(GOLD, "darknet_416.npz"))
+    region = darknet_oracle.region_forward(z["logits"], 80)
+    assert np.abs(region - z["region"]).max() < 1e-5
+    boxes, obj, prob = darknet_oracle.detect(z["region"], 416, 416, 416, 416, 0.5, 0.45, 80)
+    live = np.nonzero(obj)[0]
+    assert live.size == z["det_obj"].shape[0]
+    assert np.allclose(boxes[live], z["det_boxes"], atol=1e-3)
+    assert np.allclose(obj[live], z["det_obj"], atol=1e-6)
+    assert np.allclose(prob[live], z["det_prob"], atol=1e-6)
+    assert float(z["oracle_err"].max()) < 2e-3          # fp64 forward restatement vs libdarknet, recorded at pin time
+
+
+def test_yolo_oracle_regression_vector():
+    z = np.load(os.path.join(GOLD, "keras_416_c2.npz"))
+    w = W.synthetic_yolo_weights(2, seed=int(z["weight_seed"]))
+    frames = np.random.default_rng(int(z["frame_seed"])).integers(0, 256, (2, 416, 416, 3), dtype=np.uint8)
+    o = yolo_oracle.yolo_forward(yolo_oracle.normalize(frames[:1]).astype(np.float32), w, 2, dtype=np.float32)
+    assert np.abs(o["logits"][0] - z["logits"][0]).max() < 2e-3       # fp32 run vs committed fp64 vector
+    assert np.abs(o["feat"][0].max(axis=(0, 1)) - z["feat_globalmax"][0]).max() < 5e-3
+
+
+def test_space_to_depth_orderings_differ():
+    x = np.arange(64 * 26 * 26, dtype=np.float64).reshape(1, 64, 26, 26)
+    import torch
+    t = torch.from_numpy(x)
+    tf_order = yolo_oracle.space_to_depth_x2(t.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
+    dk = yolo_oracle.darknet_reorg(t, 2)
+    assert tf_order.shape == dk.shape == (1, 256, 13, 13)
+    assert not torch.equal(tf_order, dk)
+    assert torch.equal(torch.sort(tf_order.reshape(-1))[0], torch.sort(dk.reshape(-1))[0])   # both permutations
+
+
+def test_tracker_oracle_regression_vectors():
+    z = np.load(os.path.join(GOLD, "tracker_cases.npz"))
+    out = tracker_oracle.make_cases()
+    for k in z.files:
+        assert np.allclose(out[k], z[k], rtol=0, atol=1e-12), k
+
+
+def test_heatmap_helpers():
+    h = tracker_oracle.generate_heatmap_feat(0.25, 0.5, 0.25, 0.125, 32).reshape(32, 32)
+    assert h.sum() == (4 + 1) * (8 + 1) and h[16, 8] == 1 and h[15, 8] == 0
+    assert tracker_oracle.generate_rectangle_from_heatmap(h) == (8, 16, 16, 20)
+    assert tracker_oracle.generate_rectangle_from_heatmap(np.zeros((32, 32))) == (32, 32, -1, -1)
+
+
+def test_darknet_weight_file_roundtrip():
+    w = W.synthetic_yolo_weights(2, seed=3)
+    with tempfile.TemporaryDirectory() as d:
+        for (major, minor) in ((0, 1), (0, 2)):          # int32 vs size_t "seen" header (parser.c:1220-1226)
+            p = os.path.join(d, f"v{major}{minor}.weights")
+            W.write_darknet_weights(p, w, 2, major=major, minor=minor)
+            r = W.read_darknet_weights(p, 2)
+            assert set(r) == set(w)
+            for k in w:
+                assert np.array_equal(r[k], w[k]), k
+        with pytest.raises(ValueError):
+            W.read_darknet_weights(p, 80)                  # wrong class count -> truncated
+    assert W.n_params(80) == 50_983_561                  # 50 942 217 + 4 * sum(Cout of the 22 BN layers)
+
+
+def test_param_and_traffic_counts_match_survey():
+    # W = 50 942 217 conv weights + conv_23 bias (BN vectors excluded), R, Wr
+    t = W.traffic_model(80, 416)
+    assert t["W"] == 50_942_217
+    assert t["R"] == 8_955_648
+    assert t["Wr"] == 8_508_305
+    assert abs(t["flops"] - 29.464e9) < 0.01e9
+    assert abs(W.forward_bytes(80, 416, batch=1) - 273.6e6) < 0.1e6
