@@ -28,8 +28,10 @@ enum { B2T_SEM_KERAS = 0,     /* gamma*(x-mean)/sqrt(var+eps)+beta, tf.space_to_
        B2T_SEM_DARKNET = 1 }; /* (x-mean)/(sqrt(var)+1e-6)*gamma+beta, reorg_cpu        (blas.c:147-158, :9-30)    */
 
 /* which contraction kernel runs the convolutions */
-enum { B2T_ENGINE_TCGEN05 = 0,   /* tcgen05.mma, bf16 hi/lo split operands, 3 MMAs per product, fp32 accumulate in TMEM */
-       B2T_ENGINE_SIMT = 1 };    /* fp32 FMA on the same operands: on-device cross-check only (slow)                    */
+enum { B2T_ENGINE_TCGEN05 = 0,   /* tcgen05.mma, fp16 hi/lo split operands, 3 MMAs per product, fp32 accumulate in TMEM;
+                                    activation patch stationary in shared memory (conv_halo.cu)                        */
+       B2T_ENGINE_SIMT = 1,      /* fp32 FMA on the same operands: on-device cross-check only (slow)                    */
+       B2T_ENGINE_TCGEN05_TILE = 2 }; /* first-generation tcgen05 kernel, one TMA box per tap (conv_umma.cu); cross-check */
 
 enum { B2T_FRAME_U8 = 0,      /* HWC uint8, divided by 255 on load (utils.py:150-153 normalize) */
        B2T_FRAME_F32 = 1 };   /* HWC float32, already normalised                                 */
@@ -120,6 +122,11 @@ int  b2t_lstm_reset(b2t_lstm *l, int stream_index /* -1 = all */, void *stream);
  * stored (S,T,F) can be stepped without a gather. */
 int  b2t_lstm_step(b2t_lstm *l, const float *fv_dev, int fv_stride, const float *det_dev, int det_stride,
                    int n_streams, float *y_dev, int y_stride, int hard_sigmoid, void *stream);
+/* A whole window in one call: fv_dev (S,T,n_feat), det_dev (S,T,n_det) dense -> y_dev (S,T,n_out).  The input
+ * projection x*W of all S*T rows is one launch, only h*U + gates is sequential (T launches), the Dense head is one
+ * launch.  reset != 0 zeroes (h,c) first = Keras' stateless windows. T <= 16. */
+int  b2t_lstm_sequence(b2t_lstm *l, const float *fv_dev, const float *det_dev, int n_streams, int n_steps,
+                       float *y_dev, int reset, int hard_sigmoid, void *stream);
 /* pooled feature of the last forward's conv layer `name` for frames [0,batch): Global -> (B,C);
  * Max -> (B,(H/4)*(W/4)*C).  chw_view=1 reproduces preprocessing.py:419 (CHW buffer viewed as HWC). */
 int  b2t_pool_features(b2t_ctx *ctx, const char *name, int batch, int pool_mode, int chw_view,

@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200track.so")
 
 SEM_KERAS, SEM_DARKNET = 0, 1
-ENGINE_TCGEN05, ENGINE_SIMT = 0, 1
+ENGINE_TCGEN05, ENGINE_SIMT, ENGINE_TCGEN05_TILE = 0, 1, 2
 FRAME_U8, FRAME_F32 = 0, 1
 
 
@@ -51,6 +51,7 @@ SIGNATURES = {
     "b2t_lstm_set_weights": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b2t_lstm_reset": (C.c_int, [_vp, C.c_int, _vp]),
     "b2t_lstm_step": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, C.c_int, _vp, C.c_int, C.c_int, _vp]),
+    "b2t_lstm_sequence": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, C.c_int, C.c_int, _vp]),
     "b2t_pool_features": (C.c_int, [_vp, C.c_char_p, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "b2t_heatmap_from_box": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp]),
     "b2t_select_detection": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp,

@@ -61,7 +61,10 @@ struct ConvLayer {
     size_t off_whi = 0, off_wlo = 0, off_scale = 0, off_bias = 0;
     int ldw = 0;
     int TW = 16, TH = 8, BN = 128;
-    CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
+    CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;      // tile engine (conv_umma.cu)
+    int hC = 0, hP = 0, hR = 0, hN = 0, h_rows = 0, h_plane_bytes = 0;   // halo engine tile (conv_halo.cu)
+    bool h_small = false;                         // two-CTAs-per-SM resource shape
+    CUtensorMap tmX_hi, tmX_lo, tmW_hi, tmW_lo;
     bool have_weights = false;
 };
 
@@ -111,6 +114,59 @@ static void choose_tile(int H, int W, bool pool, int &TW, int &TH) {
     }
 }
 
+// Halo-engine tile: hR rows x hC columns of one image, patch pitch hP, MMA N = round_up(hR*hP, 16) <= 256,
+// patch (with halo) <= 256 rows of 128 bytes per plane.  Picks the geometry with the least wasted MMA columns.
+static void choose_halo_tile(int H, int W, int ksize, bool pool, ConvLayer &l) {
+    const int pad = ksize / 2, taps = ksize * ksize;
+    // short K and many tiles -> the small shape (two CTAs per SM overlap each other's prologue/epilogue)
+    const char *env = getenv("B2T_SMALL");
+    const int small_mode = env ? atoi(env) : -1;
+    l.h_small = small_mode >= 0 ? (small_mode != 0 && H >= 26) : (l.cin_pad / 64 * taps <= 36 && H >= 52);
+    const int max_rows = l.h_small ? 176 : 256, max_n = l.h_small ? 128 : 256;
+    double best = 1e30;
+    for (int nx = 1; nx <= 16; ++nx) {
+        int C = (W + nx - 1) / nx;
+        if (pool && (C & 1)) ++C;
+        const bool wrap = pad && nx == 1;                  // full-width tile: right halo column = next row's left halo
+        const int P = wrap ? W + 1 : C + 2 * pad;
+        if (P > 256) continue;
+        if (pool && (P & 1)) continue;
+        for (int R = 1; R <= H; ++R) {
+            if (pool && (R & 1)) continue;
+            const int rows = R + 2 * pad + (wrap ? 1 : 0);
+            const int N = round_up(R * P, 16);
+            if (rows * P > max_rows || N > max_n || (pool && N > 240)) break;
+            const int tiles_x = (W + C - 1) / C, tiles_y = (H + R - 1) / R;
+            // cycles per (tap, chunk) of one tile: 12 MMAs of 128 x N x 16 vs. the L2->SM stream (~42 B/clk/SM)
+            const double t_mma = 6.0 * N, t_l2 = (32768.0 + 2.0 * rows * P * 128 / taps) / 42.0;
+            const double cost = (t_mma > t_l2 ? t_mma : t_l2) * tiles_x * tiles_y;
+            if (cost < best - 1e-9) {
+                best = cost;
+                l.hC = C; l.hP = P; l.hR = R; l.hN = N; l.h_rows = rows;
+                l.h_plane_bytes = (int)align_up((size_t)rows * P * 128, 1024);
+            }
+        }
+    }
+}
+
+static int choose_splits_halo(int ctas, int cin_chunks, int taps, int n_sm) {
+    const char *env = getenv("B2T_SPLITS");
+    int best_s = 1;
+    double best_cost = 1e30;
+    const int max_s = cin_chunks > 32 ? 32 : cin_chunks;
+    for (int s = 1; s <= max_s; ++s) {
+        const int per = (cin_chunks + s - 1) / s;
+        if ((cin_chunks + per - 1) / per != s) continue;
+        if (env && atoi(env) > 0 && s != atoi(env) && s != max_s) continue;
+        // the tensor core truncates addends to the accumulator's exponent: keep one accumulation chain short
+        if (per * taps * 4 > 320 && s < max_s) continue;
+        const long waves = ((long)ctas * s + n_sm - 1) / n_sm;
+        const double cost = (double)waves * (per * taps + 10.0) + (s > 1 ? 3.0 * s : 0.0);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best_s = s; }
+    }
+    return best_s;
+}
+
 static int choose_splits(int tiles, int chunks, int n_sm) {
     const char *env = getenv("B2T_SPLITS");
     if (env && atoi(env) > 0) {
@@ -141,6 +197,7 @@ static ConvLayer &new_conv(b2t_ctx *c, int index, int k, int cin, int cout, bool
     l.ldw = k * k * l.cin_pad;
     l.BN = cout >= 128 ? 128 : 64;
     choose_tile(H, W, pool, l.TW, l.TH);
+    choose_halo_tile(H, W, k, pool, l);
     if ((int)c->conv.size() <= index) c->conv.resize(index + 1);
     c->conv[index] = l;
     return c->conv[index];
@@ -280,8 +337,12 @@ extern "C" int b2t_create(const b2t_config *cfg, b2t_ctx **out) {
         const int tiles1 = ((l.W + l.TW - 1) / l.TW) * ((l.H + l.TH - 1) / l.TH) * ((l.cout + l.BN - 1) / l.BN);
         for (int bsz = 1; bsz <= MB; ++bsz) {
             size_t s = 1;
-            if (cfg->engine != B2T_ENGINE_SIMT) {
+            if (cfg->engine == 2) {
                 s = choose_splits(tiles1 * bsz, l.k * l.k * l.cin_pad / 64, 148);
+                if (s == 1) continue;
+            } else if (cfg->engine == B2T_ENGINE_TCGEN05) {
+                const int ctas = ((l.W + l.hC - 1) / l.hC) * ((l.H + l.hR - 1) / l.hR) * ((l.cout + 127) / 128) * bsz;
+                s = choose_splits_halo(ctas, l.cin_pad / 64, l.k * l.k, 148);
                 if (s == 1) continue;
             }
             const size_t need = s * (size_t)bsz * l.H * l.W * ldp * 4;
@@ -498,6 +559,7 @@ extern "C" int b2t_finalize(b2t_ctx *c, int upload, void *stream) {
         c->encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
     }
     int rc = conv_umma_init();
+    if (!rc) rc = conv_halo_init();
     if (rc) return fail(-2, "cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString((cudaError_t)rc));
     if (upload) CK(cudaMemcpyAsync(c->d_blob, c->host_blob.data(), c->weight_bytes, cudaMemcpyHostToDevice, st));
     // pad channels / never-written halo must be finite zeros
@@ -519,6 +581,12 @@ extern "C" int b2t_finalize(b2t_ctx *c, int upload, void *stream) {
         cuuint32_t wbox[2] = {64, (cuuint32_t)l.BN};
         if ((rc = make_tmap(c, &l.tmB_hi, c->d_blob + l.off_whi, 2, wd, wst, wbox))) return rc;
         if ((rc = make_tmap(c, &l.tmB_lo, c->d_blob + l.off_wlo, 2, wd, wst, wbox))) return rc;
+        cuuint32_t xbox[4] = {64, (cuuint32_t)l.hP, (cuuint32_t)l.h_rows, 1};
+        if ((rc = make_tmap(c, &l.tmX_hi, in.hi + l.in_ch_off, 4, dims, strides, xbox))) return rc;
+        if ((rc = make_tmap(c, &l.tmX_lo, in.hi + in.plane + l.in_ch_off, 4, dims, strides, xbox))) return rc;
+        cuuint32_t wbox2[2] = {64, 128};
+        if ((rc = make_tmap(c, &l.tmW_hi, c->d_blob + l.off_whi, 2, wd, wst, wbox2))) return rc;
+        if ((rc = make_tmap(c, &l.tmW_lo, c->d_blob + l.off_wlo, 2, wd, wst, wbox2))) return rc;
     }
     c->finalized = true;
     return 0;
@@ -571,6 +639,22 @@ static int run_conv(b2t_ctx *c, ConvLayer &l, int B, float *f32_dst, cudaStream_
         if ((rc = launch_conv_simt(v, p, st))) return fail(-2, "conv_simt launch: %s", cudaGetErrorString((cudaError_t)rc));
         if ((rc = launch_splitk_epilogue(p, st))) return fail(-2, "epilogue launch: %s", cudaGetErrorString((cudaError_t)rc));
         c->launches += 2;
+        return 0;
+    }
+    if (c->cfg.engine == B2T_ENGINE_TCGEN05) {
+        p.hC = l.hC; p.hP = l.hP; p.hR = l.hR; p.hN = l.hN; p.h_rows = l.h_rows; p.h_plane_bytes = l.h_plane_bytes;
+        p.h_tiles_x = (l.W + l.hC - 1) / l.hC; p.h_tiles_y = (l.H + l.hR - 1) / l.hR;
+        const int ctas = B * p.h_tiles_x * p.h_tiles_y * ((l.cout + 127) / 128);
+        p.splits = choose_splits_halo(ctas, p.cin_chunks, l.k * l.k, c->n_sm);
+        if (p.splits > 1 && (size_t)p.splits * B * l.H * l.W * p.ldp * 4 > c->partial_bytes)
+            return fail(-2, "internal: split-K workspace too small for conv %d", l.index);
+        if ((rc = launch_conv_halo(l.h_small, l.tmX_hi, l.tmX_lo, l.tmW_hi, l.tmW_lo, p, st)))
+            return fail(-2, "conv_halo launch (conv %d): %s", l.index, cudaGetErrorString((cudaError_t)rc));
+        c->launches += 1;
+        if (p.splits > 1) {
+            if ((rc = launch_splitk_epilogue(p, st))) return fail(-2, "epilogue launch: %s", cudaGetErrorString((cudaError_t)rc));
+            c->launches += 1;
+        }
         return 0;
     }
     const int tiles = B * p.tiles_x * p.tiles_y * ((l.cout + l.BN - 1) / l.BN);
@@ -741,11 +825,13 @@ extern "C" int b2t_region_detect(b2t_ctx *c, const float *logits, int B, int gh,
 }
 
 // ------------------------------------------------------------------------------------------------ LSTM head
+static const int kMaxT = 16;
 struct b2t_lstm {
     b2t_ctx *ctx;
     int n_feat, n_det, units, n_out, max_streams;
     float *d_wp = nullptr, *d_bias = nullptr, *d_wd = nullptr, *d_bd = nullptr;
     float *d_h[2] = {nullptr, nullptr}, *d_c = nullptr;
+    float *d_zx = nullptr, *d_hseq = nullptr;      // (max_streams*kMaxT, 4u) / (max_streams*kMaxT, u) sequence scratch
     int cur = 0;
     bool have = false;
 };
@@ -759,7 +845,9 @@ extern "C" int b2t_lstm_create(b2t_ctx *ctx, int n_feat, int n_det, int units, i
     if (cudaMalloc(&l->d_wp, rows * 4 * units * 4) || cudaMalloc(&l->d_bias, 4 * units * 4) ||
         cudaMalloc(&l->d_wd, (size_t)units * n_out * 4) || cudaMalloc(&l->d_bd, n_out * 4) ||
         cudaMalloc(&l->d_h[0], (size_t)max_streams * units * 4) || cudaMalloc(&l->d_h[1], (size_t)max_streams * units * 4) ||
-        cudaMalloc(&l->d_c, (size_t)max_streams * units * 4)) {
+        cudaMalloc(&l->d_c, (size_t)max_streams * units * 4) ||
+        cudaMalloc(&l->d_zx, (size_t)max_streams * kMaxT * 4 * units * 4) ||
+        cudaMalloc(&l->d_hseq, (size_t)max_streams * kMaxT * units * 4)) {
         b2t_lstm_destroy(l);
         return fail(-2, "b2t_lstm_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
@@ -773,7 +861,7 @@ extern "C" int b2t_lstm_create(b2t_ctx *ctx, int n_feat, int n_det, int units, i
 extern "C" void b2t_lstm_destroy(b2t_lstm *l) {
     if (!l) return;
     cudaFree(l->d_wp); cudaFree(l->d_bias); cudaFree(l->d_wd); cudaFree(l->d_bd);
-    cudaFree(l->d_h[0]); cudaFree(l->d_h[1]); cudaFree(l->d_c);
+    cudaFree(l->d_h[0]); cudaFree(l->d_h[1]); cudaFree(l->d_c); cudaFree(l->d_zx); cudaFree(l->d_hseq);
     delete l;
 }
 
@@ -822,14 +910,13 @@ extern "C" int b2t_lstm_step(b2t_lstm *l, const float *fv, int fv_stride, const 
     if (det_stride <= 0) det_stride = l->n_det;
     if (y_stride <= 0) y_stride = l->n_out;
     const int nxt = l->cur ^ 1;
-    for (int s0 = 0; s0 < S; s0 += 8) {
+    {
         LstmParams p;
-        p.wp = l->d_wp; p.bias = l->d_bias;
-        p.fv = fv + (size_t)s0 * fv_stride; p.det = det ? det + (size_t)s0 * det_stride : nullptr;
+        memset(&p, 0, sizeof p);
+        p.wp = l->d_wp; p.bias = l->d_bias; p.fv = fv; p.det = det;
         p.fv_stride = fv_stride; p.det_stride = det_stride;
-        p.h_in = l->d_h[l->cur] + (size_t)s0 * l->units; p.h_out = l->d_h[nxt] + (size_t)s0 * l->units;
-        p.c = l->d_c + (size_t)s0 * l->units;
-        p.n_feat = l->n_feat; p.n_det = l->n_det; p.units = l->units; p.S = S - s0 < 8 ? S - s0 : 8;
+        p.h_in = l->d_h[l->cur]; p.h_out = l->d_h[nxt]; p.c = l->d_c;
+        p.n_feat = l->n_feat; p.n_det = l->n_det; p.units = l->units; p.S = S;
         p.hard_sigmoid = hard_sigmoid;
         const int rc = launch_lstm_gates(p, st);
         if (rc) return fail(-2, "lstm launch: %s", cudaGetErrorString((cudaError_t)rc));
@@ -843,6 +930,43 @@ extern "C" int b2t_lstm_step(b2t_lstm *l, const float *fv, int fv_stride, const 
     const int rc = launch_dense_sigmoid(l->d_h[l->cur], l->d_wd, l->d_bd, l->units, l->n_out, S, y, y_stride, st);
     if (rc) return fail(-2, "dense launch: %s", cudaGetErrorString((cudaError_t)rc));
     if (l->ctx) l->ctx->launches += 1;
+    return 0;
+}
+
+extern "C" int b2t_lstm_sequence(b2t_lstm *l, const float *fv, const float *det, int S, int T, float *y, int reset,
+                                 int hard_sigmoid, void *stream) {
+    if (!l || !l->have) return fail(-1, "b2t_lstm_sequence: weights not set");
+    if (!fv || (!det && l->n_det) || !y) return fail(-1, "b2t_lstm_sequence: null pointer");
+    if (S < 1 || S > l->max_streams || T < 1 || T > kMaxT) return fail(-1, "b2t_lstm_sequence: S=%d T=%d out of range", S, T);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if (reset && (rc = b2t_lstm_reset(l, -1, stream))) return rc;
+    const int u = l->units, R = S * T;
+    LstmParams p;
+    memset(&p, 0, sizeof p);
+    p.wp = l->d_wp; p.bias = l->d_bias;
+    p.n_feat = l->n_feat; p.n_det = l->n_det; p.units = u; p.hard_sigmoid = hard_sigmoid;
+    // (1) input projection of all S*T rows at once: it does not depend on the recurrent state
+    p.mode = 1; p.fv = fv; p.det = det; p.fv_stride = l->n_feat; p.det_stride = l->n_det;
+    p.S = R; p.zx = l->d_zx; p.zx_stride = 4 * u; p.h_in = l->d_h[l->cur]; p.h_out = l->d_h[l->cur]; p.c = l->d_c;
+    if ((rc = launch_lstm_gates(p, st))) return fail(-2, "lstm launch: %s", cudaGetErrorString((cudaError_t)rc));
+    // (2) T sequential recurrent steps over the S streams (h*U + gates); h_t kept for the Dense head
+    for (int t = 0; t < T; ++t) {
+        const int nxt = l->cur ^ 1;
+        p.mode = 2; p.S = S;
+        p.zx = l->d_zx + (size_t)t * 4 * u; p.zx_stride = T * 4 * u;
+        p.h_in = l->d_h[l->cur]; p.h_out = l->d_h[nxt];
+        p.h_seq = l->d_hseq + (size_t)t * u; p.h_seq_stride = T * u;
+        if ((rc = launch_lstm_gates(p, st))) return fail(-2, "lstm launch: %s", cudaGetErrorString((cudaError_t)rc));
+        if (S < l->max_streams)
+            CK(cudaMemcpyAsync(l->d_h[nxt] + (size_t)S * u, l->d_h[l->cur] + (size_t)S * u,
+                               (size_t)(l->max_streams - S) * u * 4, cudaMemcpyDeviceToDevice, st));
+        l->cur = nxt;
+    }
+    // (3) Dense(n_out, sigmoid) on all S*T hidden states
+    if ((rc = launch_dense_sigmoid(l->d_hseq, l->d_wd, l->d_bd, u, l->n_out, R, y, l->n_out, st)))
+        return fail(-2, "dense launch: %s", cudaGetErrorString((cudaError_t)rc));
+    if (l->ctx) l->ctx->launches += T + 2;
     return 0;
 }
 

@@ -42,6 +42,12 @@ struct ConvParams {
     float *partial;         // [splits][B*H*W][ldp] fp32 raw accumulators (split-K or SIMT engine)
     Dest out;               // full-resolution destination (hi and/or f32 may be NULL)
     Dest pout;              // pooled destination
+    // ---- halo engine (conv_halo.cu): pixel tile = hR rows x hC columns of one image, held in shared memory as
+    // an (h_rows x hP)-pixel patch with its halo; MMA N = hN = round_up(hR*hP, 16)
+    int hC, hP, hR, hN;
+    int h_rows;             // patch rows loaded per channel chunk (hR + 2*pad [+1 when the row wrap trick is used])
+    int h_plane_bytes;      // bytes between the hi and lo patch in shared memory
+    int h_tiles_x, h_tiles_y;
 };
 
 __device__ __forceinline__ float leaky(float v) { return v > 0.f ? v : 0.1f * v; }
@@ -110,6 +116,37 @@ __device__ __forceinline__ void emit8(const Dest &d, int b, int y, int x, int c,
         } else {
             for (int i = 0; i < nvalid; ++i) p[i] = d.accumulate_f ? p[i] + v[i] : v[i];
         }
+    }
+}
+
+// One channel `c` of source pixel (b,y,x) -- used by the halo engine, whose epilogue threads own a channel each.
+__device__ __forceinline__ void emit1(const Dest &d, int b, int y, int x, int c, int Cout, float v) {
+    long long pix;
+    int cc = c;
+    if (d.mode == DEST_REORG_DARKNET) {
+        const int H = d.H, W = d.W, Hd = H / 2, Wd = W / 2, out_c = Cout / 4;
+        const int s = (c * H + y) * W + x;
+        const int w2 = s % (2 * W), h2 = (s / (2 * W)) % (2 * H), c2 = s / (4 * W * H);
+        const int k = ((h2 & 1) * 2 + (w2 & 1)) * out_c + c2;
+        const int o = (w2 >> 1) + W * ((h2 >> 1) + H * k);
+        cc = o / (Hd * Wd);
+        pix = ((long long)b * Hd + (o / Wd) % Hd) * Wd + o % Wd;
+    } else if (d.mode == DEST_S2D_TF) {
+        pix = ((long long)b * (d.H / 2) + (y >> 1)) * (d.W / 2) + (x >> 1);
+        cc = ((y & 1) * 2 + (x & 1)) * Cout + c;
+    } else {
+        pix = ((long long)b * d.H + y) * d.W + x;
+    }
+    if (d.hi) {
+        op_t h, l;
+        split_f16(v, h, l);
+        op_t *p = d.hi + pix * d.pix_stride_b + d.ch_off_b + cc;
+        p[0] = h;
+        p[d.plane_stride] = l;
+    }
+    if (d.f32) {
+        float *p = d.f32 + pix * d.pix_stride_f + d.ch_off_f + cc;
+        *p = d.accumulate_f ? *p + v : v;
     }
 }
 

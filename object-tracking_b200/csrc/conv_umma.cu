@@ -338,48 +338,52 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const SimtView v, const 
 // and the 2x2 max-pool.  K = 27 is no tensor-core shape and the layer is HBM-bound (0.5 MB in, 5.5 MB out
 // per frame), so this is a direct fp32 convolution: one thread = one pooled pixel x 16 output channels.
 
+// Block = 128 threads = 2 pooled rows x 32 pooled columns x 2 channel halves.  The (6 x 66)-pixel input patch is
+// staged in shared memory as normalised floats (coalesced byte loads, LUT for u8), the 27x32 weights likewise; the
+// tap loop over kh stays rolled so the kernel body fits the instruction cache (a fully unrolled 1728-FMA body
+// thrashes it and runs 5x slower).
+constexpr int kC1W = 32, kC1H = 2;                       // pooled pixels per block
+constexpr int kC1PW = 2 * kC1W + 2, kC1PH = 2 * kC1H + 2; // input patch incl. halo
 __global__ void __launch_bounds__(128) conv1_direct_kernel(const Conv1Params p) {
     __shared__ __align__(16) float sw[27 * 32];
-    __shared__ float sscale[32], sbias[32], slut[256];
-    for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) sw[i] = p.w[i];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) slut[i] = p.lut[i];
-    if (threadIdx.x < 32) { sscale[threadIdx.x] = p.scale[threadIdx.x]; sbias[threadIdx.x] = p.bias[threadIdx.x]; }
-    __syncthreads();
+    __shared__ float sscale[32], sbias[32];
+    __shared__ float spatch[kC1PH][kC1PW][3];
     const int Hq = p.H / 2, Wq = p.W / 2;
-    const long long total = (long long)p.B * Hq * Wq * 2;
-    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    const int half = int(t & 1);
-    long long q = t >> 1;
-    const int xq = int(q % Wq);  q /= Wq;
-    const int yq = int(q % Hq);
-    const int b = int(q / Hq);
-    // 4x4x3 input patch around the 2x2 quad
-    float in[4][4][3];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int yy = 2 * yq - 1 + r;
-#pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            const int xx = 2 * xq - 1 + s;
-            const bool ok = yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
-            const long long off = (((long long)b * p.H + yy) * p.W + xx) * 3;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                float val = 0.f;
-                if (ok) val = p.dtype == 0 ? slut[reinterpret_cast<const uint8_t *>(p.frames)[off + c]]
-                                           : reinterpret_cast<const float *>(p.frames)[off + c];
-                in[r][s][c] = val;
+    const int tiles_x = (Wq + kC1W - 1) / kC1W, tiles_y = (Hq + kC1H - 1) / kC1H;
+    int t = blockIdx.x;
+    const int tx = t % tiles_x;  t /= tiles_x;
+    const int ty = t % tiles_y;
+    const int b = t / tiles_y;
+    const int xq0 = tx * kC1W, yq0 = ty * kC1H;
+    for (int i = threadIdx.x; i < 27 * 32; i += 128) sw[i] = p.w[i];
+    if (threadIdx.x < 32) { sscale[threadIdx.x] = p.scale[threadIdx.x]; sbias[threadIdx.x] = p.bias[threadIdx.x]; }
+    {   // stage the patch: rows 2*yq0-1 .. 2*yq0+2*kC1H, cols 2*xq0-1 .. 2*xq0+2*kC1W, 3 channels (contiguous bytes)
+        const int y_lo = 2 * yq0 - 1, x_lo = 2 * xq0 - 1;
+        for (int i = threadIdx.x; i < kC1PH * kC1PW * 3; i += 128) {
+            const int r = i / (kC1PW * 3), rem = i - r * (kC1PW * 3);
+            const int col = rem / 3, ch = rem - col * 3;
+            const int yy = y_lo + r, xx = x_lo + col;
+            float v = 0.f;
+            if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
+                const long long off = (((long long)b * p.H + yy) * p.W + xx) * 3 + ch;
+                // u8: image/255. -- fp32 division is bit-identical to numpy's float64 division rounded to fp32
+                // for all 256 byte values (checked exhaustively in tests/test_oracle_cpu.py)
+                v = p.dtype == 0 ? __fdiv_rn((float)__ldg(reinterpret_cast<const uint8_t *>(p.frames) + off), 255.f)
+                                 : __ldg(reinterpret_cast<const float *>(p.frames) + off);
             }
+            spatch[r][col][ch] = v;
         }
     }
+    __syncthreads();
+    const int half = threadIdx.x & 1, lx = (threadIdx.x >> 1) % kC1W, ly = (threadIdx.x >> 1) / kC1W;
+    const int xq = xq0 + lx, yq = yq0 + ly;
     float acc[4][16];
 #pragma unroll
     for (int k = 0; k < 4; ++k)
 #pragma unroll
         for (int i = 0; i < 16; ++i) acc[k][i] = 0.f;
-#pragma unroll
-    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll 1
+    for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw)
 #pragma unroll
@@ -393,14 +397,17 @@ __global__ void __launch_bounds__(128) conv1_direct_kernel(const Conv1Params p) 
                 }
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const float a = in[(k >> 1) + kh][(k & 1) + kw][c];
+                    const float a = spatch[2 * ly + (k >> 1) + kh][2 * lx + (k & 1) + kw][c];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) acc[k][i] = fmaf(a, w[i], acc[k][i]);
                 }
             }
+    }
+    if (xq >= Wq || yq >= Hq) return;
     float mx[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) mx[i] = -INFINITY;
+    const bool want_full = p.out.hi || p.out.f32;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
 #pragma unroll
@@ -408,7 +415,7 @@ __global__ void __launch_bounds__(128) conv1_direct_kernel(const Conv1Params p) 
             acc[k][i] = leaky(fmaf(acc[k][i], sscale[half * 16 + i], sbias[half * 16 + i]));
             mx[i] = fmaxf(mx[i], acc[k][i]);
         }
-        if (p.out.hi || p.out.f32) {
+        if (want_full) {
             const float(&lo8)[8] = *reinterpret_cast<const float(*)[8]>(&acc[k][0]);
             const float(&hi8)[8] = *reinterpret_cast<const float(*)[8]>(&acc[k][8]);
             emit8(p.out, b, 2 * yq + (k >> 1), 2 * xq + (k & 1), half * 16, 32, lo8);
@@ -467,8 +474,9 @@ int launch_conv_simt(const SimtView &v, const ConvParams &p, cudaStream_t st) {
     return (int)cudaGetLastError();
 }
 int launch_conv1(const Conv1Params &p, cudaStream_t st) {
-    const long long total = (long long)p.B * (p.H / 2) * (p.W / 2) * 2;
-    conv1_direct_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(p);
+    const int Hq = p.H / 2, Wq = p.W / 2;
+    const long long blocks = (long long)p.B * ((Wq + kC1W - 1) / kC1W) * ((Hq + kC1H - 1) / kC1H);
+    conv1_direct_kernel<<<(unsigned)blocks, 128, 0, st>>>(p);
     return (int)cudaGetLastError();
 }
 int launch_planes_to_f32(const op_t *hi, long long plane, int pix_stride, int ch_off, int C, long long npix,

@@ -45,6 +45,12 @@ struct LstmParams {
     int n_feat, n_det, units, S;
     int fv_stride, det_stride;   // elements between consecutive streams' rows
     int hard_sigmoid;
+    int mode;             // 0 = full step; 1 = input projection only (zx_out = x*W + b, no state change);
+                          // 2 = recurrent step on a precomputed projection (z = zx_in + h*U)
+    float *zx;            // (rows, 4*units) projection buffer (mode 1: out, mode 2: in)
+    int zx_stride;        // elements between consecutive streams' rows of zx
+    float *h_seq;         // optional copy of h' (mode 0/2), row stride h_seq_stride
+    int h_seq_stride;
 };
 
 struct PoolParams {
@@ -77,6 +83,9 @@ struct ConvLstmGateParams {
 int launch_conv_umma(int BN, const CUtensorMap &a_hi, const CUtensorMap &a_lo, const CUtensorMap &b_hi,
                      const CUtensorMap &b_lo, const ConvParams &p, cudaStream_t st);
 int conv_umma_init();
+int conv_halo_init();
+int launch_conv_halo(bool small, const CUtensorMap &x_hi, const CUtensorMap &x_lo, const CUtensorMap &w_hi,
+                     const CUtensorMap &w_lo, const ConvParams &p, cudaStream_t st);
 int launch_splitk_epilogue(const ConvParams &p, cudaStream_t st);
 int launch_conv_simt(const SimtView &v, const ConvParams &p, cudaStream_t st);
 int launch_conv1(const Conv1Params &p, cudaStream_t st);

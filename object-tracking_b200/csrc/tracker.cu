@@ -27,21 +27,24 @@ __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-
 __global__ void __launch_bounds__(kLstmThreads) lstm_gates_kernel(const LstmParams p) {
     __shared__ float red[16][16][kMaxStreams];
     const int ub = blockIdx.x;
+    const int s0 = blockIdx.y * kMaxStreams;                   // first row (stream) of this CTA's group
+    const int nS = min(kMaxStreams, p.S - s0);
     const int col = threadIdx.x & 15, ks = threadIdx.x >> 4;   // 16 columns x 16 row groups
     const int n_x = p.n_feat + p.n_det, n_rows = n_x + p.units;
     const float *w = p.wp + (long long)ub * n_rows * 16;
+    const int k_lo = p.mode == 2 ? n_x : 0, k_hi = p.mode == 1 ? n_x : n_rows;
     float acc[kMaxStreams];
 #pragma unroll
     for (int s = 0; s < kMaxStreams; ++s) acc[s] = 0.f;
-    for (int k = ks; k < n_rows; k += 16) {
+    for (int k = k_lo + ks; k < k_hi; k += 16) {
         const float wv = __ldg(w + (long long)k * 16 + col);
 #pragma unroll
         for (int s = 0; s < kMaxStreams; ++s) {
-            if (s < p.S) {
+            if (s < nS) {
                 float xv;
-                if (k < p.n_feat) xv = __ldg(p.fv + (long long)s * p.fv_stride + k);
-                else if (k < n_x) xv = __ldg(p.det + (long long)s * p.det_stride + (k - p.n_feat));
-                else xv = __ldg(p.h_in + (long long)s * p.units + (k - n_x));
+                if (k < p.n_feat) xv = __ldg(p.fv + (long long)(s0 + s) * p.fv_stride + k);
+                else if (k < n_x) xv = __ldg(p.det + (long long)(s0 + s) * p.det_stride + (k - p.n_feat));
+                else xv = __ldg(p.h_in + (long long)(s0 + s) * p.units + (k - n_x));
                 acc[s] = fmaf(xv, wv, acc[s]);
             }
         }
@@ -49,23 +52,30 @@ __global__ void __launch_bounds__(kLstmThreads) lstm_gates_kernel(const LstmPara
 #pragma unroll
     for (int s = 0; s < kMaxStreams; ++s) red[ks][col][s] = acc[s];
     __syncthreads();
-    // 4 units x S streams finish
-    if (threadIdx.x < kUnitsPerBlock * p.S) {
-        const int uu = threadIdx.x % kUnitsPerBlock, s = threadIdx.x / kUnitsPerBlock;
+    // 4 units x nS streams finish
+    if (threadIdx.x < kUnitsPerBlock * nS) {
+        const int uu = threadIdx.x % kUnitsPerBlock, s = s0 + threadIdx.x / kUnitsPerBlock;
         const int unit = ub * kUnitsPerBlock + uu;
         float z[4];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             float t = 0.f;
-            for (int r = 0; r < 16; ++r) t += red[r][g * 4 + uu][s];
-            z[g] = t + p.bias[g * p.units + unit];
+            for (int r = 0; r < 16; ++r) t += red[r][g * 4 + uu][s - s0];
+            z[g] = t + (p.mode == 2 ? p.zx[(long long)s * p.zx_stride + g * p.units + unit] : p.bias[g * p.units + unit]);
+        }
+        if (p.mode == 1) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) p.zx[(long long)s * p.zx_stride + g * p.units + unit] = z[g];
+            return;
         }
         const float i = p.hard_sigmoid ? hard_sigmoid_f(z[0]) : sigmoid_f(z[0]);
         const float f = p.hard_sigmoid ? hard_sigmoid_f(z[1]) : sigmoid_f(z[1]);
         const float o = p.hard_sigmoid ? hard_sigmoid_f(z[3]) : sigmoid_f(z[3]);
         const float cn = fmaf(f, p.c[(long long)s * p.units + unit], i * tanhf(z[2]));
+        const float hn = o * tanhf(cn);
         p.c[(long long)s * p.units + unit] = cn;
-        p.h_out[(long long)s * p.units + unit] = o * tanhf(cn);
+        p.h_out[(long long)s * p.units + unit] = hn;
+        if (p.h_seq) p.h_seq[(long long)s * p.h_seq_stride + unit] = hn;
     }
 }
 
@@ -113,6 +123,25 @@ __global__ void pool_features_kernel(const PoolParams p) {
         }
         p.out[t] = m;
     }
+}
+
+// Global max, natural layout: one CTA per (frame, 64 channels), 4 pixel lanes per channel (coalesced 128-byte rows)
+__global__ void __launch_bounds__(256) pool_global_kernel(const PoolParams p) {
+    __shared__ float red[4][64];
+    const int b = blockIdx.x, c = blockIdx.y * 64 + (threadIdx.x & 63), pl = threadIdx.x >> 6;
+    float m = -INFINITY;
+    if (c < p.C) {
+        const op_t *q = p.hi + (long long)b * p.H * p.W * p.pix_stride + p.ch_off + c;
+        for (int px = pl; px < p.H * p.W; px += 4) {
+            const op_t *e = q + (long long)px * p.pix_stride;
+            m = fmaxf(m, join_f16(e[0], e[p.plane]));
+        }
+    }
+    red[pl][threadIdx.x & 63] = m;
+    __syncthreads();
+    if (threadIdx.x < 64 && c < p.C)
+        p.out[(long long)b * p.C + c] = fmaxf(fmaxf(red[0][threadIdx.x], red[1][threadIdx.x]),
+                                              fmaxf(red[2][threadIdx.x], red[3][threadIdx.x]));
 }
 
 // ---------------------------------------------------------------- heat maps (utils.py:53-79)
@@ -219,7 +248,8 @@ __global__ void convlstm_gates_kernel(const ConvLstmGateParams p) {
 
 // ---------------------------------------------------------------- launchers
 int launch_lstm_gates(const LstmParams &p, cudaStream_t st) {
-    lstm_gates_kernel<<<p.units / kUnitsPerBlock, kLstmThreads, 0, st>>>(p);
+    dim3 grid(p.units / kUnitsPerBlock, (p.S + kMaxStreams - 1) / kMaxStreams);
+    lstm_gates_kernel<<<grid, kLstmThreads, 0, st>>>(p);
     return (int)cudaGetLastError();
 }
 int launch_dense_sigmoid(const float *h, const float *wd, const float *bd, int units, int n_out, int S, float *y,
@@ -229,6 +259,10 @@ int launch_dense_sigmoid(const float *h, const float *wd, const float *bd, int u
     return (int)cudaGetLastError();
 }
 int launch_pool_features(const PoolParams &p, cudaStream_t st) {
+    if (p.mode == 0 && !p.chw_view) {
+        pool_global_kernel<<<dim3(p.B, (p.C + 63) / 64), 256, 0, st>>>(p);
+        return (int)cudaGetLastError();
+    }
     const int per = p.mode == 0 ? p.C : (p.H / 4) * (p.W / 4) * p.C;
     const long long total = (long long)p.B * per;
     pool_features_kernel<<<(unsigned)min((long long)148 * 8, (total + 127) / 128), 128, 0, st>>>(p);

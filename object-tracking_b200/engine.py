@@ -50,7 +50,7 @@ class DetectorEngine:
         cfg.n_class, cfg.max_batch = n_class, max_batch
         cfg.semantics = {"keras": N.SEM_KERAS, "darknet": N.SEM_DARKNET}[semantics]
         cfg.bn_eps = bn_eps
-        cfg.engine = {"tcgen05": N.ENGINE_TCGEN05, "simt": N.ENGINE_SIMT}[engine]
+        cfg.engine = {"tcgen05": N.ENGINE_TCGEN05, "simt": N.ENGINE_SIMT, "tcgen05_tile": N.ENGINE_TCGEN05_TILE}[engine]
         cfg.device = device
         cfg.convlstm_units = convlstm_units
         cfg.reserved[0] = 1 if keep_prepool else 0
@@ -67,6 +67,7 @@ class DetectorEngine:
         self._scratch: Dict[Tuple, torch.Tensor] = {}
         self._logits_view = None
         self.forward_events = None
+        self._graph_launches = 0
 
     def __del__(self):
         try:
@@ -235,7 +236,12 @@ class DetectorEngine:
 
     @property
     def launches(self) -> int:
-        return self.lib.b2t_launch_count(self.h)
+        """Kernels of this library launched so far: eager launches counted by the C side + the kernel nodes of
+        every CUDA-graph replay (the C counter ticks once at capture time, each replay relaunches them)."""
+        return self.lib.b2t_launch_count(self.h) + self._graph_launches
+
+    def add_graph_launches(self, n: int) -> None:
+        self._graph_launches += n
 
 
 class LstmHead:
@@ -265,6 +271,17 @@ class LstmHead:
 
     def reset(self, stream_index: int = -1) -> None:
         N.check(self.lib.b2t_lstm_reset(self.h, stream_index, _stream()))
+
+    def sequence(self, fv: torch.Tensor, det: torch.Tensor, reset: bool = True, hard_sigmoid: bool = True,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """fv (S,T,n_feat), det (S,T,n_det) contiguous -> y (S,T,n_out): T recurrent steps of S streams."""
+        S, T = fv.shape[0], fv.shape[1]
+        if not (fv.is_contiguous() and det.is_contiguous()):
+            raise ValueError("sequence inputs must be contiguous")
+        y = out if out is not None else torch.empty((S, T, self.n_out), dtype=torch.float32, device=fv.device)
+        N.check(self.lib.b2t_lstm_sequence(self.h, fv.data_ptr(), det.data_ptr(), S, T, y.data_ptr(),
+                                           1 if reset else 0, 1 if hard_sigmoid else 0, _stream()))
+        return y
 
     def step(self, fv: torch.Tensor, det: torch.Tensor, hard_sigmoid: bool = True,
              out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -38,6 +38,7 @@ class BaseTracker(object):
         self.max_streams = max_streams
         self.ref_layout_bug = ref_layout_bug          # preprocessing.py:419 CHW-as-HWC reinterpretation (R11)
         self._detector_kwargs = dict(detector_kwargs or {})
+        self._graphs = {}
         self.load_detection_model()
 
     def load_detection_model(self):
@@ -72,28 +73,66 @@ class BaseTracker(object):
         self._steps = 0
 
     def _detect_and_pool(self, frames: torch.Tensor, heat_size: int = 0):
+        self.model_detector.engine.forward(frames)
+        return self._decode_and_pool(frames.shape[0], frames.shape[2], frames.shape[1], heat_size)
+
+    def _decode_and_pool(self, B: int, W: int, H: int, heat_size: int = 0):
+        """Everything after the conv stack, on the engine's current logits / feature buffers."""
         det = self.model_detector
-        B, H, W = frames.shape[0], frames.shape[1], frames.shape[2]
-        dets, counts = det.detect_batch(frames, W, H)
+        dets, counts = det.engine.region_detect(det.engine.logits(B), det.THRESH, det.NMS, W, H)
         det_in, heat, chosen = det.engine.select_detection(dets, counts, W, H, det.class_mask, heat_size)
         fv = det.engine.pool_features(self._fv_name, B, self.pool, self.ref_layout_bug)
         return fv, det_in, heat, chosen
 
-    def track_windows(self, frames: torch.Tensor, reset: bool = True) -> torch.Tensor:
+    def _tail(self, S: int, T: int, W: int, H: int, reset: bool) -> torch.Tensor:
+        fv, xin = self._tracker_inputs_from_state(S * T, W, H)
+        return self.head.sequence(fv.view(S, T, -1), xin.view(S, T, -1), reset=reset)
+
+    def track_windows(self, frames: torch.Tensor, reset: bool = True, graph: bool = True) -> torch.Tensor:
         """frames (S,T,H,W,3) uint8 on the GPU: S independent streams (or windows), T consecutive frames each.
-        One batched detector pass over S*T frames, then T recurrent steps over the S streams in parallel.
-        reset=True reproduces Keras' stateless windows (state zeroed at the start of every window)."""
-        S, T = frames.shape[0], frames.shape[1]
+        One batched detector pass over S*T frames, then T recurrent steps over the S streams in parallel
+        (input projection hoisted out of the recurrence).  reset=True reproduces Keras' stateless windows.
+        graph=True replays the step from two CUDA graphs captured on first use (conv stack | decode + tracker):
+        the ~45 launches of a step are launch-latency bound otherwise.  The result tensor is reused."""
+        S, T, H, W = frames.shape[0], frames.shape[1], frames.shape[2], frames.shape[3]
         if S > self.max_streams:
             raise ValueError(f"{S} streams > max_streams {self.max_streams}")
-        fv, xin = self._tracker_inputs(frames.reshape(S * T, *frames.shape[2:]))
-        fv, xin = fv.view(S, T, -1), xin.view(S, T, -1)
-        out = torch.empty((S, T, self.n_out), dtype=torch.float32, device=frames.device)
-        if reset:
-            self.head.reset(-1)
-        for t in range(T):
-            self.head.step(fv[:, t], xin[:, t], out=out[:, t])
-        return out
+        eng = self.model_detector.engine
+        if not graph:
+            eng.forward(frames.reshape(S * T, H, W, 3))
+            return self._tail(S, T, W, H, reset)
+        key = (S, T, H, W, frames.dtype, bool(reset))
+        g = self._graphs.get(key)
+        if g is None:
+            static_in = torch.empty((S * T, H, W, 3), dtype=frames.dtype, device=frames.device)
+            static_in.copy_(frames.reshape(S * T, H, W, 3))
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                      # warm-up outside capture (allocations, lazy init)
+                eng.forward(static_in)
+                self._tail(S, T, W, H, reset)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            n0 = eng.lib.b2t_launch_count(eng.h)
+            g_fwd, g_tail = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_fwd):
+                eng.forward(static_in)
+            with torch.cuda.graph(g_tail):
+                static_out = self._tail(S, T, W, H, reset)
+            g = self._graphs[key] = (g_fwd, g_tail, static_in, static_out, eng.lib.b2t_launch_count(eng.h) - n0)
+        g_fwd, g_tail, static_in, static_out, n_kernels = g
+        static_in.copy_(frames.reshape(S * T, H, W, 3), non_blocking=True)
+        ev = eng.forward_events
+        if ev is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        g_fwd.replay()
+        if ev is not None:
+            e1.record()
+            ev.append((e0, e1))
+        g_tail.replay()
+        eng.add_graph_launches(n_kernels)
+        return static_out
 
     def step(self, frame, stream: int = 0) -> np.ndarray:
         """One frame of one stream (online use).  frame: HWC uint8 array or GPU tensor.  State persists;
@@ -105,5 +144,7 @@ class BaseTracker(object):
         if getattr(self, "_steps", 0) % self.sequence_length == 0:
             self.head.reset(-1)
         self._steps = getattr(self, "_steps", 0) + 1
-        fv, xin = self._tracker_inputs(t[None].contiguous())
+        t = t[None].contiguous()
+        self.model_detector.engine.forward(t)
+        fv, xin = self._tracker_inputs_from_state(1, t.shape[2], t.shape[1])
         return self.head.step(fv, xin)[0].cpu().numpy()

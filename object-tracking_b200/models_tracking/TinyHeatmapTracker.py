@@ -30,8 +30,8 @@ class TinyHeatmapTracker(BaseTracker):
         self.head.set_weights(w)
         self.model_tracker = self.head
 
-    def _tracker_inputs(self, frames: torch.Tensor):
-        fv, _, heat, _ = self._detect_and_pool(frames, self.HEATMAP_SIZE)
+    def _tracker_inputs_from_state(self, B: int, W: int, H: int):
+        fv, _, heat, _ = self._decode_and_pool(B, W, H, self.HEATMAP_SIZE)
         return fv, heat
 
     def rectangles(self, heat_out: torch.Tensor, thresh: float = 0.75) -> torch.Tensor:

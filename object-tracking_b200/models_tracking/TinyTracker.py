@@ -29,6 +29,6 @@ class TinyTracker(BaseTracker):
         self.head.set_weights(w)
         self.model_tracker = self.head
 
-    def _tracker_inputs(self, frames: torch.Tensor):
-        fv, det_in, _, _ = self._detect_and_pool(frames)
+    def _tracker_inputs_from_state(self, B: int, W: int, H: int):
+        fv, det_in, _, _ = self._decode_and_pool(B, W, H)
         return fv, det_in

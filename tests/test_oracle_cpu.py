@@ -114,3 +114,9 @@ def test_param_and_traffic_counts_match_survey():
     assert t["Wr"] == 8_508_305
     assert abs(t["flops"] - 29.464e9) < 0.01e9
     assert abs(W.forward_bytes(80, 416, batch=1) - 273.6e6) < 0.1e6
+
+
+def test_u8_normalisation_needs_no_table():
+    # conv_1 computes float(u)/255.f in fp32; the reference computes image/255. in float64 and Keras casts to fp32
+    u = np.arange(256)
+    assert np.array_equal((u.astype(np.float64) / 255.0).astype(np.float32), u.astype(np.float32) / np.float32(255.0))
