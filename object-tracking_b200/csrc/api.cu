@@ -35,6 +35,11 @@ static int fail(int code, const char *fmt, ...) {
         if (e__ != cudaSuccess) return fail(-2, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
     } while (0)
 
+// shared with darknet_compat.cu
+int b2t_fail_internal(int code, const char *msg) {
+    snprintf(g_err, sizeof g_err, "%s", msg);
+    return code;
+}
 extern "C" const char *b2t_last_error(void) { return g_err; }
 extern "C" int b2t_version(void) { return 100; }
 

@@ -60,3 +60,16 @@ def test_compute_without_gpu_fails_loudly():
     from object_tracking_b200.engine import DetectorEngine
     with pytest.raises(N.B2TError):
         DetectorEngine(n_class=2)
+
+
+def test_library_exports_the_reference_darknet_abi():
+    """Every symbol models_detection/YOLO.py:58-119 binds (and include/darknet_compat.h declares)."""
+    import ctypes
+    lib = ctypes.CDLL(N.LIB_PATH)
+    src = open(os.path.join(ROOT, "include", "darknet_compat.h")).read()
+    bound_by_yolo_py = ["network_width", "network_height", "cuda_set_device", "get_network_boxes", "free_detections",
+                        "free_ptrs", "load_network", "do_nms_obj", "free_image", "get_metadata", "load_image_color",
+                        "rgbgr_image", "network_predict_image", "network_extract_feat", "layer_dims"]
+    for n in bound_by_yolo_py + ["network_predict", "make_image", "free_network"]:
+        assert re.search(r"\b%s\s*\(" % n, src), f"{n} not declared in darknet_compat.h"
+        assert hasattr(lib, n), f"{n} not exported"
