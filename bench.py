@@ -198,9 +198,10 @@ def main_b200(args):
 
     # synthetic clip(s): S streams x 300 frames, seeded per global stream id; resident copy + pinned host copy
     n_win = CLIP // T
+    from object_tracking_b200.sharding import shard_streams
     clips = []
-    for s in range(S):
-        rng = np.random.default_rng(1234 + rank * S + s)
+    for gid in shard_streams(world * S, rank, world):          # global stream ids owned by this rank
+        rng = np.random.default_rng(1234 + gid)
         clips.append(rng.integers(0, 256, (CLIP, IMAGE, IMAGE, 3), dtype=np.uint8))
     host = torch.from_numpy(np.stack(clips)).pin_memory()            # (S, 300, H, W, 3)
     dev = host.cuda(non_blocking=True)

@@ -7,3 +7,18 @@ alias package at the repo root.  Sub-packages ``models_detection`` / ``models_tr
 (see INTEGRATION.md).
 """
 __version__ = "0.1.0"
+
+
+def install_reference_aliases() -> None:
+    """Make the reference's module names resolve to the B200 plugin classes, so that code written against
+    ktzsh/object-tracking (``trainer.py:12-14`` importlib lookup, ``from models_detection.KerasYOLO import
+    KerasYOLO``, ``from utility.utils import decode_netout``) runs unchanged.  See INTEGRATION.md section 2."""
+    import importlib
+    import sys
+    pkg = __name__
+    for sub, mods in (("models_detection", ("KerasYOLO", "YOLO")),
+                      ("models_tracking", ("BaseTracker", "TinyTracker", "TinyHeatmapTracker", "MultiObjDetTracker")),
+                      ("utility", ("utils",))):
+        sys.modules[sub] = importlib.import_module(f"{pkg}.{sub}")
+        for m in mods:
+            sys.modules[f"{sub}.{m}"] = importlib.import_module(f"{pkg}.{sub}.{m}")

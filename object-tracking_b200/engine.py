@@ -107,9 +107,8 @@ class DetectorEngine:
 
     def broadcast_weights(self, src: int = 0) -> None:
         """The only collective on the path: one NCCL broadcast of the packed blob at init."""
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.broadcast(self.blob, src=src)
+        from .sharding import broadcast_blob
+        broadcast_blob(self.blob, src=src)
 
     # ---------------------------------------------------------------- forward
     def forward(self, frames: torch.Tensor) -> torch.Tensor:

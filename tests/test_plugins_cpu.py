@@ -1,0 +1,105 @@
+"""CPU suite, part 3: host-side logic of the plugin layer that needs no GPU -- reference-name aliasing, config
+defaults, class constants, stream sharding, and the world_size-2 gloo path of the weight broadcast."""
+import importlib
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_module_names_resolve():
+    import object_tracking_b200 as b2t
+    b2t.install_reference_aliases()
+    for name in ("TinyTracker", "TinyHeatmapTracker", "MultiObjDetTracker"):
+        cls = getattr(importlib.import_module("models_tracking." + name), name)     # trainer.py:12-14
+        assert cls.__name__ == name
+    from models_detection.KerasYOLO import KerasYOLO
+    from utility.utils import BoundBox, bbox_iou, decode_netout, normalize  # noqa: F401
+    assert KerasYOLO.OBJ_THRESHOLD == 0.5 and KerasYOLO.NMS_THRESHOLD == 0.45 and KerasYOLO.BOX == 5
+    assert len(KerasYOLO.LABELS) == 80 and KerasYOLO.MAX_BOX_PER_IMAGE == 50
+    assert KerasYOLO.ANCHORS[:2] == [0.57273, 0.677385] and KerasYOLO.weight_path == 'darknet/yolov2.weights'
+    from models_tracking.MultiObjDetTracker import MultiObjDetTracker
+    assert MultiObjDetTracker.CLASS == 12 and MultiObjDetTracker.SEQUENCE_LENGTH == 4
+
+
+def test_host_helpers_follow_reference_semantics():
+    from object_tracking_b200.utility.utils import BoundBox, bbox_iou, softmax, WeightReader
+    a = BoundBox(0.5, 0.5, 0.2, 0.2, 0.9, np.array([0.1, 0.8]))
+    b = BoundBox(0.55, 0.5, 0.2, 0.2, 0.9, np.array([0.7, 0.2]))
+    assert a.get_label() == 1 and abs(a.get_score() - 0.8) < 1e-12
+    assert abs(bbox_iou(a, b) - (0.15 * 0.2) / (0.08 - 0.15 * 0.2)) < 1e-9
+    x = np.array([[0.0, -150.0], [1.0, 2.0]])
+    s = softmax(x)                                   # global max / global-min rescale of utils.py:262-270
+    assert np.allclose(s.sum(-1), 1.0) and s[0, 1] > np.exp(-150.0)
+    import tempfile
+    with tempfile.NamedTemporaryFile(suffix=".weights") as f:
+        np.arange(10, dtype=np.float32).tofile(f.name)
+        r = WeightReader(f.name)
+        assert list(r.read_bytes(3)) == [4.0, 5.0, 6.0]          # 4-word header skipped (utils.py:138-148)
+
+
+def test_config_defaults_match_reference_config_json():
+    from object_tracking_b200.models_detection._common import load_config
+    c = load_config(None) if not os.path.exists("config.json") else load_config({})
+    c = load_config(None)
+    assert c["model_detector"]["fv_layer"] == 25 and c["model_detector"]["nms"] == 0.45
+    assert c["model_tracker"]["sequence_length"] == 4 and c["model_tracker"]["lstm_units"] == 512
+    assert c["train"]["pool"] == "Global" and c["train"]["classes"] == ["Person", "Car"]
+
+
+def test_stream_sharding_is_a_partition():
+    from object_tracking_b200.sharding import shard_streams
+    for n_streams, world in ((32, 8), (64, 8), (5, 2), (1, 4), (7, 3)):
+        seen = []
+        for r in range(world):
+            mine = shard_streams(n_streams, r, world)
+            assert mine == sorted(mine)
+            seen += mine
+        assert sorted(seen) == list(range(n_streams))
+        sizes = [len(shard_streams(n_streams, r, world)) for r in range(world)]
+        assert max(sizes) - min(sizes) <= 1
+    assert shard_streams(32, 3, 8) == [3, 11, 19, 27]             # stream i -> GPU i mod n
+
+
+@pytest.mark.timeout(180)
+def test_weight_broadcast_protocol_world_size_2_gloo(tmp_path):
+    """The N>1 init path on CPU/gloo: rank 0 packs the blob, the other rank receives it with one broadcast and
+    ends up bit-identical; streams are partitioned without overlap."""
+    script = tmp_path / "worker.py"
+    script.write_text(textwrap.dedent(f"""
+        import os, sys, hashlib
+        sys.path.insert(0, {ROOT!r})
+        import numpy as np, torch, torch.distributed as dist
+        from object_tracking_b200.sharding import shard_streams, broadcast_blob
+        from object_tracking_b200 import weights as W
+        dist.init_process_group("gloo")
+        rank, world = dist.get_rank(), dist.get_world_size()
+        n = 1 << 20
+        if rank == 0:
+            w = W.synthetic_lstm_weights(64, 32, 4, seed=5)
+            blob = torch.from_numpy(np.concatenate([v.ravel() for v in w.values()]).view(np.uint8).copy())
+            blob = torch.cat([blob, torch.zeros(n - blob.numel(), dtype=torch.uint8)])
+        else:
+            blob = torch.empty(n, dtype=torch.uint8)
+        broadcast_blob(blob, src=0)
+        digest = hashlib.sha1(blob.numpy().tobytes()).hexdigest()
+        mine = shard_streams(5, rank, world)
+        out = [None] * world
+        dist.all_gather_object(out, (digest, mine))
+        if rank == 0:
+            assert out[0][0] == out[1][0], "blob differs after broadcast"
+            assert sorted(out[0][1] + out[1][1]) == [0, 1, 2, 3, 4]
+            print("OK", out)
+        dist.destroy_process_group()
+    """))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29577", str(script)],
+                       capture_output=True, text=True, timeout=170, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "OK" in r.stdout
