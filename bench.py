@@ -217,7 +217,7 @@ def main_b200(args):
 
     # ---- value: inputs resident in HBM
     for i in range(args.warmup):
-        trk.track_windows(window(dev, i).contiguous())
+        trk.track_windows(window(dev, i))
     eng.forward_events = []
     barrier()
     sampler = ClockSampler(local)
@@ -227,7 +227,7 @@ def main_b200(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
-        out = trk.track_windows(window(dev, args.warmup + i).contiguous())
+        out = trk.track_windows(window(dev, args.warmup + i))
     e1.record()
     barrier()
     launches = eng.launches - l0

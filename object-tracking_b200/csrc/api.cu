@@ -56,6 +56,7 @@ struct ActBuf {              // split-plane activation tensor sized for max_batc
 
 struct ConvLayer {
     int index = 0, k = 1, cin = 0, cin_pad = 0, cout = 0;
+    int kchunk = 64;                              // channels per K chunk: 64 (128-byte rows) or 32 (64-byte rows)
     bool act = true, pool = false;
     int H = 0, W = 0;
     int in_buf = -1, in_ch_off = 0;               // input view
@@ -126,7 +127,8 @@ static void choose_halo_tile(int H, int W, int ksize, bool pool, ConvLayer &l) {
     // short K and many tiles -> the small shape (two CTAs per SM overlap each other's prologue/epilogue)
     const char *env = getenv("B2T_SMALL");
     const int small_mode = env ? atoi(env) : -1;
-    l.h_small = small_mode >= 0 ? (small_mode != 0 && H >= 26) : (l.cin_pad / 64 * taps <= 36 && H >= 52);
+    const int kbytes = l.kchunk * 2;
+    l.h_small = small_mode >= 0 ? (small_mode != 0 && H >= 26) : (l.cin_pad / l.kchunk * taps <= 36 && H >= 52);
     const int max_rows = l.h_small ? 176 : 256, max_n = l.h_small ? 128 : 256;
     double best = 1e30;
     for (int nx = 1; nx <= 16; ++nx) {
@@ -143,12 +145,12 @@ static void choose_halo_tile(int H, int W, int ksize, bool pool, ConvLayer &l) {
             if (rows * P > max_rows || N > max_n || (pool && N > 240)) break;
             const int tiles_x = (W + C - 1) / C, tiles_y = (H + R - 1) / R;
             // cycles per (tap, chunk) of one tile: 12 MMAs of 128 x N x 16 vs. the L2->SM stream (~42 B/clk/SM)
-            const double t_mma = 6.0 * N, t_l2 = (32768.0 + 2.0 * rows * P * 128 / taps) / 42.0;
+            const double t_mma = 6.0 * N * kbytes / 128, t_l2 = (256.0 * kbytes + 2.0 * rows * P * kbytes / taps) / 42.0;
             const double cost = (t_mma > t_l2 ? t_mma : t_l2) * tiles_x * tiles_y;
             if (cost < best - 1e-9) {
                 best = cost;
                 l.hC = C; l.hP = P; l.hR = R; l.hN = N; l.h_rows = rows;
-                l.h_plane_bytes = (int)align_up((size_t)rows * P * 128, 1024);
+                l.h_plane_bytes = (int)align_up((size_t)rows * P * kbytes, 1024);
             }
         }
     }
@@ -197,7 +199,9 @@ static int choose_splits(int tiles, int chunks, int n_sm) {
 // ------------------------------------------------------------------------------------------------ create
 static ConvLayer &new_conv(b2t_ctx *c, int index, int k, int cin, int cout, bool act, bool pool, int H, int W) {
     ConvLayer l;
-    l.index = index; l.k = k; l.cin = cin; l.cin_pad = round_up(cin, 64); l.cout = cout;
+    l.index = index; l.k = k; l.cin = cin; l.cout = cout;
+    l.kchunk = (cin == 32 && c->cfg.engine != 2) ? 32 : 64;   // conv_2: 32 input channels, SWIZZLE_64B rows
+    l.cin_pad = round_up(cin, l.kchunk);
     l.act = act; l.pool = pool; l.H = H; l.W = W;
     l.ldw = k * k * l.cin_pad;
     l.BN = cout >= 128 ? 128 : 64;
@@ -268,7 +272,8 @@ extern "C" int b2t_create(const b2t_config *cfg, b2t_ctx **out) {
                 l.out_buf = add_buf(c, nm, H, H, round_up(l.cout, 64));
                 if (i == 13) skip_buf = l.out_buf;
             }
-            l.pout_buf = add_buf(c, std::string("pool_") + std::to_string(i), H / 2, H / 2, round_up(l.cout, 64));
+            l.pout_buf = add_buf(c, std::string("pool_") + std::to_string(i), H / 2, H / 2,
+                                 (i == 1 && cfg->engine != 2) ? 32 : round_up(l.cout, 64));
         } else {
             l.out_buf = add_buf(c, nm, H, H, round_up(l.cout, 64));
         }
@@ -347,7 +352,7 @@ extern "C" int b2t_create(const b2t_config *cfg, b2t_ctx **out) {
                 if (s == 1) continue;
             } else if (cfg->engine == B2T_ENGINE_TCGEN05) {
                 const int ctas = ((l.W + l.hC - 1) / l.hC) * ((l.H + l.hR - 1) / l.hR) * ((l.cout + 127) / 128) * bsz;
-                s = choose_splits_halo(ctas, l.cin_pad / 64, l.k * l.k, 148);
+                s = choose_splits_halo(ctas, l.cin_pad / l.kchunk, l.k * l.k, 148);
                 if (s == 1) continue;
             }
             const size_t need = s * (size_t)bsz * l.H * l.W * ldp * 4;
@@ -533,10 +538,11 @@ extern "C" int b2t_set_convlstm_weights(b2t_ctx *c, const float *kernel, const f
 
 // ------------------------------------------------------------------------------------------------ finalize
 static int make_tmap(b2t_ctx *c, CUtensorMap *tm, void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides,
-                     const cuuint32_t *box) {
+                     const cuuint32_t *box, bool sw64 = false) {
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = c->encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, base, dims, strides, box, es,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, sw64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(-2, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return 0;
@@ -579,19 +585,24 @@ extern "C" int b2t_finalize(b2t_ctx *c, int upload, void *stream) {
         cuuint64_t dims[4] = {(cuuint64_t)l.cin_pad, (cuuint64_t)l.W, (cuuint64_t)l.H, (cuuint64_t)nb};
         cuuint64_t strides[3] = {(cuuint64_t)in.C * 2, (cuuint64_t)in.C * 2 * l.W, (cuuint64_t)in.C * 2 * l.W * l.H};
         cuuint32_t box[4] = {64, (cuuint32_t)l.TW, (cuuint32_t)l.TH, 1};
-        if ((rc = make_tmap(c, &l.tmA_hi, in.hi + l.in_ch_off, 4, dims, strides, box))) return rc;
-        if ((rc = make_tmap(c, &l.tmA_lo, in.hi + in.plane + l.in_ch_off, 4, dims, strides, box))) return rc;
+        if (l.kchunk == 64) {
+            if ((rc = make_tmap(c, &l.tmA_hi, in.hi + l.in_ch_off, 4, dims, strides, box))) return rc;
+            if ((rc = make_tmap(c, &l.tmA_lo, in.hi + in.plane + l.in_ch_off, 4, dims, strides, box))) return rc;
+        }
         cuuint64_t wd[2] = {(cuuint64_t)l.ldw, (cuuint64_t)l.cout};
         cuuint64_t wst[1] = {(cuuint64_t)l.ldw * 2};
         cuuint32_t wbox[2] = {64, (cuuint32_t)l.BN};
-        if ((rc = make_tmap(c, &l.tmB_hi, c->d_blob + l.off_whi, 2, wd, wst, wbox))) return rc;
-        if ((rc = make_tmap(c, &l.tmB_lo, c->d_blob + l.off_wlo, 2, wd, wst, wbox))) return rc;
-        cuuint32_t xbox[4] = {64, (cuuint32_t)l.hP, (cuuint32_t)l.h_rows, 1};
-        if ((rc = make_tmap(c, &l.tmX_hi, in.hi + l.in_ch_off, 4, dims, strides, xbox))) return rc;
-        if ((rc = make_tmap(c, &l.tmX_lo, in.hi + in.plane + l.in_ch_off, 4, dims, strides, xbox))) return rc;
-        cuuint32_t wbox2[2] = {64, 128};
-        if ((rc = make_tmap(c, &l.tmW_hi, c->d_blob + l.off_whi, 2, wd, wst, wbox2))) return rc;
-        if ((rc = make_tmap(c, &l.tmW_lo, c->d_blob + l.off_wlo, 2, wd, wst, wbox2))) return rc;
+        if (l.kchunk == 64) {
+            if ((rc = make_tmap(c, &l.tmB_hi, c->d_blob + l.off_whi, 2, wd, wst, wbox))) return rc;
+            if ((rc = make_tmap(c, &l.tmB_lo, c->d_blob + l.off_wlo, 2, wd, wst, wbox))) return rc;
+        }
+        const bool sw64 = l.kchunk == 32;
+        cuuint32_t xbox[4] = {(cuuint32_t)l.kchunk, (cuuint32_t)l.hP, (cuuint32_t)l.h_rows, 1};
+        if ((rc = make_tmap(c, &l.tmX_hi, in.hi + l.in_ch_off, 4, dims, strides, xbox, sw64))) return rc;
+        if ((rc = make_tmap(c, &l.tmX_lo, in.hi + in.plane + l.in_ch_off, 4, dims, strides, xbox, sw64))) return rc;
+        cuuint32_t wbox2[2] = {(cuuint32_t)l.kchunk, 128};
+        if ((rc = make_tmap(c, &l.tmW_hi, c->d_blob + l.off_whi, 2, wd, wst, wbox2, sw64))) return rc;
+        if ((rc = make_tmap(c, &l.tmW_lo, c->d_blob + l.off_wlo, 2, wd, wst, wbox2, sw64))) return rc;
     }
     c->finalized = true;
     return 0;
@@ -615,7 +626,8 @@ static Dest dest_planes(const b2t_ctx *c, int buf, int ch_off, int srcH, int src
 static int run_conv(b2t_ctx *c, ConvLayer &l, int B, float *f32_dst, cudaStream_t st) {
     ConvParams p;
     memset(&p, 0, sizeof p);
-    p.B = B; p.H = l.H; p.W = l.W; p.ksize = l.k; p.cin_chunks = l.cin_pad / 64; p.Cout = l.cout;
+    p.B = B; p.H = l.H; p.W = l.W; p.ksize = l.k; p.cin_chunks = l.cin_pad / l.kchunk; p.Cout = l.cout;
+    p.kbytes = l.kchunk * 2;
     p.TW = l.TW; p.TH = l.TH;
     p.tiles_x = (l.W + l.TW - 1) / l.TW; p.tiles_y = (l.H + l.TH - 1) / l.TH;
     p.chunks_total = l.k * l.k * p.cin_chunks;

@@ -106,19 +106,20 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_consta
         if (elect_one()) {
             int ws = 0;
             uint32_t wphase = 0;
-            const uint32_t halo_tx = 2u * p.h_rows * p.hP * 128u;
+            const uint32_t halo_tx = 2u * p.h_rows * p.hP * p.kbytes, w_tx = 2u * 128u * p.kbytes;
+            const int kelems = p.kbytes / 2;
             for (int it = 0; it < n_chunks; ++it) {
                 const int ci = c_begin + it, hb = it % kHaloBufs;
                 mbar_wait(&halo_empty[hb], ((it / kHaloBufs) & 1) ^ 1);
                 mbar_expect_tx(&halo_full[hb], halo_tx);
                 uint8_t *hdst = s_halo + hb * kHaloBufBytes;
-                tma_load_4d(&tmX_hi, &halo_full[hb], hdst, ci * 64, x0 - pad, y0 - pad, b, kEvictNormal);
-                tma_load_4d(&tmX_lo, &halo_full[hb], hdst + p.h_plane_bytes, ci * 64, x0 - pad, y0 - pad, b, kEvictNormal);
+                tma_load_4d(&tmX_hi, &halo_full[hb], hdst, ci * kelems, x0 - pad, y0 - pad, b, kEvictNormal);
+                tma_load_4d(&tmX_lo, &halo_full[hb], hdst + p.h_plane_bytes, ci * kelems, x0 - pad, y0 - pad, b, kEvictNormal);
                 for (int tap = 0; tap < taps; ++tap) {
                     mbar_wait(&w_empty[ws], wphase ^ 1);
-                    mbar_expect_tx(&w_full[ws], kWStageBytes);
+                    mbar_expect_tx(&w_full[ws], w_tx);
                     uint8_t *wdst = s_w + ws * kWStageBytes;
-                    const int kcoord = (tap * p.cin_chunks + ci) * 64;
+                    const int kcoord = (tap * p.cin_chunks + ci) * kelems;
                     tma_load_2d(&tmW_hi, &w_full[ws], wdst, kcoord, cout0, kEvictLast);
                     tma_load_2d(&tmW_lo, &w_full[ws], wdst + kWTileBytes, kcoord, cout0, kEvictLast);
                     if (++ws == kWStages) { ws = 0; wphase ^= 1; }
@@ -140,13 +141,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_consta
                 tc_fence_after();
                 if (elect_one()) {
                     const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
-                    const uint32_t shift = (kh * p.hP + kw) * 128;
+                    const uint32_t shift = (kh * p.hP + kw) * p.kbytes;
+                    const int ksteps = p.kbytes / 32;
                     const uint32_t wh = smem_u32(s_w + ws * kWStageBytes), wl = wh + kWTileBytes;
                     const uint32_t t_main = tmem_base + (mma_it % n_main) * N;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint64_t dwh = umma_desc_sw128(wh + k * 32), dwl = umma_desc_sw128(wl + k * 32);
-                        const uint64_t dxh = umma_desc_sw128(xh + shift + k * 32), dxl = umma_desc_sw128(xl + shift + k * 32);
+#pragma unroll 1
+                    for (int k = 0; k < ksteps; ++k) {
+                        const uint64_t dwh = umma_desc_kmajor(wh + k * 32, p.kbytes), dwl = umma_desc_kmajor(wl + k * 32, p.kbytes);
+                        const uint64_t dxh = umma_desc_kmajor(xh + shift + k * 32, p.kbytes),
+                                       dxl = umma_desc_kmajor(xl + shift + k * 32, p.kbytes);
                         umma_f16(t_corr, dwl, dxh, idesc, (mma_it | k) ? 1u : 0u);
                         umma_f16(t_corr, dwh, dxl, idesc, 1u);
                         umma_f16(t_main, dwh, dxh, idesc, (mma_it >= n_main || k) ? 1u : 0u);

@@ -48,6 +48,7 @@ struct ConvParams {
     int h_rows;             // patch rows loaded per channel chunk (hR + 2*pad [+1 when the row wrap trick is used])
     int h_plane_bytes;      // bytes between the hi and lo patch in shared memory
     int h_tiles_x, h_tiles_y;
+    int kbytes;             // bytes of one K-chunk row: 128 (64 channels, SWIZZLE_128B) or 64 (32 channels, SWIZZLE_64B)
 };
 
 __device__ __forceinline__ float leaky(float v) { return v > 0.f ? v : 0.1f * v; }

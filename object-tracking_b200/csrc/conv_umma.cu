@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const SimtView v, const 
         pb = int(m / ((long long)p.W * p.H));
     }
     const int pad = p.ksize >> 1;
-    const int cin_pad = p.cin_chunks * 64;
+    const int cin_pad = p.cin_chunks * (p.kbytes / 2);
     for (int tap = 0; tap < p.ksize * p.ksize; ++tap) {
         const int kh = tap / p.ksize, kw = tap % p.ksize;
         const int yy = py + kh - pad, xx = px + kw - pad;
@@ -375,7 +375,9 @@ __global__ void __launch_bounds__(128) conv1_direct_kernel(const Conv1Params p) 
         }
     }
     __syncthreads();
-    const int half = threadIdx.x & 1, lx = (threadIdx.x >> 1) % kC1W, ly = (threadIdx.x >> 1) / kC1W;
+    // channel half is warp-uniform (warps 0,1 -> channels 0..15, warps 2,3 -> 16..31): the weight reads below are
+    // shared-memory broadcasts (1 wavefront) instead of 4-way split loads
+    const int half = threadIdx.x >> 6, lx = threadIdx.x % kC1W, ly = (threadIdx.x >> 5) & 1;
     const int xq = xq0 + lx, yq = yq0 + ly;
     float acc[4][16];
 #pragma unroll

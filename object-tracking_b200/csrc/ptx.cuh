@@ -113,6 +113,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     return d;
 }
 
+// Same for rows of `row_bytes` = 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B, layout type 4, 8-row atoms of 512 B).
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t saddr, uint32_t row_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>((8 * row_bytes) >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(row_bytes == 128 ? 2 : 4) << 61;
+    return d;
+}
+
 // kind::f16 instruction descriptor: D=f32, A=B=fp16 (format 0), both K-major, M x N tile.
 __host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N) {
     return (1u << 4)          // c_format = F32

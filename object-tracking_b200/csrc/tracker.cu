@@ -24,33 +24,65 @@ constexpr int kMaxStreams = 8;      // streams per launch group
 __device__ __forceinline__ float hard_sigmoid_f(float x) { return fminf(fmaxf(fmaf(0.2f, x, 0.5f), 0.f), 1.f); }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
 
+// Thread layout: 4 lanes cover the 16 columns of one packed weight row (one float4 each), a warp covers 8
+// consecutive rows (512 contiguous bytes per load instruction), the CTA's 8 warps cover 64 rows per iteration and
+// the row loop is unrolled x4 so that every thread keeps 4 independent 16-byte loads in flight (the kernel is a
+// latency-bound GEMV: memory-level parallelism is what buys bandwidth).
 __global__ void __launch_bounds__(kLstmThreads) lstm_gates_kernel(const LstmParams p) {
-    __shared__ float red[16][16][kMaxStreams];
+    __shared__ float red[8][16][kMaxStreams];
     const int ub = blockIdx.x;
     const int s0 = blockIdx.y * kMaxStreams;                   // first row (stream) of this CTA's group
     const int nS = min(kMaxStreams, p.S - s0);
-    const int col = threadIdx.x & 15, ks = threadIdx.x >> 4;   // 16 columns x 16 row groups
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c4 = lane & 3, rq = threadIdx.x >> 2;            // column quad, row slot (0..63)
     const int n_x = p.n_feat + p.n_det, n_rows = n_x + p.units;
-    const float *w = p.wp + (long long)ub * n_rows * 16;
+    const float4 *w = reinterpret_cast<const float4 *>(p.wp + (long long)ub * n_rows * 16) + c4;
     const int k_lo = p.mode == 2 ? n_x : 0, k_hi = p.mode == 1 ? n_x : n_rows;
-    float acc[kMaxStreams];
+    float acc[kMaxStreams][4];
 #pragma unroll
-    for (int s = 0; s < kMaxStreams; ++s) acc[s] = 0.f;
-    for (int k = k_lo + ks; k < k_hi; k += 16) {
-        const float wv = __ldg(w + (long long)k * 16 + col);
+    for (int s = 0; s < kMaxStreams; ++s)
 #pragma unroll
-        for (int s = 0; s < kMaxStreams; ++s) {
-            if (s < nS) {
-                float xv;
-                if (k < p.n_feat) xv = __ldg(p.fv + (long long)(s0 + s) * p.fv_stride + k);
-                else if (k < n_x) xv = __ldg(p.det + (long long)(s0 + s) * p.det_stride + (k - p.n_feat));
-                else xv = __ldg(p.h_in + (long long)(s0 + s) * p.units + (k - n_x));
-                acc[s] = fmaf(xv, wv, acc[s]);
+        for (int j = 0; j < 4; ++j) acc[s][j] = 0.f;
+    auto xval = [&](int s, int k) -> float {
+        if (k < p.n_feat) return __ldg(p.fv + (long long)(s0 + s) * p.fv_stride + k);
+        if (k < n_x) return __ldg(p.det + (long long)(s0 + s) * p.det_stride + (k - p.n_feat));
+        return __ldg(p.h_in + (long long)(s0 + s) * p.units + (k - n_x));
+    };
+    for (int k0 = k_lo + rq; k0 < k_hi; k0 += 4 * 64) {
+        float4 wv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = k0 + u * 64;
+            wv[u] = k < k_hi ? __ldg(w + (long long)k * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = k0 + u * 64;
+            if (k < k_hi) {
+#pragma unroll
+                for (int s = 0; s < kMaxStreams; ++s) {
+                    if (s < nS) {
+                        const float xv = xval(s, k);
+                        acc[s][0] = fmaf(xv, wv[u].x, acc[s][0]);
+                        acc[s][1] = fmaf(xv, wv[u].y, acc[s][1]);
+                        acc[s][2] = fmaf(xv, wv[u].z, acc[s][2]);
+                        acc[s][3] = fmaf(xv, wv[u].w, acc[s][3]);
+                    }
+                }
             }
         }
     }
+    // reduce the 8 row slots of a warp (lane bits 2..4), fixed order, then the 8 warps through shared memory
 #pragma unroll
-    for (int s = 0; s < kMaxStreams; ++s) red[ks][col][s] = acc[s];
+    for (int s = 0; s < kMaxStreams; ++s)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float v = acc[s][j];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if (lane < 4) red[warp][c4 * 4 + j][s] = v;
+        }
     __syncthreads();
     // 4 units x nS streams finish
     if (threadIdx.x < kUnitsPerBlock * nS) {
@@ -60,7 +92,7 @@ __global__ void __launch_bounds__(kLstmThreads) lstm_gates_kernel(const LstmPara
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             float t = 0.f;
-            for (int r = 0; r < 16; ++r) t += red[r][g * 4 + uu][s - s0];
+            for (int r = 0; r < 8; ++r) t += red[r][g * 4 + uu][s - s0];
             z[g] = t + (p.mode == 2 ? p.zx[(long long)s * p.zx_stride + g * p.units + unit] : p.bias[g * p.units + unit]);
         }
         if (p.mode == 1) {

@@ -105,7 +105,7 @@ class BaseTracker(object):
         g = self._graphs.get(key)
         if g is None:
             static_in = torch.empty((S * T, H, W, 3), dtype=frames.dtype, device=frames.device)
-            static_in.copy_(frames.reshape(S * T, H, W, 3))
+            static_in.view(S, T, H, W, 3).copy_(frames)
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):                      # warm-up outside capture (allocations, lazy init)
@@ -121,7 +121,7 @@ class BaseTracker(object):
                 static_out = self._tail(S, T, W, H, reset)
             g = self._graphs[key] = (g_fwd, g_tail, static_in, static_out, eng.lib.b2t_launch_count(eng.h) - n0)
         g_fwd, g_tail, static_in, static_out, n_kernels = g
-        static_in.copy_(frames.reshape(S * T, H, W, 3), non_blocking=True)
+        static_in.view(S, T, H, W, 3).copy_(frames, non_blocking=True)     # strided views welcome: one copy
         ev = eng.forward_events
         if ev is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -16,9 +16,13 @@
 using namespace b2t;
 
 constexpr int N = 128, ROWS_B = 160;
+#ifndef ROWB
+#define ROWB 128          // bytes per K-major row: 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
+#endif
+constexpr int KEL = ROWB / 2;   // K elements per row
 
 __device__ __forceinline__ uint64_t desc_with_base(uint32_t saddr, uint32_t base_off) {
-    return umma_desc_sw128(saddr) | (uint64_t(base_off & 7) << 49);
+    return umma_desc_kmajor(saddr, ROWB) | (uint64_t(base_off & 7) << 49);
 }
 
 __global__ void __launch_bounds__(128, 1) probe_kernel(const __grid_constant__ CUtensorMap tmA,
@@ -26,8 +30,8 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const __grid_constant__ C
                                                        int use_base) {
     extern __shared__ uint8_t raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
-    uint8_t *sA = smem, *sB = smem + 128 * 128;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(sB + ROWS_B * 128);
+    uint8_t *sA = smem, *sB = smem + 128 * ROWB;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sB + ROWS_B * ROWB);
     uint64_t *done = bar + 1;
     uint32_t *slot = reinterpret_cast<uint32_t *>(done + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -42,15 +46,15 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const __grid_constant__ C
     tc_fence_after();
     const uint32_t tacc = *slot;
     if (warp == 0 && elect_one()) {
-        mbar_expect_tx(bar, 128 * 128 + ROWS_B * 128);
+        mbar_expect_tx(bar, 128 * ROWB + ROWS_B * ROWB);
         tma_load_2d(&tmA, bar, sA, 0, 0, kEvictNormal);
         tma_load_2d(&tmB, bar, sB, 0, 0, kEvictNormal);
         mbar_wait(bar, 0);
         tc_fence_after();
         const uint32_t idesc = umma_idesc_f16(128, N);
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t a = smem_u32(sA) + k * 32, b = smem_u32(sB) + r0 * 128 + k * 32;
-            const uint64_t da = umma_desc_sw128(a);
+        for (int k = 0; k < ROWB / 32; ++k) {
+            const uint32_t a = smem_u32(sA) + k * 32, b = smem_u32(sB) + r0 * ROWB + k * 32;
+            const uint64_t da = umma_desc_kmajor(a, ROWB);
             const uint64_t db = desc_with_base(b, use_base ? ((b >> 7) & 7) : 0);
             umma_f16(tacc, da, db, idesc, k ? 1u : 0u);
         }
@@ -71,7 +75,7 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const __grid_constant__ C
 }
 
 int main() {
-    std::vector<__half> A(128 * 64), B(ROWS_B * 64);
+    std::vector<__half> A(128 * KEL), B(ROWS_B * KEL);
     srand(1);
     for (auto &x : A) x = __float2half((rand() % 17 - 8) / 8.f);
     for (auto &x : B) x = __float2half((rand() % 17 - 8) / 8.f);
@@ -89,19 +93,19 @@ int main() {
     CUtensorMap tA, tB;
     cuuint32_t es[2] = {1, 1};
     {
-        cuuint64_t d[2] = {64, 128}, s[1] = {128};
-        cuuint32_t b[2] = {64, 128};
+        cuuint64_t d[2] = {KEL, 128}, s[1] = {ROWB};
+        cuuint32_t b[2] = {KEL, 128};
         enc(&tA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, dA, d, s, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            (ROWB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     }
     {
-        cuuint64_t d[2] = {64, ROWS_B}, s[1] = {128};
-        cuuint32_t b[2] = {64, ROWS_B};
+        cuuint64_t d[2] = {KEL, ROWS_B}, s[1] = {ROWB};
+        cuuint32_t b[2] = {KEL, ROWS_B};
         CUresult r = enc(&tB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, dB, d, s, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                         (ROWB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r) { printf("encode B failed %d\n", (int)r); return 1; }
     }
-    const int smem = 128 * 128 + ROWS_B * 128 + 1024 + 64;
+    const int smem = 128 * ROWB + ROWS_B * ROWB + 1024 + 64;
     cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     std::vector<float> O(128 * N);
     for (int use_base = 0; use_base < 2; ++use_base)
@@ -115,10 +119,10 @@ int main() {
             for (int m = 0; m < 128; ++m)
                 for (int n = 0; n < N; ++n) {
                     double ref = 0;
-                    for (int k = 0; k < 64; ++k) ref += (double)__half2float(A[m * 64 + k]) * __half2float(B[(r0 + n) * 64 + k]);
+                    for (int k = 0; k < KEL; ++k) ref += (double)__half2float(A[m * KEL + k]) * __half2float(B[(r0 + n) * KEL + k]);
                     worst = fmax(worst, fabs(ref - O[m * N + n]));
                 }
-            printf("base_offset=%s r0=%2d  max|err| = %g  %s\n", use_base ? "addr" : "0   ", r0, worst, worst < 1e-3 ? "OK" : "WRONG");
+            printf("row_bytes=%d base_offset=%s r0=%2d  max|err| = %g  %s\n", ROWB, use_base ? "addr" : "0   ", r0, worst, worst < 1e-3 ? "OK" : "WRONG");
         }
     return 0;
 }
