@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const SimtView v, const 
 // thrashes it and runs 5x slower).
 constexpr int kC1W = 32, kC1H = 2;                       // pooled pixels per block
 constexpr int kC1PW = 2 * kC1W + 2, kC1PH = 2 * kC1H + 2; // input patch incl. halo
-__global__ void __launch_bounds__(128) conv1_direct_kernel(const Conv1Params p) {
+__global__ void __launch_bounds__(128, 4) conv1_direct_kernel(const Conv1Params p) {
     __shared__ __align__(16) float sw[27 * 32];
     __shared__ float sscale[32], sbias[32];
     __shared__ float spatch[kC1PH][kC1PW][3];
@@ -379,11 +379,12 @@ __global__ void __launch_bounds__(128) conv1_direct_kernel(const Conv1Params p) 
     // shared-memory broadcasts (1 wavefront) instead of 4-way split loads
     const int half = threadIdx.x >> 6, lx = threadIdx.x % kC1W, ly = (threadIdx.x >> 5) & 1;
     const int xq = xq0 + lx, yq = yq0 + ly;
-    float acc[4][16];
+    // packed fp32x2 FMAs (sm_100 FFMA2): two output channels per instruction, each lane an IEEE fma
+    float2 acc2[4][8];
 #pragma unroll
     for (int k = 0; k < 4; ++k)
 #pragma unroll
-        for (int i = 0; i < 16; ++i) acc[k][i] = 0.f;
+        for (int i = 0; i < 8; ++i) acc2[k][i] = make_float2(0.f, 0.f);
 #pragma unroll 1
     for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
@@ -391,20 +392,27 @@ __global__ void __launch_bounds__(128) conv1_direct_kernel(const Conv1Params p) 
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 const float4 *wr = reinterpret_cast<const float4 *>(&sw[((kh * 3 + kw) * 3 + c) * 32 + half * 16]);
-                float w[16];
+                float2 w2[8];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const float4 f = wr[i];
-                    w[4 * i] = f.x; w[4 * i + 1] = f.y; w[4 * i + 2] = f.z; w[4 * i + 3] = f.w;
+                    w2[2 * i] = make_float2(f.x, f.y);
+                    w2[2 * i + 1] = make_float2(f.z, f.w);
                 }
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const float a = spatch[2 * ly + (k >> 1) + kh][2 * lx + (k & 1) + kw][c];
+                    const float2 aa = make_float2(a, a);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) acc[k][i] = fmaf(a, w[i], acc[k][i]);
+                    for (int i = 0; i < 8; ++i) acc2[k][i] = __ffma2_rn(aa, w2[i], acc2[k][i]);
                 }
             }
     }
+    float acc[4][16];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { acc[k][2 * i] = acc2[k][i].x; acc[k][2 * i + 1] = acc2[k][i].y; }
     if (xq >= Wq || yq >= Hq) return;
     float mx[16];
 #pragma unroll

@@ -304,3 +304,111 @@ def test_tiny_tracker_window_end_to_end():
     # online stepping gives the same window
     ys = np.stack([trk.step(frames[0, t]) for t in range(4)])
     assert np.abs(ys - y_eager[0].cpu().numpy()).max() < 1e-5
+
+
+def test_yolov2_608_config_c5():
+    """BASELINE config 5 geometry: 608x608 input, 19x19 grid, C=80 (one frame, fp64 oracle)."""
+    w = W.synthetic_yolo_weights(80, seed=0)
+    frames = np.random.default_rng(608).integers(0, 256, (1, 608, 608, 3), dtype=np.uint8)
+    e = _engine(n_class=80, image_size=608, max_batch=1)
+    e.set_weights(w)
+    e.finalize()
+    lg = e.forward(torch.from_numpy(frames).cuda())
+    assert tuple(lg.shape) == (1, 19, 19, 5, 85)
+    o = yolo_oracle.yolo_forward(yolo_oracle.normalize(frames), w, 80, dtype=np.float64)
+    assert np.abs(lg.cpu().numpy() - o["logits"]).max() < 1e-3
+    boxes, counts = e.decode(lg, 0.5, 0.45)
+    ref = decode_oracle.boxes_to_array(decode_oracle.decode_netout(lg.cpu().numpy()[0], 0.5, 0.45, W.ANCHORS, 80))
+    n = int(counts.cpu()[0])
+    assert n == len(ref)
+    assert np.array_equal(boxes.cpu().numpy()[0, :n, 6:8].astype(np.float64), ref[:, 6:8])
+    fv = e.pool_features("conv_feat", 1, "Max").cpu().numpy()[0]          # MaxPooling2D(4,4)+Flatten: 19 -> 4
+    ref_fv = tracker_oracle.pool_features(o["feat"][0], "Max")
+    assert fv.shape == ref_fv.shape == (4 * 4 * 1024,)
+    assert np.abs(fv - ref_fv).max() < 3e-3
+
+
+def test_pool_reference_layout_view():
+    """preprocessing.py:419 reshapes darknet's CHW buffer as (H,W,C) without a transpose."""
+    w = W.synthetic_yolo_weights(2, seed=0)
+    frames = np.random.default_rng(3).integers(0, 256, (1, 416, 416, 3), dtype=np.uint8)
+    e = _engine(n_class=2, max_batch=1)
+    e.set_weights(w)
+    e.finalize()
+    e.forward(torch.from_numpy(frames).cuda())
+    feat = e.extract("conv_feat", 1).cpu().numpy()[0]
+    for pool in ("Global", "Max"):
+        got = e.pool_features("conv_feat", 1, pool, chw_view=True).cpu().numpy()[0]
+        ref = tracker_oracle.pool_features(feat, pool, ref_layout_bug=True)
+        assert np.array_equal(got, ref.astype(np.float32)), pool
+        got = e.pool_features("conv_feat", 1, pool, chw_view=False).cpu().numpy()[0]
+        assert np.array_equal(got, tracker_oracle.pool_features(feat, pool).astype(np.float32)), pool
+
+
+def test_heatmap_tracker_window():
+    from object_tracking_b200.models_tracking.TinyHeatmapTracker import TinyHeatmapTracker
+    cfg = {"model_detector": {"name": "YOLO", "config_file": "cfg/yolov2.cfg", "meta_file": "cfg/coco.data",
+                              "weights_file": "none.weights", "fv_layer": 25, "nms": 0.45, "thresh": 0.5, "hier_thresh": 0.5},
+           "model_tracker": {"name": "TinyHeatmapTracker", "lstm_units": 512, "sequence_length": 4, "heatmap_size": 32},
+           "train": {"cpu_only": 0, "dgpu_id": 0, "tgpu_id": 0, "pool": "Global", "batch_size": 4, "max_epochs": 0,
+                     "tensorboard_dir": "logs/", "saved_model_dir": "models/", "classes": ["Person", "Car"]}}
+    trk = TinyHeatmapTracker(cfg, max_streams=2)
+    frames = np.random.default_rng(11).integers(0, 256, (2, 4, 416, 416, 3), dtype=np.uint8)
+    fr = torch.from_numpy(frames).cuda()
+    y = trk.track_windows(fr).clone()
+    assert tuple(y.shape) == (2, 4, 1024) and float(y.min()) >= 0 and float(y.max()) <= 1
+    assert torch.equal(y, trk.track_windows(fr, graph=False))
+    # oracle chain for stream 1, from the engine's own detections and pooled features
+    eng = trk.model_detector.engine
+    eng.forward(fr.reshape(8, 416, 416, 3))
+    fv, _, heat, chosen = trk._decode_and_pool(8, 416, 416, 32)
+    dets, counts = eng.region_detect(eng.logits(8), 0.5, 0.45, 416, 416)
+    wl = {k: v.astype(np.float64) for k, v in W.synthetic_lstm_weights(1024 + 1024, 512, 1024, seed=1).items()}
+    h = np.zeros((1, 512)); c = np.zeros((1, 512))
+    for t in range(4):
+        i = 4 + t
+        k = int(chosen.cpu()[i])
+        lst = [] if k < 0 else [("x", 1.0, tuple(float(v) for v in dets.cpu().numpy()[i, k, :4]))]
+        ref_heat = tracker_oracle.detection_to_tracker_input(lst, 416, 416, heatmap_size=32)
+        assert np.array_equal(heat.cpu().numpy()[i], ref_heat.astype(np.float32))
+        yy, h, c = tracker_oracle.tracker_step(fv.cpu().numpy()[i][None].astype(np.float64), ref_heat[None], h, c, wl)
+        assert np.abs(y[1, t].cpu().numpy() - yy[0]).max() < 1e-4
+    rect = trk.rectangles(y)
+    assert tuple(rect.shape) == (2, 4, 4)
+
+
+def test_keras_yolo_and_multiobj_plugins(tmp_path):
+    """KerasYOLO.predict / extract with image files and MultiObjDetTracker.predict (MOT17-shaped, C=12)."""
+    import cv2
+    from object_tracking_b200.models_detection.KerasYOLO import KerasYOLO
+    from object_tracking_b200.models_tracking.MultiObjDetTracker import MultiObjDetTracker
+    rng = np.random.default_rng(5)
+    paths = []
+    for i in range(4):
+        p = str(tmp_path / f"f{i}.png")
+        cv2.imwrite(p, rng.integers(0, 256, (300, 400, 3), dtype=np.uint8))
+        paths.append(p)
+    argv = {"LABELS": ["a", "b"], "BATCH_SIZE": 2, "IMAGE_H": 416, "IMAGE_W": 416, "GRID_H": 13, "GRID_W": 13}
+    ky = KerasYOLO(argv)
+    assert ky.CLASS == 2 and ky.synthetic_weights
+    out = str(tmp_path / "o.png")
+    boxes = ky.predict(paths[0], out)
+    assert os.path.exists(out)
+    img = cv2.resize(cv2.imread(paths[0]), (416, 416))
+    w = W.synthetic_yolo_weights(2, seed=0)
+    o = yolo_oracle.yolo_forward(yolo_oracle.normalize(img[None]), w, 2, dtype=np.float64)
+    ref = decode_oracle.decode_netout(o["logits"][0].astype(np.float32), 0.5, 0.45, W.ANCHORS, 2)
+    assert len(boxes) == len(ref)
+    for a, b in zip(boxes, ref):
+        assert a.get_label() == b.get_label() and abs(a.x - b.x) < 1e-3 and abs(a.w - b.w) < 1e-3
+    feat = ky.extract(paths[0], "conv_feat")
+    assert feat.shape == (13, 13, 1024) and np.abs(feat - o["feat"][0]).max() < 3e-3
+    del ky
+    mt = MultiObjDetTracker(convlstm_units=64)
+    assert mt.CLASS == 12 and mt.detector.BATCH_SIZE == 4
+    outs = [str(tmp_path / f"t{i}.png") for i in range(4)]
+    trk = mt.predict(paths, outs)
+    assert len(trk) == 4 and all(os.path.exists(p) for p in outs)
+    x = np.stack([cv2.resize(cv2.imread(p), (416, 416)) for p in paths])
+    trk2, det2 = mt.track_window(x)
+    assert [len(b) for b in trk2] == [len(b) for b in trk]
