@@ -45,32 +45,46 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe).  nvidia-smi takes a
+    few hundred ms to emit its first line, so it is started before the warm-up and its timestamped samples are
+    filtered to the timed window [mark_start, mark_end]."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.index, self.proc, self.lines = index, None, []
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line)
+            self.lines.append((time.time(), line))
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
+        inside = [ln for (t, ln) in self.lines if self.t0 is not None and self.t0 <= t <= self.t1 + 0.03]
+        window = "timed region"
+        if len(inside) < 2:                                   # very short timed region: use every sample under load
+            inside, window = [ln for (_, ln) in self.lines], "warm-up + timed region"
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -82,7 +96,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
@@ -216,13 +230,14 @@ def main_b200(args):
         torch.cuda.synchronize()
 
     # ---- value: inputs resident in HBM
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for i in range(args.warmup):
         trk.track_windows(window(dev, i))
     eng.forward_events = []
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.mark_start()
     l0 = eng.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -230,21 +245,48 @@ def main_b200(args):
         out = trk.track_windows(window(dev, args.warmup + i))
     e1.record()
     barrier()
+    sampler.mark_end()
     launches = eng.launches - l0
     ms = e0.elapsed_time(e1)
     fwd_ms = sum(a.elapsed_time(b) for a, b in eng.forward_events) / max(1, len(eng.forward_events))
     eng.forward_events = None
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- e2e: pinned host frames in, host result out, every step
-    for i in range(2):
-        trk.track_windows(window(host, i).contiguous().pin_memory().cuda(non_blocking=True)).cpu()
-    stage = torch.empty((S, T, IMAGE, IMAGE, 3), dtype=torch.uint8).pin_memory()
+    # ---- e2e: through the plugin call (TinyTracker.track_windows) with HOST buffers: every step's frames travel
+    # pinned host -> device inside the timed region and every step's result is read back to the host.  The copy of
+    # step i+1 is issued on a second stream while step i computes (double-buffered device staging).
+    copy_stream = torch.cuda.Stream()
+    stage = [torch.empty((S, T, IMAGE, IMAGE, 3), dtype=torch.uint8, device="cuda") for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def upload(i, slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])                  # the step that last used this slot is done
+            w = window(host, i)
+            for s in range(S):                                      # S contiguous 2 MB pinned segments -> async DMA
+                stage[slot][s].copy_(w[s], non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    y_host = torch.empty((S, T, 4), dtype=torch.float32).pin_memory()
+    for slot in range(2):
+        consumed[slot].record()
+    for i in range(2):                                              # warm the path (graphs exist already)
+        upload(i, i & 1)
+        torch.cuda.current_stream().wait_event(ready[i & 1])
+        y_host.copy_(trk.track_windows(stage[i & 1]))
+        consumed[i & 1].record()
     barrier()
     t0 = time.perf_counter()
+    upload(args.warmup, 0)
     for i in range(args.steps):
-        stage.copy_(window(host, args.warmup + i))                    # the step's frames, in pinned memory
-        y = trk.track_windows(stage.cuda(non_blocking=True)).cpu()    # H2D, path, D2H (+sync)
+        slot = i & 1
+        if i + 1 < args.steps:
+            upload(args.warmup + i + 1, slot ^ 1)
+        torch.cuda.current_stream().wait_event(ready[slot])
+        y = trk.track_windows(stage[slot])
+        consumed[slot].record()
+        y_host.copy_(y)                                             # D2H + sync: the host has this step's boxes
     barrier()
     e2e_s = time.perf_counter() - t0
 
@@ -300,7 +342,7 @@ def main_b200(args):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--windows", type=int, default=4, help="independent 4-frame windows (streams) per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
