@@ -71,6 +71,8 @@ struct ConvLayer {
     int hC = 0, hP = 0, hR = 0, hN = 0, h_rows = 0, h_plane_bytes = 0;   // halo engine tile (conv_halo.cu)
     bool h_small = false;                         // two-CTAs-per-SM resource shape
     CUtensorMap tmX_hi, tmX_lo, tmW_hi, tmW_lo;
+    CUtensorMap tmWp_hi, tmWp_lo;                 // persistent variant: weight box of w_rows = min(128, round_up(Cout, 64)) rows
+    int w_rows = 128;
     bool have_weights = false;
 };
 
@@ -603,6 +605,10 @@ extern "C" int b2t_finalize(b2t_ctx *c, int upload, void *stream) {
         cuuint32_t wbox2[2] = {(cuuint32_t)l.kchunk, 128};
         if ((rc = make_tmap(c, &l.tmW_hi, c->d_blob + l.off_whi, 2, wd, wst, wbox2, sw64))) return rc;
         if ((rc = make_tmap(c, &l.tmW_lo, c->d_blob + l.off_wlo, 2, wd, wst, wbox2, sw64))) return rc;
+        l.w_rows = l.cout <= 64 ? 64 : 128;
+        cuuint32_t wbox3[2] = {(cuuint32_t)l.kchunk, (cuuint32_t)l.w_rows};
+        if ((rc = make_tmap(c, &l.tmWp_hi, c->d_blob + l.off_whi, 2, wd, wst, wbox3, sw64))) return rc;
+        if ((rc = make_tmap(c, &l.tmWp_lo, c->d_blob + l.off_wlo, 2, wd, wst, wbox3, sw64))) return rc;
     }
     c->finalized = true;
     return 0;
@@ -665,7 +671,25 @@ static int run_conv(b2t_ctx *c, ConvLayer &l, int B, float *f32_dst, cudaStream_
         p.splits = choose_splits_halo(ctas, p.cin_chunks, l.k * l.k, c->n_sm);
         if (p.splits > 1 && (size_t)p.splits * B * l.H * l.W * p.ldp * 4 > c->partial_bytes)
             return fail(-2, "internal: split-K workspace too small for conv %d", l.index);
-        if ((rc = launch_conv_halo(l.h_small, l.tmX_hi, l.tmX_lo, l.tmW_hi, l.tmW_lo, p, st)))
+        static const int persist_mode = getenv("B2T_PERSIST") ? atoi(getenv("B2T_PERSIST")) : 1;
+        // persistent variant where it measured faster: 1x1 layers and layers whose weights stay resident
+        bool persist = persist_mode && l.h_small && p.splits == 1 && p.hN <= 128 && ctas > 2 * c->n_sm &&
+                       (l.k == 1 || (l.cout <= 128 && l.k * l.k * p.cin_chunks * 2 * l.w_rows * p.kbytes <= 96 * 1024) ||
+                        persist_mode > 1);
+        if (persist) {
+            p.pw_patch_bytes = 2 * l.h_plane_bytes;
+            p.pw_stage_bytes = (int)align_up((size_t)p.hN * 132 * 4, 1024);
+            p.pw_tile_bytes = 2 * l.w_rows * p.kbytes;
+            // leave a few KB of the 228 KB SM array to L1
+            const int room = 222 * 1024 - 1024 /*align*/ - 1024 /*barriers*/ - 2 * p.pw_patch_bytes - p.pw_stage_bytes;
+            p.pw_stages = room / p.pw_tile_bytes > 16 ? 16 : room / p.pw_tile_bytes;
+            if (p.pw_stages < 2) persist = false;
+        }
+        if (persist)
+            rc = launch_conv_halo_persist(c->n_sm, l.tmX_hi, l.tmX_lo, l.tmWp_hi, l.tmWp_lo, p, st);
+        else
+            rc = launch_conv_halo(l.h_small, l.tmX_hi, l.tmX_lo, l.tmW_hi, l.tmW_lo, p, st);
+        if (rc)
             return fail(-2, "conv_halo launch (conv %d): %s", l.index, cudaGetErrorString((cudaError_t)rc));
         c->launches += 1;
         if (p.splits > 1) {

@@ -27,7 +27,104 @@ namespace b2t {
 
 constexpr int kWTileBytes = 128 * 64 * 2;            // one plane of a weight tile
 constexpr int kWStageBytes = 2 * kWTileBytes;
-constexpr int kHaloThreads = 192;
+constexpr int kEpiThreads = 256;                     // 8 epilogue warps: two per TMEM lane quarter, each takes half the columns
+constexpr int kHaloThreads = 64 + kEpiThreads;
+
+// Epilogue of one tile, run by the 8 epilogue warps (CTA warps 2..9).
+// phase 1: a thread owns one output channel (TMEM lane = warp%4 quarter) and half of the tile's pixel columns:
+//          accumulators -> fp32 sum -> scale/bias/LeakyReLU -> shared-memory stage [pixel][channel];
+// phase 2: threads walk (pixel, 8-channel group) items: 16-byte coalesced stores, 2x2 max-pool, hi/lo split,
+//          concat / space-to-depth addressing through emit8(), or raw fp32 split-K partials.
+// `acc_free` (may be NULL) is arrived on once every accumulator has been read (persistent kernel).
+constexpr int kStageLd = 132;                            // floats per staged pixel (128 + pad, keeps 16-byte alignment)
+__device__ __forceinline__ void halo_epilogue(const ConvParams &p, float *stage, uint32_t tmem_acc, int n_acc, int N,
+                                              int b, int y0, int x0, int cout0, int zsplit, uint64_t *acc_free) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int et = threadIdx.x - 64;                     // 0..255
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int ch_local = q * 32 + lane, ch = cout0 + ch_local;
+    const bool finish = p.splits == 1;
+    const float sc = (finish && ch < p.Cout) ? __ldg(p.scale + ch) : 0.f;
+    const float bi = (finish && ch < p.Cout) ? __ldg(p.bias + ch) : 0.f;
+    const uint32_t lane_addr = tmem_acc + (uint32_t(q * 32) << 16);
+#pragma unroll 1
+    for (int n0 = half * 16; n0 < N; n0 += 32) {
+        uint32_t a[16], c2[16];
+        float v[16];
+        tmem_ld16(lane_addr + n0, a);
+        tmem_ld16(lane_addr + (n_acc - 1) * N + n0, c2);   // the correction accumulator is the last one
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(a[i]) + __uint_as_float(c2[i]);
+#pragma unroll 1
+        for (int m = 1; m < n_acc - 1; ++m) {              // extra main accumulators (round-robin scheme)
+            tmem_ld16(lane_addr + m * N + n0, a);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += __uint_as_float(a[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            float tv = v[i];
+            if (finish) {
+                tv = fmaf(tv, sc, bi);
+                tv = p.act ? fmaxf(tv, 0.1f * tv) : tv;    // LeakyReLU(0.1) == max(x, 0.1 x)
+            }
+            stage[(n0 + i) * kStageLd + ch_local] = tv;
+        }
+    }
+    tc_fence_before();
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (acc_free && et == 0) mbar_arrive(acc_free);
+    const int g = et & 15, ps = et >> 4;                   // channel group, pixel slot (16 slots)
+    const int rows_valid = min(p.hR, p.H - y0), cols_valid = min(p.hC, p.W - x0);
+    if (!finish) {
+        const int chn = cout0 + g * 8;
+        if (chn < p.ldp) {
+            const long long mtot = (long long)p.B * p.H * p.W;
+            for (int r = 0; r < rows_valid; ++r) {
+                float *rowp = p.partial + ((long long)zsplit * mtot + ((long long)b * p.H + y0 + r) * p.W + x0) * p.ldp + chn;
+                for (int c = ps; c < cols_valid; c += 16) {
+                    const float4 *src = reinterpret_cast<const float4 *>(stage + (r * p.hP + c) * kStageLd + g * 8);
+                    float4 *dst = reinterpret_cast<float4 *>(rowp + (long long)c * p.ldp);
+                    dst[0] = src[0];
+                    dst[1] = src[1];
+                }
+            }
+        }
+        return;
+    }
+    if (cout0 + g * 8 >= p.Cout) return;
+    if (p.out.hi || p.out.f32) {
+        for (int r = 0; r < rows_valid; ++r)
+            for (int c = ps; c < cols_valid; c += 16) {
+                const float4 *src = reinterpret_cast<const float4 *>(stage + (r * p.hP + c) * kStageLd + g * 8);
+                const float4 lo4 = src[0], hi4 = src[1];
+                const float v8[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+                emit8(p.out, b, y0 + r, x0 + c, cout0 + g * 8, p.Cout, v8);
+            }
+    }
+    if (p.pool) {
+        const int pr = rows_valid >> 1, pc = cols_valid >> 1;
+        for (int r2 = 0; r2 < pr; ++r2)
+            for (int c2 = ps; c2 < pc; c2 += 16) {
+                const float *s0 = stage + (2 * r2 * p.hP + 2 * c2) * kStageLd + g * 8;
+                float v8[8];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const float4 a0 = reinterpret_cast<const float4 *>(s0)[h];
+                    const float4 a1 = reinterpret_cast<const float4 *>(s0 + kStageLd)[h];
+                    const float4 a2 = reinterpret_cast<const float4 *>(s0 + p.hP * kStageLd)[h];
+                    const float4 a3 = reinterpret_cast<const float4 *>(s0 + (p.hP + 1) * kStageLd)[h];
+                    v8[4 * h + 0] = fmaxf(fmaxf(a0.x, a1.x), fmaxf(a2.x, a3.x));
+                    v8[4 * h + 1] = fmaxf(fmaxf(a0.y, a1.y), fmaxf(a2.y, a3.y));
+                    v8[4 * h + 2] = fmaxf(fmaxf(a0.z, a1.z), fmaxf(a2.z, a3.z));
+                    v8[4 * h + 3] = fmaxf(fmaxf(a0.w, a1.w), fmaxf(a2.w, a3.w));
+                }
+                emit8(p.pout, b, ((y0 >> 1) + r2), ((x0 >> 1) + c2), cout0 + g * 8, p.Cout, v8);
+            }
+    }
+}
 
 // Two resource shapes of the same kernel:
 //  * big   -- one CTA per SM: two 64 KB patch buffers (double-buffered over channel chunks), 3 weight stages, all
@@ -65,8 +162,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_consta
     uint64_t *w_empty = w_full + kWStages;                      // [kWStages]
     uint64_t *accum_bar = w_empty + kWStages;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_bar + 1);
-    float *s_scale = reinterpret_cast<float *>(tail + 256);
-    float *s_bias = s_scale + 128;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int t = blockIdx.x;
@@ -91,11 +186,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_consta
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
-    if (warp >= 2) {
-        const int i = threadIdx.x - 64, c = cout0 + i;
-        s_scale[i] = (c < p.Cout) ? p.scale[c] : 0.f;
-        s_bias[i] = (c < p.Cout) ? p.bias[c] : 0.f;
-    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -163,104 +253,170 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_consta
             }
         }
     } else {
-        // ===================== epilogue =====================
-        // phase 1: each thread owns one output channel (TMEM lane): accumulators -> fp32 sum -> scale/bias/leaky
-        //          -> shared-memory stage [pixel][channel] (the operand buffers are dead once accum_bar fires);
-        // phase 2: the 128 threads walk (pixel, 8-channel group) items: coalesced 16-byte stores, 2x2 max-pool,
-        //          hi/lo split, concat / space-to-depth addressing -- all through emit8().
+        // ===================== epilogue (the operand buffers are dead once accum_bar fires) =====================
         mbar_wait(accum_bar, 0);
         tc_fence_after();
-        const int q = warp & 3, et = threadIdx.x - 64;
-        const int ch_local = q * 32 + lane;
-        const float sc = s_scale[ch_local], bi = s_bias[ch_local];
-        const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16);
-        float *stage = reinterpret_cast<float *>(smem);
-        constexpr int kLd = 132;                                  // floats per staged pixel (128 + pad, 16-byte aligned)
-        const bool finish = p.splits == 1;
-#pragma unroll 1
-        for (int n0 = 0; n0 < N; n0 += 16) {
-            uint32_t a[16];
-            float v[16];
-            tmem_ld16(lane_addr + n0, a);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(a[i]);
-#pragma unroll 1
-            for (int m = 1; m <= n_main; ++m) {
-                tmem_ld16(lane_addr + m * N + n0, a);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] += __uint_as_float(a[i]);
-            }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                float tv = v[i];
-                if (finish) {
-                    tv = fmaf(tv, sc, bi);
-                    tv = p.act ? leaky(tv) : tv;
-                }
-                stage[(n0 + i) * kLd + ch_local] = tv;
-            }
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");           // epilogue warps only
-        const int groups = min(16, (p.Cout - cout0 + 7) / 8);     // 8-channel groups that exist in this cout tile
-        const long long mtot = (long long)p.B * p.H * p.W;
-        const int rows_valid = min(p.hR, p.H - y0), cols_valid = min(p.hC, p.W - x0);
-        if (!finish) {
-            const int items = rows_valid * cols_valid * 16;
-#pragma unroll 1
-            for (int it = et; it < items; it += 128) {
-                const int g = it & 15, px = it >> 4;
-                const int r = px / cols_valid, c = px - r * cols_valid;
-                const int chn = cout0 + g * 8;
-                if (chn >= p.ldp) continue;
-                const float4 *src = reinterpret_cast<const float4 *>(stage + (r * p.hP + c) * kLd + g * 8);
-                float4 *dst = reinterpret_cast<float4 *>(
-                    p.partial + ((long long)blockIdx.z * mtot + ((long long)b * p.H + y0 + r) * p.W + x0 + c) * p.ldp + chn);
-                dst[0] = src[0];
-                dst[1] = src[1];
-            }
-        } else {
-            if (p.out.hi || p.out.f32) {
-                const int items = rows_valid * cols_valid * groups;
-#pragma unroll 1
-                for (int it = et; it < items; it += 128) {
-                    const int g = it % groups, px = it / groups;
-                    const int r = px / cols_valid, c = px - r * cols_valid;
-                    const float4 *src = reinterpret_cast<const float4 *>(stage + (r * p.hP + c) * kLd + g * 8);
-                    const float4 lo4 = src[0], hi4 = src[1];
-                    const float v8[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
-                    emit8(p.out, b, y0 + r, x0 + c, cout0 + g * 8, p.Cout, v8);
-                }
-            }
-            if (p.pool) {
-                const int pr = rows_valid >> 1, pc = cols_valid >> 1;
-                const int items = pr * pc * groups;
-#pragma unroll 1
-                for (int it = et; it < items; it += 128) {
-                    const int g = it % groups, px = it / groups;
-                    const int r = (px / pc) * 2, c = (px - (px / pc) * pc) * 2;
-                    const float *s0 = stage + (r * p.hP + c) * kLd + g * 8;
-                    float v8[8];
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const float4 a0 = reinterpret_cast<const float4 *>(s0)[h];
-                        const float4 a1 = reinterpret_cast<const float4 *>(s0 + kLd)[h];
-                        const float4 a2 = reinterpret_cast<const float4 *>(s0 + p.hP * kLd)[h];
-                        const float4 a3 = reinterpret_cast<const float4 *>(s0 + (p.hP + 1) * kLd)[h];
-                        v8[4 * h + 0] = fmaxf(fmaxf(a0.x, a1.x), fmaxf(a2.x, a3.x));
-                        v8[4 * h + 1] = fmaxf(fmaxf(a0.y, a1.y), fmaxf(a2.y, a3.y));
-                        v8[4 * h + 2] = fmaxf(fmaxf(a0.z, a1.z), fmaxf(a2.z, a3.z));
-                        v8[4 * h + 3] = fmaxf(fmaxf(a0.w, a1.w), fmaxf(a2.w, a3.w));
-                    }
-                    emit8(p.pout, b, (y0 + r) >> 1, (x0 + c) >> 1, cout0 + g * 8, p.Cout, v8);
-                }
-            }
-        }
+        halo_epilogue(p, reinterpret_cast<float *>(smem), tmem_base, n_main + 1, N, b, y0, x0, cout0, blockIdx.z, nullptr);
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Persistent variant for the short-K layers (splits == 1, N <= 128): one CTA per SM walks a static round-robin list
+// of (pixel tile, cout tile) items.  TMEM holds two accumulator sets (main + correction each) and the epilogue has
+// its own staging buffer, so the epilogue of item j overlaps the TMA + MMA main loop of item j+1 and the CTA
+// prologue (barrier init, TMEM allocation, descriptor prefetch) is paid once per SM instead of once per tile.
+// Shared memory is carved at run time: [2 patch buffers][epilogue stage N x 132 floats][weight ring].  The ring holds
+// as many (tap, chunk) weight tiles as fit (p.pw_stages <= 16): enough bytes in flight to cover the L2 latency
+// (an SM needs ~80 KB outstanding to pull 42 B/clk), and when ALL of a layer's weight tiles fit and there is a
+// single cout tile (conv_2, conv_4) they are loaded once per CTA and stay resident.
+constexpr int kPMaxWStages = 16;
+constexpr int kPSmemBytes = 227 * 1024 - 1024;
+
+__global__ void __launch_bounds__(kHaloThreads, 1)
+conv_halo_persist_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
+                         const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
+                         const ConvParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *tail = smem;                                        // barriers first (fixed offsets)
+    uint64_t *patch_full = reinterpret_cast<uint64_t *>(tail);   // [2]
+    uint64_t *patch_empty = patch_full + 2;
+    uint64_t *acc_full = patch_empty + 2;
+    uint64_t *acc_empty = acc_full + 2;
+    uint64_t *w_full = acc_empty + 2;                            // [kPMaxWStages]
+    uint64_t *w_empty = w_full + kPMaxWStages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(w_empty + kPMaxWStages);
+    uint8_t *s_patch = smem + 1024;
+    float *stage = reinterpret_cast<float *>(s_patch + 2 * p.pw_patch_bytes);
+    uint8_t *s_w = reinterpret_cast<uint8_t *>(stage) + p.pw_stage_bytes;
+    const int n_ws = p.pw_stages, w_tile = p.pw_tile_bytes, w_plane = w_tile / 2;
+    const int kPPatchBytes = p.pw_patch_bytes;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pad = p.ksize >> 1, taps = p.ksize * p.ksize;
+    const int N = p.hN;
+    const int n_ct = (p.Cout + 127) / 128;
+    const int n_items = p.B * p.h_tiles_y * p.h_tiles_x * n_ct;
+    const bool resident = n_ct == 1 && taps * p.cin_chunks <= n_ws;   // every weight tile of the layer stays in smem
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmX_hi); tma_prefetch_desc(&tmX_lo);
+        tma_prefetch_desc(&tmW_hi); tma_prefetch_desc(&tmW_lo);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&patch_full[i], 1); mbar_init(&patch_empty[i], 1);
+            mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 1);
+        }
+        for (int i = 0; i < kPMaxWStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto decode_item = [&](int item, int &b, int &y0, int &x0, int &cout0) {
+        const int ct = item % n_ct;  item /= n_ct;
+        const int tx = item % p.h_tiles_x;  item /= p.h_tiles_x;
+        const int ty = item % p.h_tiles_y;
+        b = item / p.h_tiles_y;
+        y0 = ty * p.hR; x0 = tx * p.hC; cout0 = ct * 128;
+    };
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            const uint32_t patch_tx = 2u * p.h_rows * p.hP * p.kbytes, w_tx = (uint32_t)w_tile;
+            const int kelems = p.kbytes / 2;
+            int g_chunk = 0, g_w = 0;
+            auto load_w = [&](int ws, int ci, int tap, int cout0) {
+                mbar_expect_tx(&w_full[ws], w_tx);
+                uint8_t *wdst = s_w + ws * w_tile;
+                const int kcoord = (tap * p.cin_chunks + ci) * kelems;
+                tma_load_2d(&tmW_hi, &w_full[ws], wdst, kcoord, cout0, kEvictLast);
+                tma_load_2d(&tmW_lo, &w_full[ws], wdst + w_plane, kcoord, cout0, kEvictLast);
+            };
+            if (resident)
+                for (int ci = 0; ci < p.cin_chunks; ++ci)
+                    for (int tap = 0; tap < taps; ++tap) load_w(ci * taps + tap, ci, tap, 0);
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                int b, y0, x0, cout0;
+                decode_item(item, b, y0, x0, cout0);
+                for (int ci = 0; ci < p.cin_chunks; ++ci, ++g_chunk) {
+                    const int hb = g_chunk & 1;
+                    mbar_wait(&patch_empty[hb], ((g_chunk >> 1) & 1) ^ 1);
+                    mbar_expect_tx(&patch_full[hb], patch_tx);
+                    uint8_t *hdst = s_patch + hb * kPPatchBytes;
+                    tma_load_4d(&tmX_hi, &patch_full[hb], hdst, ci * kelems, x0 - pad, y0 - pad, b, kEvictNormal);
+                    tma_load_4d(&tmX_lo, &patch_full[hb], hdst + p.h_plane_bytes, ci * kelems, x0 - pad, y0 - pad, b, kEvictNormal);
+                    if (resident) continue;
+                    for (int tap = 0; tap < taps; ++tap, ++g_w) {
+                        const int ws = g_w % n_ws;
+                        mbar_wait(&w_empty[ws], ((g_w / n_ws) & 1) ^ 1);
+                        load_w(ws, ci, tap, cout0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = umma_idesc_f16(128, N);
+        const int ksteps = p.kbytes / 32;
+        int g_chunk = 0, g_w = 0, j = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
+            const int ab = j & 1;
+            mbar_wait(&acc_empty[ab], ((j >> 1) & 1) ^ 1);       // the epilogue has drained this accumulator set
+            tc_fence_after();
+            const uint32_t t_main = tmem_base + ab * 2 * N, t_corr = t_main + N;
+            for (int ci = 0; ci < p.cin_chunks; ++ci, ++g_chunk) {
+                const int hb = g_chunk & 1;
+                mbar_wait(&patch_full[hb], (g_chunk >> 1) & 1);
+                const uint32_t xh = smem_u32(s_patch + hb * kPPatchBytes), xl = xh + p.h_plane_bytes;
+                for (int tap = 0; tap < taps; ++tap, ++g_w) {
+                    const int ws = resident ? ci * taps + tap : g_w % n_ws;
+                    mbar_wait(&w_full[ws], resident ? 0 : (g_w / n_ws) & 1);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
+                        const uint32_t shift = (kh * p.hP + kw) * p.kbytes;
+                        const uint32_t wh = smem_u32(s_w + ws * w_tile), wl = wh + w_plane;
+#pragma unroll 1
+                        for (int k = 0; k < ksteps; ++k) {
+                            const uint64_t dwh = umma_desc_kmajor(wh + k * 32, p.kbytes), dwl = umma_desc_kmajor(wl + k * 32, p.kbytes);
+                            const uint64_t dxh = umma_desc_kmajor(xh + shift + k * 32, p.kbytes),
+                                           dxl = umma_desc_kmajor(xl + shift + k * 32, p.kbytes);
+                            const uint32_t acc = (ci | tap | k) ? 1u : 0u;   // first MMA of the item overwrites
+                            umma_f16(t_corr, dwl, dxh, idesc, acc);
+                            umma_f16(t_corr, dwh, dxl, idesc, 1u);
+                            umma_f16(t_main, dwh, dxh, idesc, acc);
+                        }
+                        if (!resident) umma_commit(&w_empty[ws]);
+                        if (tap == taps - 1) umma_commit(&patch_empty[hb]);
+                        if (tap == taps - 1 && ci == p.cin_chunks - 1) umma_commit(&acc_full[ab]);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue (overlaps the next item's main loop) =====================
+        int j = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
+            int b, y0, x0, cout0;
+            decode_item(item, b, y0, x0, cout0);
+            const int ab = j & 1;
+            mbar_wait(&acc_full[ab], (j >> 1) & 1);
+            tc_fence_after();
+            halo_epilogue(p, stage, tmem_base + ab * 2 * N, 2, N, b, y0, x0, cout0, 0, &acc_empty[ab]);
+            asm volatile("bar.sync 1, 256;" ::: "memory");       // stage buffer free for the next item
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
 int conv_halo_init() {
@@ -271,7 +427,17 @@ int conv_halo_init() {
     if (e != cudaSuccess) return (int)e;
     // ask for the full shared-memory carve-out so that two small CTAs fit on an SM
     e = cudaFuncSetAttribute(conv_halo_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(conv_halo_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes);
     return (int)e;
+}
+
+int launch_conv_halo_persist(int n_sm, const CUtensorMap &x_hi, const CUtensorMap &x_lo, const CUtensorMap &w_hi,
+                             const CUtensorMap &w_lo, const ConvParams &p, cudaStream_t st) {
+    const int items = p.B * p.h_tiles_x * p.h_tiles_y * ((p.Cout + 127) / 128);
+    const int smem = 1024 /*align*/ + 1024 /*barriers*/ + 2 * p.pw_patch_bytes + p.pw_stage_bytes + p.pw_stages * p.pw_tile_bytes;
+    conv_halo_persist_kernel<<<items < n_sm ? items : n_sm, kHaloThreads, smem, st>>>(x_hi, x_lo, w_hi, w_lo, p);
+    return (int)cudaGetLastError();
 }
 
 int launch_conv_halo(bool small, const CUtensorMap &x_hi, const CUtensorMap &x_lo, const CUtensorMap &w_hi,

@@ -49,6 +49,11 @@ struct ConvParams {
     int h_plane_bytes;      // bytes between the hi and lo patch in shared memory
     int h_tiles_x, h_tiles_y;
     int kbytes;             // bytes of one K-chunk row: 128 (64 channels, SWIZZLE_128B) or 64 (32 channels, SWIZZLE_64B)
+    // persistent variant: run-time shared-memory carve-up
+    int pw_patch_bytes;     // one patch buffer (hi + lo)
+    int pw_stage_bytes;     // epilogue stage
+    int pw_tile_bytes;      // one weight tile (hi + lo) = 2 * w_rows * kbytes
+    int pw_stages;          // weight tiles that fit in the ring (<= 16)
 };
 
 __device__ __forceinline__ float leaky(float v) { return v > 0.f ? v : 0.1f * v; }

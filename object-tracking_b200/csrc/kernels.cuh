@@ -86,6 +86,8 @@ int conv_umma_init();
 int conv_halo_init();
 int launch_conv_halo(bool small, const CUtensorMap &x_hi, const CUtensorMap &x_lo, const CUtensorMap &w_hi,
                      const CUtensorMap &w_lo, const ConvParams &p, cudaStream_t st);
+int launch_conv_halo_persist(int n_sm, const CUtensorMap &x_hi, const CUtensorMap &x_lo, const CUtensorMap &w_hi,
+                             const CUtensorMap &w_lo, const ConvParams &p, cudaStream_t st);
 int launch_splitk_epilogue(const ConvParams &p, cudaStream_t st);
 int launch_conv_simt(const SimtView &v, const ConvParams &p, cudaStream_t st);
 int launch_conv1(const Conv1Params &p, cudaStream_t st);
