@@ -685,9 +685,26 @@ static int run_conv(b2t_ctx *c, ConvLayer &l, int B, float *f32_dst, cudaStream_
             p.pw_stages = room / p.pw_tile_bytes > 16 ? 16 : room / p.pw_tile_bytes;
             if (p.pw_stages < 2) persist = false;
         }
+        static long long *d_trace = nullptr;
+        const char *tr = getenv("B2T_TRACE_CONV");
+        if (persist && tr && atoi(tr) == l.index) {
+            if (!d_trace) cudaMalloc(&d_trace, 64 * 8 * 8);
+            cudaMemsetAsync(d_trace, 0, 64 * 8 * 8, st);
+            p.trace = d_trace;
+        }
         if (persist)
             rc = launch_conv_halo_persist(c->n_sm, l.tmX_hi, l.tmX_lo, l.tmWp_hi, l.tmWp_lo, p, st);
-        else
+        if (persist && p.trace) {
+            long long h[64 * 8];
+            cudaStreamSynchronize(st);
+            cudaMemcpy(h, d_trace, sizeof h, cudaMemcpyDeviceToHost);
+            const long long t0 = h[1];
+            fprintf(stderr, "[trace conv_%d] item: patch_issue | mma: wait_acc_begin acc_ok patch_ok | epi: wait_begin acc_full done (cycles rel.)\n", l.index);
+            for (int j = 0; j < 12; ++j)
+                fprintf(stderr, "  %2d: %7lld | %7lld %7lld %7lld | %7lld %7lld %7lld\n", j, h[j * 8] - t0, h[j * 8 + 1] - t0,
+                        h[j * 8 + 2] - t0, h[j * 8 + 3] - t0, h[j * 8 + 4] - t0, h[j * 8 + 5] - t0, h[j * 8 + 6] - t0);
+        }
+        if (!persist)
             rc = launch_conv_halo(l.h_small, l.tmX_hi, l.tmX_lo, l.tmW_hi, l.tmW_lo, p, st);
         if (rc)
             return fail(-2, "conv_halo launch (conv %d): %s", l.index, cudaGetErrorString((cudaError_t)rc));

@@ -218,31 +218,28 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_consta
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        const uint32_t idesc = umma_idesc_f16(128, N);
+        const uint32_t idesc = umma_idesc_f16(128, N), dhi = umma_desc_hi(p.kbytes);
         const uint32_t t_corr = tmem_base + n_main * N;
         int ws = 0, mma_it = 0;
         uint32_t wphase = 0;
         for (int it = 0; it < n_chunks; ++it) {
             const int hb = it % kHaloBufs;
             mbar_wait(&halo_full[hb], (it / kHaloBufs) & 1);
-            const uint32_t xh = smem_u32(s_halo + hb * kHaloBufBytes), xl = xh + p.h_plane_bytes;
+            const uint32_t xh16 = umma_desc_lo(smem_u32(s_halo + hb * kHaloBufBytes)), xl16 = xh16 + (p.h_plane_bytes >> 4);
             for (int tap = 0; tap < taps; ++tap, ++mma_it) {
                 mbar_wait(&w_full[ws], wphase);
                 tc_fence_after();
-                if (elect_one()) {
+                if (lane == 0) {
                     const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
-                    const uint32_t shift = (kh * p.hP + kw) * p.kbytes;
-                    const int ksteps = p.kbytes / 32;
-                    const uint32_t wh = smem_u32(s_w + ws * kWStageBytes), wl = wh + kWTileBytes;
+                    const uint32_t shift16 = ((kh * p.hP + kw) * p.kbytes) >> 4;
+                    const uint32_t wh = umma_desc_lo(smem_u32(s_w + ws * kWStageBytes)), wl = wh + (kWTileBytes >> 4);
                     const uint32_t t_main = tmem_base + (mma_it % n_main) * N;
-#pragma unroll 1
-                    for (int k = 0; k < ksteps; ++k) {
-                        const uint64_t dwh = umma_desc_kmajor(wh + k * 32, p.kbytes), dwl = umma_desc_kmajor(wl + k * 32, p.kbytes);
-                        const uint64_t dxh = umma_desc_kmajor(xh + shift + k * 32, p.kbytes),
-                                       dxl = umma_desc_kmajor(xl + shift + k * 32, p.kbytes);
-                        umma_f16(t_corr, dwl, dxh, idesc, (mma_it | k) ? 1u : 0u);
-                        umma_f16(t_corr, dwh, dxl, idesc, 1u);
-                        umma_f16(t_main, dwh, dxh, idesc, (mma_it >= n_main || k) ? 1u : 0u);
+                    const uint32_t am = mma_it >= n_main ? 1u : 0u, ac = mma_it ? 1u : 0u;
+                    umma_kstep(t_main, t_corr, wh, wl, xh16 + shift16, xl16 + shift16, dhi, idesc, am, ac);
+                    umma_kstep(t_main, t_corr, wh + 2, wl + 2, xh16 + shift16 + 2, xl16 + shift16 + 2, dhi, idesc, 1u, 1u);
+                    if (p.kbytes == 128) {
+                        umma_kstep(t_main, t_corr, wh + 4, wl + 4, xh16 + shift16 + 4, xl16 + shift16 + 4, dhi, idesc, 1u, 1u);
+                        umma_kstep(t_main, t_corr, wh + 6, wl + 6, xh16 + shift16 + 6, xl16 + shift16 + 6, dhi, idesc, 1u, 1u);
                     }
                     umma_commit(&w_empty[ws]);
                     if (tap == taps - 1) umma_commit(&halo_empty[hb]);
@@ -348,6 +345,7 @@ conv_halo_persist_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
                 for (int ci = 0; ci < p.cin_chunks; ++ci, ++g_chunk) {
                     const int hb = g_chunk & 1;
                     mbar_wait(&patch_empty[hb], ((g_chunk >> 1) & 1) ^ 1);
+                    if (p.trace && blockIdx.x == 0 && ci == 0 && g_chunk < 64) p.trace[g_chunk * 8 + 0] = clock64();
                     mbar_expect_tx(&patch_full[hb], patch_tx);
                     uint8_t *hdst = s_patch + hb * kPPatchBytes;
                     tma_load_4d(&tmX_hi, &patch_full[hb], hdst, ci * kelems, x0 - pad, y0 - pad, b, kEvictNormal);
@@ -363,35 +361,34 @@ conv_halo_persist_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        const uint32_t idesc = umma_idesc_f16(128, N);
-        const int ksteps = p.kbytes / 32;
+        const uint32_t idesc = umma_idesc_f16(128, N), dhi = umma_desc_hi(p.kbytes);
         int g_chunk = 0, g_w = 0, j = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
             const int ab = j & 1;
+            if (p.trace && blockIdx.x == 0 && j < 64 && lane == 0) p.trace[j * 8 + 1] = clock64();
             mbar_wait(&acc_empty[ab], ((j >> 1) & 1) ^ 1);       // the epilogue has drained this accumulator set
             tc_fence_after();
+            if (p.trace && blockIdx.x == 0 && j < 64 && lane == 0) p.trace[j * 8 + 2] = clock64();
             const uint32_t t_main = tmem_base + ab * 2 * N, t_corr = t_main + N;
             for (int ci = 0; ci < p.cin_chunks; ++ci, ++g_chunk) {
                 const int hb = g_chunk & 1;
                 mbar_wait(&patch_full[hb], (g_chunk >> 1) & 1);
-                const uint32_t xh = smem_u32(s_patch + hb * kPPatchBytes), xl = xh + p.h_plane_bytes;
+                if (p.trace && blockIdx.x == 0 && j < 64 && lane == 0 && ci == 0) p.trace[j * 8 + 3] = clock64();
+                const uint32_t xh16 = umma_desc_lo(smem_u32(s_patch + hb * kPPatchBytes)), xl16 = xh16 + (p.h_plane_bytes >> 4);
                 for (int tap = 0; tap < taps; ++tap, ++g_w) {
                     const int ws = resident ? ci * taps + tap : g_w % n_ws;
                     mbar_wait(&w_full[ws], resident ? 0 : (g_w / n_ws) & 1);
                     tc_fence_after();
-                    if (elect_one()) {
+                    if (lane == 0) {
                         const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
-                        const uint32_t shift = (kh * p.hP + kw) * p.kbytes;
-                        const uint32_t wh = smem_u32(s_w + ws * w_tile), wl = wh + w_plane;
-#pragma unroll 1
-                        for (int k = 0; k < ksteps; ++k) {
-                            const uint64_t dwh = umma_desc_kmajor(wh + k * 32, p.kbytes), dwl = umma_desc_kmajor(wl + k * 32, p.kbytes);
-                            const uint64_t dxh = umma_desc_kmajor(xh + shift + k * 32, p.kbytes),
-                                           dxl = umma_desc_kmajor(xl + shift + k * 32, p.kbytes);
-                            const uint32_t acc = (ci | tap | k) ? 1u : 0u;   // first MMA of the item overwrites
-                            umma_f16(t_corr, dwl, dxh, idesc, acc);
-                            umma_f16(t_corr, dwh, dxl, idesc, 1u);
-                            umma_f16(t_main, dwh, dxh, idesc, acc);
+                        const uint32_t shift16 = ((kh * p.hP + kw) * p.kbytes) >> 4;
+                        const uint32_t wh = umma_desc_lo(smem_u32(s_w + ws * w_tile)), wl = wh + (w_plane >> 4);
+                        const uint32_t acc = (ci | tap) ? 1u : 0u;        // first MMA of the item overwrites
+                        umma_kstep(t_main, t_corr, wh, wl, xh16 + shift16, xl16 + shift16, dhi, idesc, acc, acc);
+                        umma_kstep(t_main, t_corr, wh + 2, wl + 2, xh16 + shift16 + 2, xl16 + shift16 + 2, dhi, idesc, 1u, 1u);
+                        if (p.kbytes == 128) {
+                            umma_kstep(t_main, t_corr, wh + 4, wl + 4, xh16 + shift16 + 4, xl16 + shift16 + 4, dhi, idesc, 1u, 1u);
+                            umma_kstep(t_main, t_corr, wh + 6, wl + 6, xh16 + shift16 + 6, xl16 + shift16 + 6, dhi, idesc, 1u, 1u);
                         }
                         if (!resident) umma_commit(&w_empty[ws]);
                         if (tap == taps - 1) umma_commit(&patch_empty[hb]);
@@ -408,10 +405,13 @@ conv_halo_persist_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
             int b, y0, x0, cout0;
             decode_item(item, b, y0, x0, cout0);
             const int ab = j & 1;
+            if (p.trace && blockIdx.x == 0 && j < 64 && threadIdx.x == 64) p.trace[j * 8 + 4] = clock64();
             mbar_wait(&acc_full[ab], (j >> 1) & 1);
             tc_fence_after();
+            if (p.trace && blockIdx.x == 0 && j < 64 && threadIdx.x == 64) p.trace[j * 8 + 5] = clock64();
             halo_epilogue(p, stage, tmem_base + ab * 2 * N, 2, N, b, y0, x0, cout0, 0, &acc_empty[ab]);
             asm volatile("bar.sync 1, 256;" ::: "memory");       // stage buffer free for the next item
+            if (p.trace && blockIdx.x == 0 && j < 64 && threadIdx.x == 64) p.trace[j * 8 + 6] = clock64();
         }
     }
     tc_fence_before();

@@ -54,6 +54,7 @@ struct ConvParams {
     int pw_stage_bytes;     // epilogue stage
     int pw_tile_bytes;      // one weight tile (hi + lo) = 2 * w_rows * kbytes
     int pw_stages;          // weight tiles that fit in the ring (<= 16)
+    long long *trace;       // developer instrumentation (NULL in production): per-item clock64 stamps of CTA 0
 };
 
 __device__ __forceinline__ float leaky(float v) { return v > 0.f ? v : 0.1f * v; }

@@ -142,6 +142,29 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Cheap descriptor arithmetic for the MMA issue loop (one thread issues every MMA of the CTA, so each instruction
+// it spends on descriptor bit-twiddling is tensor-pipe idle time): the high word is constant per kernel, the low
+// word is (address >> 4) | LBO and is advanced by plain integer adds (+2 per 32-byte K step, +rows*row_bytes/16
+// per tap shift).  Shared-memory addresses are < 256 KB, so the 14-bit address field cannot overflow.
+__device__ __forceinline__ uint32_t umma_desc_hi(uint32_t row_bytes) {
+    return ((8 * row_bytes) >> 4) | (1u << 14) | ((row_bytes == 128 ? 2u : 4u) << 29);
+}
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFF) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint64_t umma_desc_make(uint32_t lo, uint32_t hi) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+    return d;
+}
+// the three MMAs of one 16-deep K step: corrections (w_lo*x_hi + w_hi*x_lo) and the main product (w_hi*x_hi)
+__device__ __forceinline__ void umma_kstep(uint32_t t_main, uint32_t t_corr, uint32_t wh, uint32_t wl, uint32_t xh,
+                                           uint32_t xl, uint32_t hi, uint32_t idesc, uint32_t acc_main, uint32_t acc_corr) {
+    const uint64_t dwh = umma_desc_make(wh, hi), dwl = umma_desc_make(wl, hi);
+    const uint64_t dxh = umma_desc_make(xh, hi), dxl = umma_desc_make(xl, hi);
+    umma_f16(t_corr, dwl, dxh, idesc, acc_corr);
+    umma_f16(t_corr, dwh, dxl, idesc, 1u);
+    umma_f16(t_main, dwh, dxh, idesc, acc_main);
+}
+
 // arrives on the mbarrier once every previously issued tcgen05.mma of this thread has completed
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
