@@ -685,6 +685,7 @@ static int run_conv(b2t_ctx *c, ConvLayer &l, int B, float *f32_dst, cudaStream_
             p.pw_stages = room / p.pw_tile_bytes > 16 ? 16 : room / p.pw_tile_bytes;
             if (p.pw_stages < 2) persist = false;
         }
+        { static const int dbg = getenv("B2T_DBG") ? atoi(getenv("B2T_DBG")) : 0; p.dbg = dbg; }
         static long long *d_trace = nullptr;
         const char *tr = getenv("B2T_TRACE_CONV");
         if (persist && tr && atoi(tr) == l.index) {

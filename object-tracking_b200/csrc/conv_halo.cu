@@ -76,6 +76,7 @@ __device__ __forceinline__ void halo_epilogue(const ConvParams &p, float *stage,
     tc_fence_before();
     asm volatile("bar.sync 1, 256;" ::: "memory");
     if (acc_free && et == 0) mbar_arrive(acc_free);
+    if (p.dbg & 4) return;
     const int g = et & 15, ps = et >> 4;                   // channel group, pixel slot (16 slots)
     const int rows_valid = min(p.hR, p.H - y0), cols_valid = min(p.hC, p.W - x0);
     if (!finish) {
@@ -163,7 +164,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_consta
     uint64_t *accum_bar = w_empty + kWStages;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_bar + 1);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp-uniform role index: the shuffle lets the compiler prove uniformity, so the role branches are uniform
+    // branches and the MMA issuer's descriptor arithmetic stays in uniform registers (no R2UR / waterfall loops
+    // around UTCHMMA -- the single issuing thread is otherwise the kernel's bottleneck)
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
     int t = blockIdx.x;
     const int tx = t % p.h_tiles_x;  t /= p.h_tiles_x;
     const int ty = t % p.h_tiles_y;
@@ -189,63 +193,88 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_consta
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (elect_one()) {
-            int ws = 0;
-            uint32_t wphase = 0;
-            const uint32_t halo_tx = 2u * p.h_rows * p.hP * p.kbytes, w_tx = 2u * 128u * p.kbytes;
-            const int kelems = p.kbytes / 2;
-            for (int it = 0; it < n_chunks; ++it) {
-                const int ci = c_begin + it, hb = it % kHaloBufs;
-                mbar_wait(&halo_empty[hb], ((it / kHaloBufs) & 1) ^ 1);
-                mbar_expect_tx(&halo_full[hb], halo_tx);
-                uint8_t *hdst = s_halo + hb * kHaloBufBytes;
-                tma_load_4d(&tmX_hi, &halo_full[hb], hdst, ci * kelems, x0 - pad, y0 - pad, b, kEvictNormal);
-                tma_load_4d(&tmX_lo, &halo_full[hb], hdst + p.h_plane_bytes, ci * kelems, x0 - pad, y0 - pad, b, kEvictNormal);
-                for (int tap = 0; tap < taps; ++tap) {
-                    mbar_wait(&w_empty[ws], wphase ^ 1);
-                    mbar_expect_tx(&w_full[ws], w_tx);
-                    uint8_t *wdst = s_w + ws * kWStageBytes;
-                    const int kcoord = (tap * p.cin_chunks + ci) * kelems;
-                    tma_load_2d(&tmW_hi, &w_full[ws], wdst, kcoord, cout0, kEvictLast);
-                    tma_load_2d(&tmW_lo, &w_full[ws], wdst + kWTileBytes, kcoord, cout0, kEvictLast);
-                    if (++ws == kWStages) { ws = 0; wphase ^= 1; }
+        // ===================== TMA producer (whole warp runs the uniform loops, one elected lane issues) =====
+        int ws = 0;
+        uint32_t wphase = 0;
+        const uint32_t halo_tx = 2u * p.h_rows * p.hP * p.kbytes, w_tx = 2u * 128u * p.kbytes;
+        const int kelems = p.kbytes / 2;
+        for (int it = 0; it < n_chunks; ++it) {
+            const int ci = c_begin + it, hb = it % kHaloBufs;
+            mbar_wait(&halo_empty[hb], ((it / kHaloBufs) & 1) ^ 1);
+            uint8_t *hdst = s_halo + hb * kHaloBufBytes;
+            const bool skip_x = (p.dbg & 2) && it >= kHaloBufs;
+            if (elect_one()) {
+                if (skip_x) mbar_arrive(&halo_full[hb]);
+                else {
+                    mbar_expect_tx(&halo_full[hb], halo_tx);
+                    tma_load_4d(&tmX_hi, &halo_full[hb], hdst, ci * kelems, x0 - pad, y0 - pad, b, kEvictNormal);
+                    tma_load_4d(&tmX_lo, &halo_full[hb], hdst + p.h_plane_bytes, ci * kelems, x0 - pad, y0 - pad, b, kEvictNormal);
                 }
+            }
+            __syncwarp();
+            int kcoord = ci * kelems;
+            for (int tap = 0; tap < taps; ++tap) {
+                mbar_wait(&w_empty[ws], wphase ^ 1);
+                const bool skip_w = (p.dbg & 1) && (it || tap >= kWStages);
+                uint8_t *wdst = s_w + ws * kWStageBytes;
+                if (elect_one()) {
+                    if (skip_w) mbar_arrive(&w_full[ws]);
+                    else {
+                        mbar_expect_tx(&w_full[ws], w_tx);
+                        tma_load_2d(&tmW_hi, &w_full[ws], wdst, kcoord, cout0, kEvictLast);
+                        tma_load_2d(&tmW_lo, &w_full[ws], wdst + kWTileBytes, kcoord, cout0, kEvictLast);
+                    }
+                }
+                __syncwarp();
+                kcoord += p.cin_chunks * kelems;
+                if (++ws == kWStages) { ws = 0; wphase ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
+        // Everything below is warp-uniform (kernel parameters, loop counters, shuffled values): descriptors are
+        // built with uniform-datapath adds and lane 0 only executes the tcgen05 instructions themselves.
         const uint32_t idesc = umma_idesc_f16(128, N), dhi = umma_desc_hi(p.kbytes);
         const uint32_t t_corr = tmem_base + n_main * N;
-        int ws = 0, mma_it = 0;
-        uint32_t wphase = 0;
+        const uint32_t kb16 = p.kbytes >> 4, row16 = p.hP * kb16 - (p.ksize - 1) * kb16;
+        const uint32_t w16_0 = umma_desc_lo(smem_u32(s_w)), h16_0 = umma_desc_lo(smem_u32(s_halo));
+        const uint32_t xl_off = p.h_plane_bytes >> 4;
+        const bool k128 = p.kbytes == 128, issue = !(p.dbg & 8);
+        int ws = 0, mi = 0;
+        uint32_t wphase = 0, first = 1, am = 0;
         for (int it = 0; it < n_chunks; ++it) {
             const int hb = it % kHaloBufs;
             mbar_wait(&halo_full[hb], (it / kHaloBufs) & 1);
-            const uint32_t xh16 = umma_desc_lo(smem_u32(s_halo + hb * kHaloBufBytes)), xl16 = xh16 + (p.h_plane_bytes >> 4);
-            for (int tap = 0; tap < taps; ++tap, ++mma_it) {
+            uint32_t xh = h16_0 + hb * (kHaloBufBytes >> 4);
+            int kw = 0;
+            for (int tap = 0; tap < taps; ++tap) {
                 mbar_wait(&w_full[ws], wphase);
                 tc_fence_after();
-                if (lane == 0) {
-                    const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
-                    const uint32_t shift16 = ((kh * p.hP + kw) * p.kbytes) >> 4;
-                    const uint32_t wh = umma_desc_lo(smem_u32(s_w + ws * kWStageBytes)), wl = wh + (kWTileBytes >> 4);
-                    const uint32_t t_main = tmem_base + (mma_it % n_main) * N;
-                    const uint32_t am = mma_it >= n_main ? 1u : 0u, ac = mma_it ? 1u : 0u;
-                    umma_kstep(t_main, t_corr, wh, wl, xh16 + shift16, xl16 + shift16, dhi, idesc, am, ac);
-                    umma_kstep(t_main, t_corr, wh + 2, wl + 2, xh16 + shift16 + 2, xl16 + shift16 + 2, dhi, idesc, 1u, 1u);
-                    if (p.kbytes == 128) {
-                        umma_kstep(t_main, t_corr, wh + 4, wl + 4, xh16 + shift16 + 4, xl16 + shift16 + 4, dhi, idesc, 1u, 1u);
-                        umma_kstep(t_main, t_corr, wh + 6, wl + 6, xh16 + shift16 + 6, xl16 + shift16 + 6, dhi, idesc, 1u, 1u);
+                const uint32_t wh = w16_0 + ws * (kWStageBytes >> 4), wl = wh + (kWTileBytes >> 4);
+                const uint32_t xl = xh + xl_off;
+                const uint32_t t_main = tmem_base + mi * N;
+                const uint32_t ac = first ^ 1u;
+                const bool last_tap = tap == taps - 1;
+                if (elect_one()) {
+                    if (issue) {
+                        umma_kstep(t_main, t_corr, wh, wl, xh, xl, dhi, idesc, am, ac);
+                        umma_kstep(t_main, t_corr, wh + 2, wl + 2, xh + 2, xl + 2, dhi, idesc, 1u, 1u);
+                        if (k128) {
+                            umma_kstep(t_main, t_corr, wh + 4, wl + 4, xh + 4, xl + 4, dhi, idesc, 1u, 1u);
+                            umma_kstep(t_main, t_corr, wh + 6, wl + 6, xh + 6, xl + 6, dhi, idesc, 1u, 1u);
+                        }
                     }
                     umma_commit(&w_empty[ws]);
-                    if (tap == taps - 1) umma_commit(&halo_empty[hb]);
-                    if (tap == taps - 1 && it == n_chunks - 1) umma_commit(accum_bar);
+                    if (last_tap) umma_commit(&halo_empty[hb]);
+                    if (last_tap && it == n_chunks - 1) umma_commit(accum_bar);
                 }
                 __syncwarp();
+                first = 0;
+                if (++mi == n_main) { mi = 0; am = 1; }          // every main accumulator has been written once
+                if (++kw == p.ksize) { kw = 0; xh += row16; } else xh += kb16;   // next tap: patch start shifted by (kh*hP + kw) rows
                 if (++ws == kWStages) { ws = 0; wphase ^= 1; }
             }
         }
@@ -292,7 +321,7 @@ conv_halo_persist_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
     const int n_ws = p.pw_stages, w_tile = p.pw_tile_bytes, w_plane = w_tile / 2;
     const int kPPatchBytes = p.pw_patch_bytes;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform (see above)
     const int pad = p.ksize >> 1, taps = p.ksize * p.ksize;
     const int N = p.hN;
     const int n_ct = (p.Cout + 127) / 128;
@@ -313,7 +342,7 @@ conv_halo_persist_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     auto decode_item = [&](int item, int &b, int &y0, int &x0, int &cout0) {
         const int ct = item % n_ct;  item /= n_ct;
@@ -324,45 +353,63 @@ conv_halo_persist_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
     };
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (elect_one()) {
-            const uint32_t patch_tx = 2u * p.h_rows * p.hP * p.kbytes, w_tx = (uint32_t)w_tile;
-            const int kelems = p.kbytes / 2;
-            int g_chunk = 0, g_w = 0;
-            auto load_w = [&](int ws, int ci, int tap, int cout0) {
-                mbar_expect_tx(&w_full[ws], w_tx);
-                uint8_t *wdst = s_w + ws * w_tile;
-                const int kcoord = (tap * p.cin_chunks + ci) * kelems;
-                tma_load_2d(&tmW_hi, &w_full[ws], wdst, kcoord, cout0, kEvictLast);
-                tma_load_2d(&tmW_lo, &w_full[ws], wdst + w_plane, kcoord, cout0, kEvictLast);
-            };
-            if (resident)
-                for (int ci = 0; ci < p.cin_chunks; ++ci)
-                    for (int tap = 0; tap < taps; ++tap) load_w(ci * taps + tap, ci, tap, 0);
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                int b, y0, x0, cout0;
-                decode_item(item, b, y0, x0, cout0);
-                for (int ci = 0; ci < p.cin_chunks; ++ci, ++g_chunk) {
-                    const int hb = g_chunk & 1;
-                    mbar_wait(&patch_empty[hb], ((g_chunk >> 1) & 1) ^ 1);
-                    if (p.trace && blockIdx.x == 0 && ci == 0 && g_chunk < 64) p.trace[g_chunk * 8 + 0] = clock64();
-                    mbar_expect_tx(&patch_full[hb], patch_tx);
-                    uint8_t *hdst = s_patch + hb * kPPatchBytes;
-                    tma_load_4d(&tmX_hi, &patch_full[hb], hdst, ci * kelems, x0 - pad, y0 - pad, b, kEvictNormal);
-                    tma_load_4d(&tmX_lo, &patch_full[hb], hdst + p.h_plane_bytes, ci * kelems, x0 - pad, y0 - pad, b, kEvictNormal);
-                    if (resident) continue;
-                    for (int tap = 0; tap < taps; ++tap, ++g_w) {
-                        const int ws = g_w % n_ws;
-                        mbar_wait(&w_empty[ws], ((g_w / n_ws) & 1) ^ 1);
-                        load_w(ws, ci, tap, cout0);
+        // ===================== TMA producer (whole warp runs the uniform loops, one elected lane issues) =====
+        const uint32_t patch_tx = 2u * p.h_rows * p.hP * p.kbytes, w_tx = (uint32_t)w_tile;
+        const int kelems = p.kbytes / 2;
+        int g_chunk = 0, ws = 0, n_loaded = 0;
+        uint32_t wphase = 0;
+        auto load_w = [&](int ws, int ci, int tap, int cout0) {
+            mbar_expect_tx(&w_full[ws], w_tx);
+            uint8_t *wdst = s_w + ws * w_tile;
+            const int kcoord = (tap * p.cin_chunks + ci) * kelems;
+            tma_load_2d(&tmW_hi, &w_full[ws], wdst, kcoord, cout0, kEvictLast);
+            tma_load_2d(&tmW_lo, &w_full[ws], wdst + w_plane, kcoord, cout0, kEvictLast);
+        };
+        if (resident && elect_one())
+            for (int ci = 0; ci < p.cin_chunks; ++ci)
+                for (int tap = 0; tap < taps; ++tap) load_w(ci * taps + tap, ci, tap, 0);
+        __syncwarp();
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            int b, y0, x0, cout0;
+            decode_item(item, b, y0, x0, cout0);
+            for (int ci = 0; ci < p.cin_chunks; ++ci, ++g_chunk) {
+                const int hb = g_chunk & 1;
+                mbar_wait(&patch_empty[hb], ((g_chunk >> 1) & 1) ^ 1);
+                if (p.trace && blockIdx.x == 0 && ci == 0 && g_chunk < 64 && lane == 0) p.trace[g_chunk * 8 + 0] = clock64();
+                uint8_t *hdst = s_patch + hb * kPPatchBytes;
+                const bool skip_x = (p.dbg & 2) && g_chunk >= 2;
+                if (elect_one()) {
+                    if (skip_x) mbar_arrive(&patch_full[hb]);
+                    else {
+                        mbar_expect_tx(&patch_full[hb], patch_tx);
+                        tma_load_4d(&tmX_hi, &patch_full[hb], hdst, ci * kelems, x0 - pad, y0 - pad, b, kEvictNormal);
+                        tma_load_4d(&tmX_lo, &patch_full[hb], hdst + p.h_plane_bytes, ci * kelems, x0 - pad, y0 - pad, b, kEvictNormal);
                     }
+                }
+                __syncwarp();
+                if (resident) continue;
+                for (int tap = 0; tap < taps; ++tap) {
+                    mbar_wait(&w_empty[ws], wphase ^ 1);
+                    const bool skip_w = (p.dbg & 1) && n_loaded >= n_ws;
+                    if (elect_one()) {
+                        if (skip_w) mbar_arrive(&w_full[ws]);
+                        else load_w(ws, ci, tap, cout0);
+                    }
+                    __syncwarp();
+                    ++n_loaded;
+                    if (++ws == n_ws) { ws = 0; wphase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+        // ===================== MMA issuer (warp-uniform arithmetic, lane 0 executes the tcgen05 instructions) =====
         const uint32_t idesc = umma_idesc_f16(128, N), dhi = umma_desc_hi(p.kbytes);
-        int g_chunk = 0, g_w = 0, j = 0;
+        const uint32_t kb16 = p.kbytes >> 4, row16 = p.hP * kb16 - (p.ksize - 1) * kb16;
+        const uint32_t w16_0 = umma_desc_lo(smem_u32(s_w)), p16_0 = umma_desc_lo(smem_u32(s_patch));
+        const uint32_t xl_off = p.h_plane_bytes >> 4, wl_off = w_plane >> 4, wt16 = w_tile >> 4, pb16 = kPPatchBytes >> 4;
+        const bool k128 = p.kbytes == 128, issue = !(p.dbg & 8);
+        int g_chunk = 0, j = 0, ws = 0;
+        uint32_t wphase = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
             const int ab = j & 1;
             if (p.trace && blockIdx.x == 0 && j < 64 && lane == 0) p.trace[j * 8 + 1] = clock64();
@@ -370,31 +417,36 @@ conv_halo_persist_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
             tc_fence_after();
             if (p.trace && blockIdx.x == 0 && j < 64 && lane == 0) p.trace[j * 8 + 2] = clock64();
             const uint32_t t_main = tmem_base + ab * 2 * N, t_corr = t_main + N;
+            uint32_t acc = 0;                                     // first MMA of the item overwrites
+            if (resident) ws = 0;
             for (int ci = 0; ci < p.cin_chunks; ++ci, ++g_chunk) {
                 const int hb = g_chunk & 1;
                 mbar_wait(&patch_full[hb], (g_chunk >> 1) & 1);
                 if (p.trace && blockIdx.x == 0 && j < 64 && lane == 0 && ci == 0) p.trace[j * 8 + 3] = clock64();
-                const uint32_t xh16 = umma_desc_lo(smem_u32(s_patch + hb * kPPatchBytes)), xl16 = xh16 + (p.h_plane_bytes >> 4);
-                for (int tap = 0; tap < taps; ++tap, ++g_w) {
-                    const int ws = resident ? ci * taps + tap : g_w % n_ws;
-                    mbar_wait(&w_full[ws], resident ? 0 : (g_w / n_ws) & 1);
+                uint32_t xh = p16_0 + hb * pb16;
+                int kw = 0;
+                for (int tap = 0; tap < taps; ++tap) {
+                    mbar_wait(&w_full[ws], resident ? 0 : wphase);
                     tc_fence_after();
-                    if (lane == 0) {
-                        const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
-                        const uint32_t shift16 = ((kh * p.hP + kw) * p.kbytes) >> 4;
-                        const uint32_t wh = umma_desc_lo(smem_u32(s_w + ws * w_tile)), wl = wh + (w_plane >> 4);
-                        const uint32_t acc = (ci | tap) ? 1u : 0u;        // first MMA of the item overwrites
-                        umma_kstep(t_main, t_corr, wh, wl, xh16 + shift16, xl16 + shift16, dhi, idesc, acc, acc);
-                        umma_kstep(t_main, t_corr, wh + 2, wl + 2, xh16 + shift16 + 2, xl16 + shift16 + 2, dhi, idesc, 1u, 1u);
-                        if (p.kbytes == 128) {
-                            umma_kstep(t_main, t_corr, wh + 4, wl + 4, xh16 + shift16 + 4, xl16 + shift16 + 4, dhi, idesc, 1u, 1u);
-                            umma_kstep(t_main, t_corr, wh + 6, wl + 6, xh16 + shift16 + 6, xl16 + shift16 + 6, dhi, idesc, 1u, 1u);
+                    const uint32_t wh = w16_0 + ws * wt16, wl = wh + wl_off, xl = xh + xl_off;
+                    const bool last_tap = tap == taps - 1;
+                    if (elect_one()) {
+                        if (issue) {
+                            umma_kstep(t_main, t_corr, wh, wl, xh, xl, dhi, idesc, acc, acc);
+                            umma_kstep(t_main, t_corr, wh + 2, wl + 2, xh + 2, xl + 2, dhi, idesc, 1u, 1u);
+                            if (k128) {
+                                umma_kstep(t_main, t_corr, wh + 4, wl + 4, xh + 4, xl + 4, dhi, idesc, 1u, 1u);
+                                umma_kstep(t_main, t_corr, wh + 6, wl + 6, xh + 6, xl + 6, dhi, idesc, 1u, 1u);
+                            }
                         }
                         if (!resident) umma_commit(&w_empty[ws]);
-                        if (tap == taps - 1) umma_commit(&patch_empty[hb]);
-                        if (tap == taps - 1 && ci == p.cin_chunks - 1) umma_commit(&acc_full[ab]);
+                        if (last_tap) umma_commit(&patch_empty[hb]);
+                        if (last_tap && ci == p.cin_chunks - 1) umma_commit(&acc_full[ab]);
                     }
                     __syncwarp();
+                    acc = 1;
+                    if (++kw == p.ksize) { kw = 0; xh += row16; } else xh += kb16;
+                    if (++ws == n_ws && !resident) { ws = 0; wphase ^= 1; }
                 }
             }
         }

@@ -54,6 +54,8 @@ struct ConvParams {
     int pw_stage_bytes;     // epilogue stage
     int pw_tile_bytes;      // one weight tile (hi + lo) = 2 * w_rows * kbytes
     int pw_stages;          // weight tiles that fit in the ring (<= 16)
+    int dbg;                // developer experiments (0 in production): 1 = weight TMA only for the first ring pass,
+                            // 2 = patch TMA only for the first buffers, 4 = no epilogue stores, 8 = no MMAs (results are wrong)
     long long *trace;       // developer instrumentation (NULL in production): per-item clock64 stamps of CTA 0
 };
 
