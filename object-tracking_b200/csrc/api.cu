@@ -73,6 +73,10 @@ struct ConvLayer {
     CUtensorMap tmX_hi, tmX_lo, tmW_hi, tmW_lo;
     CUtensorMap tmWp_hi, tmWp_lo;                 // persistent variant: weight box of w_rows = min(128, round_up(Cout, 64)) rows
     int w_rows = 128;
+    // pixel-major persistent variant (conv_pm.cu) for the narrow layers
+    bool pm = false, pm_flat = false;             // flat: 1x1 conv over the pixel list of the whole batch
+    int pmC = 0, pmP = 0, pmR = 0, pm_rows = 0, pm_plane_bytes = 0;
+    CUtensorMap tmXp_hi, tmXp_lo;
     bool have_weights = false;
 };
 
@@ -88,6 +92,8 @@ struct b2t_ctx {
     int L_CIN = 0, L_CREC = 0, L_HEAD = 0;        // indices of the ConvLSTM layers (0 = absent)
     // conv_1
     size_t off_w1 = 0, off_s1 = 0, off_b1 = 0, off_lut = 0;
+    size_t off_w1pm = 0, off_s1pm = 0;           // conv_1 on the tensor cores: packed fp16 (hi,lo) weights, scale / 255
+    size_t off_c8 = 0;                            // workspace: frames as fp16 integers, 8 channels per pixel
     // memory
     size_t weight_bytes = 0, ws_bytes = 0;
     std::vector<uint8_t> host_blob;
@@ -158,6 +164,30 @@ static void choose_halo_tile(int H, int W, int ksize, bool pool, ConvLayer &l) {
     }
 }
 
+// Pixel-major tile (conv_pm.cu): hR rows x hC columns with hR * hP <= 128 (the MMA's M), fewest tiles wins.
+// row_bytes = bytes of one patch row (K chunk of one pixel); mode 1 (conv_1) rows cover 4 pixels.
+static void choose_pm_tile(int H, int W, int ksize, bool pool, int row_bytes, bool ints, ConvLayer &l) {
+    const int pad = ksize / 2;
+    long best = -1;
+    for (int C = 1; C <= W && C <= 128; ++C) {
+        if (pool && (C & 1)) continue;
+        const int P = C + 2 * pad;
+        if (P > 128 || (pool && (P & 1))) continue;
+        int R = 128 / P;
+        if (R > H) R = H;
+        if (pool) R &= ~1;
+        if (R < 1) continue;
+        const long tiles = (long)((W + C - 1) / C) * ((H + R - 1) / R);
+        if (best < 0 || tiles < best) {
+            best = tiles;
+            l.pmC = C; l.pmP = P; l.pmR = R; l.pm_rows = R + 2 * pad;
+            const int reach = 128 + 2 * pad * P + 2 * pad + (ints ? 2 : 0);      // rows the shifted operands can touch
+            const int rows = l.pm_rows * P > reach ? l.pm_rows * P : reach;
+            l.pm_plane_bytes = (int)align_up((size_t)rows * row_bytes, 1024);
+        }
+    }
+}
+
 static int choose_splits_halo(int ctas, int cin_chunks, int taps, int n_sm) {
     const char *env = getenv("B2T_SPLITS");
     int best_s = 1;
@@ -209,6 +239,7 @@ static ConvLayer &new_conv(b2t_ctx *c, int index, int k, int cin, int cout, bool
     l.BN = cout >= 128 ? 128 : 64;
     choose_tile(H, W, pool, l.TW, l.TH);
     choose_halo_tile(H, W, k, pool, l);
+    if (cout <= 64 && c->cfg.engine == B2T_ENGINE_TCGEN05) choose_pm_tile(H, W, k, pool, index == 1 ? 16 : l.kchunk * 2, index == 1, l);
     if ((int)c->conv.size() <= index) c->conv.resize(index + 1);
     c->conv[index] = l;
     return c->conv[index];
@@ -249,7 +280,9 @@ extern "C" int b2t_create(const b2t_config *cfg, b2t_ctx **out) {
     c->off_s1 = align_up(27 * 32 * 4, 256);
     c->off_b1 = c->off_s1 + 256;
     c->off_lut = c->off_b1 + 256;
-    c->weight_bytes = c->off_lut + 1024;
+    c->off_w1pm = c->off_lut + 1024;
+    c->off_s1pm = c->off_w1pm + 3 * 4096;
+    c->weight_bytes = c->off_s1pm + 512;
 
     const int Gs = c->G;
     const bool lstm = cfg->convlstm_units > 0;
@@ -340,6 +373,7 @@ extern "C" int b2t_create(const b2t_config *cfg, b2t_ctx **out) {
         o += align_up((size_t)b.plane * 2 * 2, 1024);
     }
     c->off_logits = o;  o += align_up((size_t)MB * Gs * Gs * AD * 4, 1024);
+    c->off_c8 = o;  o += align_up((size_t)MB * H0 * H0 * 16, 1024);
     // split-K / SIMT partials: worst case over layers and batch sizes
     size_t pb = 0;
     for (size_t i = 2; i < c->conv.size(); ++i) {
@@ -451,8 +485,33 @@ extern "C" int b2t_set_conv_weights(b2t_ctx *c, int idx, const float *ker, const
     if (idx == 1) {
         float *w = reinterpret_cast<float *>(c->host_blob.data() + c->off_w1);
         memcpy(w, ker, 27 * 32 * 4);   // (kh,kw,cin,cout) is already [tap*3+cin][32]
-        fold_bn(c, 32, gamma, beta, mean, var, reinterpret_cast<float *>(c->host_blob.data() + c->off_s1),
-                reinterpret_cast<float *>(c->host_blob.data() + c->off_b1));
+        float *s1 = reinterpret_cast<float *>(c->host_blob.data() + c->off_s1);
+        fold_bn(c, 32, gamma, beta, mean, var, s1, reinterpret_cast<float *>(c->host_blob.data() + c->off_b1));
+        // tensor-core path (conv_pm.cu mode 1): per kernel row kh a [32 cout][32 k] fp16 tile, k = kw*8 + cin, stored
+        // as 128-byte core matrices [cout/8][k/8][cout%8][k%8]; hi plane then lo plane; 1/255 goes into the scale
+        op_t *wp = reinterpret_cast<op_t *>(c->host_blob.data() + c->off_w1pm);
+        float *s1pm = reinterpret_cast<float *>(c->host_blob.data() + c->off_s1pm);
+        memset(wp, 0, 3 * 4096);
+        for (int co = 0; co < 32; ++co) {
+            float m = 0.f;
+            for (int t = 0; t < 27; ++t) m = fmaxf(m, fabsf(ker[t * 32 + co]));
+            int shift = 0;
+            if (m > 0.f && std::isfinite(m)) {
+                int e;
+                frexpf(m, &e);
+                shift = 8 - e;
+                if (shift > 40) shift = 40;
+                if (shift < -8) shift = -8;
+            }
+            const float up = ldexpf(1.f, shift);
+            for (int kh = 0; kh < 3; ++kh)
+                for (int kw = 0; kw < 3; ++kw)
+                    for (int ci = 0; ci < 3; ++ci) {
+                        const size_t d = (size_t)kh * 2048 + (size_t)((co / 8) * 4 + kw) * 64 + (co % 8) * 8 + ci;   // fp16 elements
+                        split_f16(ker[((kh * 3 + kw) * 3 + ci) * 32 + co] * up, wp[d], wp[d + 1024]);
+                    }
+            s1pm[co] = (float)((double)s1[co] * (double)ldexpf(1.f, -shift) / 255.0);
+        }
     } else {
         std::vector<float> un;
         pack_conv(c, l, ker, l.cin, nullptr, un);
@@ -540,10 +599,11 @@ extern "C" int b2t_set_convlstm_weights(b2t_ctx *c, const float *kernel, const f
 
 // ------------------------------------------------------------------------------------------------ finalize
 static int make_tmap(b2t_ctx *c, CUtensorMap *tm, void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides,
-                     const cuuint32_t *box, bool sw64 = false) {
+                     const cuuint32_t *box, int swz = 0 /* 0 = 128B, 1 = 64B, 2 = none */) {
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = c->encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, base, dims, strides, box, es,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, sw64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           swz == 2 ? CU_TENSOR_MAP_SWIZZLE_NONE : swz == 1 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(-2, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -573,6 +633,7 @@ extern "C" int b2t_finalize(b2t_ctx *c, int upload, void *stream) {
     }
     int rc = conv_umma_init();
     if (!rc) rc = conv_halo_init();
+    if (!rc) rc = conv_pm_init();
     if (rc) return fail(-2, "cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString((cudaError_t)rc));
     if (upload) CK(cudaMemcpyAsync(c->d_blob, c->host_blob.data(), c->weight_bytes, cudaMemcpyHostToDevice, st));
     // pad channels / never-written halo must be finite zeros
@@ -609,6 +670,45 @@ extern "C" int b2t_finalize(b2t_ctx *c, int upload, void *stream) {
         cuuint32_t wbox3[2] = {(cuuint32_t)l.kchunk, (cuuint32_t)l.w_rows};
         if ((rc = make_tmap(c, &l.tmWp_hi, c->d_blob + l.off_whi, 2, wd, wst, wbox3, sw64))) return rc;
         if ((rc = make_tmap(c, &l.tmWp_lo, c->d_blob + l.off_wlo, 2, wd, wst, wbox3, sw64))) return rc;
+        // pixel-major variant: narrow layers whose weights all stay resident in shared memory
+        static const int pm_mode = getenv("B2T_PM") ? atoi(getenv("B2T_PM")) : 1;
+        l.pm = false;
+        if (pm_mode && l.pmC && c->cfg.engine == B2T_ENGINE_TCGEN05 && l.cout <= 64 && nb == MB) {
+            l.pm_flat = l.k == 1 && !l.pool && l.out_mode == DEST_PLAIN;
+            const int kbytes = l.kchunk * 2;
+            const int plane = l.pm_flat ? 128 * kbytes : l.pm_plane_bytes;
+            const int ld = round_up(l.cout, 16) + 4;
+            const size_t smem = 1024 + 2048 + 2 * 2 * (size_t)plane + 2 * align_up((size_t)128 * ld * 4, 1024) +
+                                (size_t)l.k * l.k * (l.cin_pad / l.kchunk) * 2 * l.w_rows * kbytes;
+            if (smem <= 226 * 1024) {
+                l.pm = true;
+                if (l.pm_flat) {
+                    const cuuint64_t npx = (cuuint64_t)MB * l.H * l.W;
+                    cuuint64_t fd[4] = {(cuuint64_t)l.cin_pad, npx, 1, 1};
+                    cuuint64_t fs[3] = {(cuuint64_t)in.C * 2, (cuuint64_t)in.C * 2 * npx, (cuuint64_t)in.C * 2 * npx};
+                    cuuint32_t fb[4] = {(cuuint32_t)l.kchunk, 128, 1, 1};
+                    if ((rc = make_tmap(c, &l.tmXp_hi, in.hi + l.in_ch_off, 4, fd, fs, fb, sw64))) return rc;
+                    if ((rc = make_tmap(c, &l.tmXp_lo, in.hi + in.plane + l.in_ch_off, 4, fd, fs, fb, sw64))) return rc;
+                } else {
+                    cuuint32_t pbox[4] = {(cuuint32_t)l.kchunk, (cuuint32_t)l.pmP, (cuuint32_t)l.pm_rows, 1};
+                    if ((rc = make_tmap(c, &l.tmXp_hi, in.hi + l.in_ch_off, 4, dims, strides, pbox, sw64))) return rc;
+                    if ((rc = make_tmap(c, &l.tmXp_lo, in.hi + in.plane + l.in_ch_off, 4, dims, strides, pbox, sw64))) return rc;
+                }
+            }
+        }
+    }
+    {   // conv_1 on the tensor cores: TMA view of the fp16-integer frame copy [MB][H][W][8]
+        ConvLayer &l = c->conv[1];
+        static const int pm_mode = getenv("B2T_PM") ? atoi(getenv("B2T_PM")) : 1;
+        l.pm = false;
+        if (pm_mode && l.pmC && c->cfg.engine == B2T_ENGINE_TCGEN05) {
+            cuuint64_t dims[4] = {8, (cuuint64_t)l.W, (cuuint64_t)l.H, (cuuint64_t)MB};
+            cuuint64_t strides[3] = {16, (cuuint64_t)16 * l.W, (cuuint64_t)16 * l.W * l.H};
+            cuuint32_t box[4] = {8, (cuuint32_t)l.pmP, (cuuint32_t)l.pm_rows, 1};
+            if ((rc = make_tmap(c, &l.tmXp_hi, c->d_ws + c->off_c8, 4, dims, strides, box, 2))) return rc;
+            l.tmXp_lo = l.tmXp_hi;
+            l.pm = true;
+        }
     }
     c->finalized = true;
     return 0;
@@ -664,6 +764,32 @@ static int run_conv(b2t_ctx *c, ConvLayer &l, int B, float *f32_dst, cudaStream_
         c->launches += 2;
         return 0;
     }
+    if (c->cfg.engine == B2T_ENGINE_TCGEN05 && l.pm && !f32_dst) {
+        p.splits = 1;
+        p.dbg = getenv("B2T_DBG") ? atoi(getenv("B2T_DBG")) : 0;
+        p.pm_mode = 0;
+        p.pm_n = round_up(l.cout, 16);
+        p.pm_tmem_cols = 4 * p.pm_n <= 128 ? 128 : 4 * p.pm_n <= 256 ? 256 : 512;
+        p.pm_stage_ld = p.pm_n + 4;
+        p.pm_glog = p.pm_n <= 32 ? 2 : p.pm_n <= 64 ? 3 : 4;
+        p.pw_stage_bytes = (int)align_up((size_t)128 * p.pm_stage_ld * 4, 1024);
+        p.pw_tile_bytes = 2 * l.w_rows * p.kbytes;
+        if (l.pm_flat) {
+            p.B = 1; p.H = 1; p.W = B * l.H * l.W;
+            p.hC = 128; p.hP = 128; p.hR = 1; p.h_rows = 1;
+            p.h_plane_bytes = 128 * p.kbytes;
+        } else {
+            p.hC = l.pmC; p.hP = l.pmP; p.hR = l.pmR; p.h_rows = l.pm_rows;
+            p.h_plane_bytes = l.pm_plane_bytes;
+        }
+        p.hN = 128;
+        p.pw_patch_bytes = 2 * p.h_plane_bytes;
+        p.h_tiles_x = (p.W + p.hC - 1) / p.hC; p.h_tiles_y = (p.H + p.hR - 1) / p.hR;
+        if ((rc = launch_conv_pm(c->n_sm, l.tmXp_hi, l.tmXp_lo, l.tmWp_hi, l.tmWp_lo, p, st)))
+            return fail(-2, "conv_pm launch (conv %d): %s", l.index, cudaGetErrorString((cudaError_t)rc));
+        c->launches += 1;
+        return 0;
+    }
     if (c->cfg.engine == B2T_ENGINE_TCGEN05) {
         p.hC = l.hC; p.hP = l.hP; p.hR = l.hR; p.hN = l.hN; p.h_rows = l.h_rows; p.h_plane_bytes = l.h_plane_bytes;
         p.h_tiles_x = (l.W + l.hC - 1) / l.hC; p.h_tiles_y = (l.H + l.hR - 1) / l.hR;
@@ -671,8 +797,9 @@ static int run_conv(b2t_ctx *c, ConvLayer &l, int B, float *f32_dst, cudaStream_
         p.splits = choose_splits_halo(ctas, p.cin_chunks, l.k * l.k, c->n_sm);
         if (p.splits > 1 && (size_t)p.splits * B * l.H * l.W * p.ldp * 4 > c->partial_bytes)
             return fail(-2, "internal: split-K workspace too small for conv %d", l.index);
-        static const int persist_mode = getenv("B2T_PERSIST") ? atoi(getenv("B2T_PERSIST")) : 1;
-        // persistent variant where it measured faster: 1x1 layers and layers whose weights stay resident
+        static const int persist_mode = getenv("B2T_PERSIST") ? atoi(getenv("B2T_PERSIST")) : 2;
+        // persistent variant (one CTA per SM, TMEM double buffering) for every short-K layer with enough tiles;
+        // B2T_PERSIST=1 restricts it to 1x1 layers and layers whose weights stay resident, 0 disables it
         bool persist = persist_mode && l.h_small && p.splits == 1 && p.hN <= 128 && ctas > 2 * c->n_sm &&
                        (l.k == 1 || (l.cout <= 128 && l.k * l.k * p.cin_chunks * 2 * l.w_rows * p.kbytes <= 96 * 1024) ||
                         persist_mode > 1);
@@ -732,6 +859,31 @@ static int run_conv(b2t_ctx *c, ConvLayer &l, int B, float *f32_dst, cudaStream_
 
 static int run_conv1(b2t_ctx *c, const void *frames, int dtype, int B, cudaStream_t st) {
     ConvLayer &l = c->conv[1];
+    if (l.pm && dtype == B2T_FRAME_U8) {
+        // tensor-core path: frame -> fp16 integers (8 ch / pixel), then conv_pm_kernel mode 1
+        int rc = launch_frames_to_c8(frames, c->d_ws + c->off_c8, (long long)B * l.H * l.W, st);
+        if (rc) return fail(-2, "frames_to_c8 launch: %s", cudaGetErrorString((cudaError_t)rc));
+        ConvParams p;
+        memset(&p, 0, sizeof p);
+        p.B = B; p.H = l.H; p.W = l.W; p.ksize = 3; p.cin_chunks = 1; p.Cout = 32; p.kbytes = 16;
+        p.act = 1; p.pool = 1; p.splits = 1; p.ldp = 32;
+        p.scale = reinterpret_cast<const float *>(c->d_blob + c->off_s1pm);
+        p.bias = reinterpret_cast<const float *>(c->d_blob + c->off_b1);
+        p.out = dest_planes(c, l.out_buf, 0, l.H, l.W, DEST_PLAIN);
+        p.pout = dest_planes(c, l.pout_buf, 0, l.H / 2, l.W / 2, DEST_PLAIN);
+        p.hC = l.pmC; p.hP = l.pmP; p.hR = l.pmR; p.h_rows = l.pm_rows; p.hN = 128;
+        p.h_plane_bytes = l.pm_plane_bytes;
+        p.h_tiles_x = (l.W + p.hC - 1) / p.hC; p.h_tiles_y = (l.H + p.hR - 1) / p.hR;
+        p.pm_mode = 1; p.pm_n = 32; p.pm_tmem_cols = 128; p.pm_stage_ld = 36; p.pm_glog = 2;
+        p.pw_patch_bytes = l.pm_plane_bytes;
+        p.pw_stage_bytes = (int)align_up((size_t)128 * 36 * 4, 1024);
+        p.pm_w = c->d_blob + c->off_w1pm; p.pm_w_bytes = 3 * 4096;
+        p.dbg = getenv("B2T_DBG") ? atoi(getenv("B2T_DBG")) : 0;
+        if ((rc = launch_conv_pm(c->n_sm, l.tmXp_hi, l.tmXp_lo, l.tmXp_hi, l.tmXp_lo, p, st)))
+            return fail(-2, "conv_pm launch (conv 1): %s", cudaGetErrorString((cudaError_t)rc));
+        c->launches += 2;
+        return 0;
+    }
     Conv1Params p;
     memset(&p, 0, sizeof p);
     p.frames = frames; p.dtype = dtype; p.B = B; p.H = l.H; p.W = l.W;

@@ -77,54 +77,7 @@ __device__ __forceinline__ void halo_epilogue(const ConvParams &p, float *stage,
     asm volatile("bar.sync 1, 256;" ::: "memory");
     if (acc_free && et == 0) mbar_arrive(acc_free);
     if (p.dbg & 4) return;
-    const int g = et & 15, ps = et >> 4;                   // channel group, pixel slot (16 slots)
-    const int rows_valid = min(p.hR, p.H - y0), cols_valid = min(p.hC, p.W - x0);
-    if (!finish) {
-        const int chn = cout0 + g * 8;
-        if (chn < p.ldp) {
-            const long long mtot = (long long)p.B * p.H * p.W;
-            for (int r = 0; r < rows_valid; ++r) {
-                float *rowp = p.partial + ((long long)zsplit * mtot + ((long long)b * p.H + y0 + r) * p.W + x0) * p.ldp + chn;
-                for (int c = ps; c < cols_valid; c += 16) {
-                    const float4 *src = reinterpret_cast<const float4 *>(stage + (r * p.hP + c) * kStageLd + g * 8);
-                    float4 *dst = reinterpret_cast<float4 *>(rowp + (long long)c * p.ldp);
-                    dst[0] = src[0];
-                    dst[1] = src[1];
-                }
-            }
-        }
-        return;
-    }
-    if (cout0 + g * 8 >= p.Cout) return;
-    if (p.out.hi || p.out.f32) {
-        for (int r = 0; r < rows_valid; ++r)
-            for (int c = ps; c < cols_valid; c += 16) {
-                const float4 *src = reinterpret_cast<const float4 *>(stage + (r * p.hP + c) * kStageLd + g * 8);
-                const float4 lo4 = src[0], hi4 = src[1];
-                const float v8[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
-                emit8(p.out, b, y0 + r, x0 + c, cout0 + g * 8, p.Cout, v8);
-            }
-    }
-    if (p.pool) {
-        const int pr = rows_valid >> 1, pc = cols_valid >> 1;
-        for (int r2 = 0; r2 < pr; ++r2)
-            for (int c2 = ps; c2 < pc; c2 += 16) {
-                const float *s0 = stage + (2 * r2 * p.hP + 2 * c2) * kStageLd + g * 8;
-                float v8[8];
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const float4 a0 = reinterpret_cast<const float4 *>(s0)[h];
-                    const float4 a1 = reinterpret_cast<const float4 *>(s0 + kStageLd)[h];
-                    const float4 a2 = reinterpret_cast<const float4 *>(s0 + p.hP * kStageLd)[h];
-                    const float4 a3 = reinterpret_cast<const float4 *>(s0 + (p.hP + 1) * kStageLd)[h];
-                    v8[4 * h + 0] = fmaxf(fmaxf(a0.x, a1.x), fmaxf(a2.x, a3.x));
-                    v8[4 * h + 1] = fmaxf(fmaxf(a0.y, a1.y), fmaxf(a2.y, a3.y));
-                    v8[4 * h + 2] = fmaxf(fmaxf(a0.z, a1.z), fmaxf(a2.z, a3.z));
-                    v8[4 * h + 3] = fmaxf(fmaxf(a0.w, a1.w), fmaxf(a2.w, a3.w));
-                }
-                emit8(p.pout, b, ((y0 >> 1) + r2), ((x0 >> 1) + c2), cout0 + g * 8, p.Cout, v8);
-            }
-    }
+    epilogue_store(p, stage, kStageLd, 4, b, y0, x0, cout0, zsplit, et, kEpiThreads);
 }
 
 // Two resource shapes of the same kernel:

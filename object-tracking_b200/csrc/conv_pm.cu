@@ -1,0 +1,301 @@
+// conv_pm_kernel -- "pixel-major" persistent convolution for the narrow layers at the top of the network
+// (conv_1: 3 -> 32, conv_2: 32 -> 64, conv_4: 128 -> 64 channels).
+//
+// conv_halo_kernel puts the output channels on the MMA's M dimension (128 TMEM lanes); with Cout = 32 or 64 half or
+// three quarters of every tcgen05.mma would be wasted.  Here the roles are swapped:
+//
+//   D[pixel, cout] = sum_{tap, c} X[pixel + tap, c] * Wt[cout, tap, c]
+//
+// * M = 128 pixels of one image tile (A operand).  The tile's activation patch (with halo) sits in shared memory
+//   exactly as in conv_halo_kernel -- rows ordered x-fastest with pitch hP -- and tap (kh,kw) is the same patch read
+//   through a descriptor whose start address is advanced by (kh*hP + kw) rows.
+// * N = Cout rounded up to 16 (B operand = the layer's weights, all (tap, chunk) tiles resident in shared memory,
+//   loaded once per CTA).
+// * mode 0 (conv_2, conv_4): fp16 (hi, lo) activations and weights, three MMAs per 16-deep K step as everywhere else.
+// * mode 1 (conv_1 on uint8 frames): the frame is stored as fp16 integers 0..255 (exact, so there is no lo plane),
+//   8 channels per pixel (3 used) = one 16-byte core-matrix row.  With the no-swizzle K-major layout
+//   (row m at 16*m bytes: SBO = 128 B, K group j at +16*j bytes: LBO = 16 B) the operand row of pixel m covers the
+//   pixels m .. m+3 of the patch: the kw taps of the 3x3 window are folded into K by the descriptor itself (an
+//   im2col that costs nothing), one K = 32 step per kernel row kh.  1/255 is folded into the epilogue scale.
+// * TMEM holds two accumulator sets (main + correction, N columns each) so the 8-warp epilogue of tile j overlaps
+//   the MMAs of tile j+1; the epilogue thread owns one pixel (TMEM lane) and half of the channels, stages
+//   [pixel][channel] in shared memory and shares the coalesced store phase (2x2 max-pool, hi/lo split) with
+//   conv_halo_kernel.
+#include "kernels.cuh"
+
+namespace b2t {
+
+constexpr int kPmThreads = 64 + 256;
+
+__device__ __forceinline__ void umma_pm3(uint32_t t_main, uint32_t t_corr, uint32_t xh, uint32_t xl, uint32_t wh, uint32_t wl,
+                                         uint32_t hi, uint32_t idesc, uint32_t acc) {
+    const uint64_t dxh = umma_desc_make(xh, hi), dxl = umma_desc_make(xl, hi);
+    const uint64_t dwh = umma_desc_make(wh, hi), dwl = umma_desc_make(wl, hi);
+    umma_f16(t_corr, dxh, dwl, idesc, acc);
+    umma_f16(t_corr, dxl, dwh, idesc, 1u);
+    umma_f16(t_main, dxh, dwh, idesc, acc);
+}
+
+__global__ void __launch_bounds__(kPmThreads, 2)
+conv_pm_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
+               const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
+               const ConvParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t *patch_full = reinterpret_cast<uint64_t *>(smem);   // [2]
+    uint64_t *patch_empty = patch_full + 2;
+    uint64_t *acc_full = patch_empty + 2;
+    uint64_t *acc_empty = acc_full + 2;
+    uint64_t *w_full = acc_empty + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(w_full + 1);
+    float *s_scale = reinterpret_cast<float *>(smem + 256);       // [128]
+    float *s_bias = s_scale + 128;
+    uint8_t *s_patch = smem + 2048;
+    float *stage = reinterpret_cast<float *>(s_patch + 2 * p.pw_patch_bytes);
+    uint8_t *s_w = reinterpret_cast<uint8_t *>(stage) + 2 * p.pw_stage_bytes;      // two stage buffers (one per epilogue group)
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform
+    const int pad = p.ksize >> 1, taps = p.ksize * p.ksize;
+    const int N = p.pm_n;
+    const int n_items = p.B * p.h_tiles_y * p.h_tiles_x;
+    const int n_wtiles = taps * p.cin_chunks;
+    const bool ints = p.pm_mode == 1;
+
+    // ---- prologue: barriers, zeroed patch buffers (the MMA reads a few rows past the loaded box: finite zeros),
+    //      scale/bias, conv_1's packed weights, TMEM
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmX_hi);
+        if (!ints) { tma_prefetch_desc(&tmX_lo); tma_prefetch_desc(&tmW_hi); tma_prefetch_desc(&tmW_lo); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&patch_full[i], 1); mbar_init(&patch_empty[i], 1);
+            mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 1);
+        }
+        mbar_init(w_full, 1);
+        fence_barrier_init();
+    }
+    for (int i = threadIdx.x; i < 2 * p.pw_patch_bytes / 16; i += kPmThreads)
+        reinterpret_cast<uint4 *>(s_patch)[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x < 128) {
+        s_scale[threadIdx.x] = threadIdx.x < p.Cout ? __ldg(p.scale + threadIdx.x) : 0.f;
+        s_bias[threadIdx.x] = threadIdx.x < p.Cout ? __ldg(p.bias + threadIdx.x) : 0.f;
+    }
+    if (ints)
+        for (int i = threadIdx.x; i < p.pm_w_bytes / 16; i += kPmThreads)
+            reinterpret_cast<uint4 *>(s_w)[i] = __ldg(reinterpret_cast<const uint4 *>(p.pm_w) + i);
+    fence_proxy_async();
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.pm_tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+    auto decode_item = [&](int item, int &b, int &y0, int &x0) {
+        const int tx = item % p.h_tiles_x;  item /= p.h_tiles_x;
+        const int ty = item % p.h_tiles_y;
+        b = item / p.h_tiles_y;
+        y0 = ty * p.hR; x0 = tx * p.hC;
+    };
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        const int kelems = p.kbytes / 2;
+        const uint32_t patch_tx = (ints ? 1u : 2u) * p.h_rows * p.hP * p.kbytes;
+        if (!ints && elect_one()) {                       // every weight tile of the layer, once
+            mbar_expect_tx(w_full, (uint32_t)n_wtiles * p.pw_tile_bytes);
+            for (int ci = 0; ci < p.cin_chunks; ++ci)
+                for (int tap = 0; tap < taps; ++tap) {
+                    uint8_t *wdst = s_w + (ci * taps + tap) * p.pw_tile_bytes;
+                    const int kcoord = (tap * p.cin_chunks + ci) * kelems;
+                    tma_load_2d(&tmW_hi, w_full, wdst, kcoord, 0, kEvictLast);
+                    tma_load_2d(&tmW_lo, w_full, wdst + p.pw_tile_bytes / 2, kcoord, 0, kEvictLast);
+                }
+        }
+        __syncwarp();
+        int g_chunk = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            int b, y0, x0;
+            decode_item(item, b, y0, x0);
+            for (int ci = 0; ci < p.cin_chunks; ++ci, ++g_chunk) {
+                const int hb = g_chunk & 1;
+                mbar_wait(&patch_empty[hb], ((g_chunk >> 1) & 1) ^ 1);
+                uint8_t *hdst = s_patch + hb * p.pw_patch_bytes;
+                const bool skip_x = (p.dbg & 2) && g_chunk >= 2;
+                if (elect_one()) {
+                    if (skip_x) mbar_arrive(&patch_full[hb]);
+                    else {
+                        mbar_expect_tx(&patch_full[hb], patch_tx);
+                        tma_load_4d(&tmX_hi, &patch_full[hb], hdst, ci * kelems, x0 - pad, y0 - pad, b, kEvictNormal);
+                        if (!ints)
+                            tma_load_4d(&tmX_lo, &patch_full[hb], hdst + p.h_plane_bytes, ci * kelems, x0 - pad, y0 - pad, b, kEvictNormal);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (warp-uniform arithmetic, one elected lane issues) =====================
+        const uint32_t idesc = umma_idesc_f16(128, N);
+        const uint32_t p16_0 = umma_desc_lo(smem_u32(s_patch)), pb16 = p.pw_patch_bytes >> 4;
+        const uint32_t w16 = (smem_u32(s_w) & 0x3FFFF) >> 4;
+        int g_chunk = 0, j = 0;
+        if (!ints) { mbar_wait(w_full, 0); tc_fence_after(); }
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
+            const int ab = j & 1;
+            mbar_wait(&acc_empty[ab], ((j >> 1) & 1) ^ 1);       // the epilogue has drained this accumulator set
+            tc_fence_after();
+            const uint32_t t_main = tmem_base + ab * 2 * N, t_corr = t_main + N;
+            if (ints) {
+                // conv_1: A rows = pixels (16 B each, SBO 128 B, LBO 16 B -> a row spans 4 pixels = K 32);
+                // B = [32 cout][32 k] per kernel row, core matrices of 128 B: LBO 128 B (next K group), SBO 512 B
+                const int hb = g_chunk & 1;
+                mbar_wait(&patch_full[hb], (g_chunk >> 1) & 1);
+                tc_fence_after();
+                const uint32_t a_hi = (128u >> 4) | (1u << 14), b_hi = (512u >> 4) | (1u << 14);
+                const uint32_t xa = p16_0 + hb * pb16;                       // LBO field = 1 (16 B) from umma_desc_lo
+                const uint32_t wb = w16 | ((128u >> 4) << 16);
+                if (elect_one()) {
+#pragma unroll
+                    for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+                        for (int ks = 0; ks < 2; ++ks) {
+                            const uint64_t da = umma_desc_make(xa + kh * p.hP + 2 * ks, a_hi);
+                            const uint64_t dwh = umma_desc_make(wb + kh * (4096 >> 4) + ks * (256 >> 4), b_hi);
+                            const uint64_t dwl = umma_desc_make(wb + kh * (4096 >> 4) + (2048 >> 4) + ks * (256 >> 4), b_hi);
+                            const uint32_t acc = (kh | ks) ? 1u : 0u;
+                            if (p.dbg & 8) continue;
+                            umma_f16(t_corr, da, dwl, idesc, acc);
+                            umma_f16(t_main, da, dwh, idesc, acc);
+                        }
+                    }
+                    umma_commit(&patch_empty[hb]);
+                    umma_commit(&acc_full[ab]);
+                }
+                __syncwarp();
+                ++g_chunk;
+                continue;
+            }
+            const uint32_t dhi = umma_desc_hi(p.kbytes);
+            const uint32_t kb16 = p.kbytes >> 4, row16 = p.hP * kb16 - (p.ksize - 1) * kb16;
+            const uint32_t xl_off = p.h_plane_bytes >> 4, wl_off = p.pw_tile_bytes >> 5, wt16 = p.pw_tile_bytes >> 4;
+            const bool k128 = p.kbytes == 128;
+            uint32_t acc = 0, wh = w16 | (1u << 16);
+            for (int ci = 0; ci < p.cin_chunks; ++ci, ++g_chunk) {
+                const int hb = g_chunk & 1;
+                mbar_wait(&patch_full[hb], (g_chunk >> 1) & 1);
+                tc_fence_after();
+                uint32_t xh = p16_0 + hb * pb16;
+                int kw = 0;
+                for (int tap = 0; tap < taps; ++tap) {
+                    const uint32_t xl = xh + xl_off, wl = wh + wl_off;
+                    const bool last_tap = tap == taps - 1;
+                    if (elect_one()) {
+                        if (!(p.dbg & 8)) {
+                        umma_pm3(t_main, t_corr, xh, xl, wh, wl, dhi, idesc, acc);
+                        umma_pm3(t_main, t_corr, xh + 2, xl + 2, wh + 2, wl + 2, dhi, idesc, 1u);
+                        }
+                        if (k128 && !(p.dbg & 8)) {
+                            umma_pm3(t_main, t_corr, xh + 4, xl + 4, wh + 4, wl + 4, dhi, idesc, 1u);
+                            umma_pm3(t_main, t_corr, xh + 6, xl + 6, wh + 6, wl + 6, dhi, idesc, 1u);
+                        }
+                        if (last_tap) umma_commit(&patch_empty[hb]);
+                        if (last_tap && ci == p.cin_chunks - 1) umma_commit(&acc_full[ab]);
+                    }
+                    __syncwarp();
+                    acc = 1;
+                    wh += wt16;
+                    if (++kw == p.ksize) { kw = 0; xh += row16; } else xh += kb16;
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue: two independent groups of 4 warps, group g owns accumulator set g and
+        // stage buffer g and takes every other item, so the (latency-bound) epilogues of two tiles are in flight
+        // while the MMAs of the following ones run =====================
+        const int grp = (warp - 2) >> 2, q = warp & 3;
+        const int n = q * 32 + lane;                              // this thread's pixel (TMEM lane)
+        const int et = (threadIdx.x - 64) & 127;
+        const int ld = p.pm_stage_ld;
+        float *my_stage = stage + grp * (p.pw_stage_bytes >> 2);
+        const uint32_t t_main = tmem_base + grp * 2 * N + (uint32_t(q * 32) << 16);
+        int k = 0;
+        for (int item = blockIdx.x + grp * gridDim.x; item < n_items; item += 2 * gridDim.x, ++k) {
+            int b, y0, x0;
+            decode_item(item, b, y0, x0);
+            mbar_wait(&acc_full[grp], k & 1);
+            tc_fence_after();
+            for (int c0 = 0; c0 < N; c0 += 16) {
+                uint32_t a[16], c2[16];
+                tmem_ld16(t_main + c0, a);
+                tmem_ld16(t_main + N + c0, c2);
+                tmem_ld_wait();
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float tv = __uint_as_float(a[i]) + __uint_as_float(c2[i]);
+                    tv = fmaf(tv, s_scale[c0 + i], s_bias[c0 + i]);
+                    v[i] = p.act ? fmaxf(tv, 0.1f * tv) : tv;
+                }
+                float4 *dst = reinterpret_cast<float4 *>(my_stage + n * ld + c0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
+            tc_fence_before();
+            if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+            if (et == 0) mbar_arrive(&acc_empty[grp]);
+            if (!(p.dbg & 4)) epilogue_store(p, my_stage, ld, p.pm_glog, b, y0, x0, 0, 0, et, 128);
+            if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.pm_tmem_cols) : "memory");
+}
+
+// uint8 HWC3 frame -> fp16 [pixel][8] (channels 3..7 zero), the integer values 0..255 exactly
+__global__ void __launch_bounds__(256) frames_to_c8_kernel(const uint8_t *__restrict__ src, uint4 *__restrict__ dst, long long npix) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
+        const uint8_t *s = src + 3 * i;
+        const __half2 a = __floats2half2_rn((float)s[0], (float)s[1]);
+        const __half2 b = __floats2half2_rn((float)s[2], 0.f);
+        uint4 o;
+        o.x = *reinterpret_cast<const uint32_t *>(&a);
+        o.y = *reinterpret_cast<const uint32_t *>(&b);
+        o.z = 0; o.w = 0;
+        dst[i] = o;
+    }
+}
+
+int conv_pm_init() {
+    cudaError_t e = cudaFuncSetAttribute(conv_pm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaFuncSetAttribute(conv_pm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+}
+
+int conv_pm_smem_bytes(const ConvParams &p) {
+    const int w = p.pm_mode == 1 ? p.pm_w_bytes : p.ksize * p.ksize * p.cin_chunks * p.pw_tile_bytes;
+    return 1024 /*align*/ + 2048 /*barriers, scale, bias*/ + 2 * p.pw_patch_bytes + 2 * p.pw_stage_bytes + w;
+}
+
+int launch_conv_pm(int n_sm, const CUtensorMap &x_hi, const CUtensorMap &x_lo, const CUtensorMap &w_hi,
+                   const CUtensorMap &w_lo, const ConvParams &p, cudaStream_t st) {
+    const int items = p.B * p.h_tiles_x * p.h_tiles_y;
+    const int smem = conv_pm_smem_bytes(p);
+    // two co-resident CTAs per SM when shared memory and TMEM allow (conv_1, conv_4): they hide each other's
+    // per-tile barrier and store latencies
+    const int per_sm = (2 * (smem + 1024) <= 227 * 1024 && 2 * p.pm_tmem_cols <= 512) ? 2 : 1;
+    const int grid = items < n_sm * per_sm ? items : n_sm * per_sm;
+    conv_pm_kernel<<<grid, kPmThreads, smem, st>>>(x_hi, x_lo, w_hi, w_lo, p);
+    return (int)cudaGetLastError();
+}
+
+int launch_frames_to_c8(const void *frames, void *dst, long long npix, cudaStream_t st) {
+    const int blocks = (int)((npix + 255) / 256 < 148 * 16 ? (npix + 255) / 256 : 148 * 16);
+    frames_to_c8_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint8_t *>(frames), reinterpret_cast<uint4 *>(dst), npix);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace b2t

@@ -54,6 +54,14 @@ struct ConvParams {
     int pw_stage_bytes;     // epilogue stage
     int pw_tile_bytes;      // one weight tile (hi + lo) = 2 * w_rows * kbytes
     int pw_stages;          // weight tiles that fit in the ring (<= 16)
+    // pixel-major variant (conv_pm.cu): pixels on the MMA's M dimension, all weight tiles resident in shared memory
+    int pm_mode;            // 0 = fp16 (hi,lo) activations, swizzled K chunks; 1 = conv_1: fp16 integer frame, 8 ch / pixel
+    int pm_n;               // MMA N = Cout rounded up to 16 (<= 128)
+    int pm_tmem_cols;       // power of two >= 4 * pm_n
+    int pm_stage_ld;        // floats per staged pixel (pm_n + 4)
+    int pm_glog;            // log2 of the 8-channel groups per pixel in the store phase
+    const unsigned char *pm_w;   // mode 1: packed weights [kh][plane][32 cout x 32 k, 128-byte core matrices]
+    int pm_w_bytes;
     int dbg;                // developer experiments (0 in production): 1 = weight TMA only for the first ring pass,
                             // 2 = patch TMA only for the first buffers, 4 = no epilogue stores, 8 = no MMAs (results are wrong)
     long long *trace;       // developer instrumentation (NULL in production): per-item clock64 stamps of CTA 0
@@ -124,6 +132,65 @@ __device__ __forceinline__ void emit8(const Dest &d, int b, int y, int x, int c,
             reinterpret_cast<float4 *>(p)[1] = bq;
         } else {
             for (int i = 0; i < nvalid; ++i) p[i] = d.accumulate_f ? p[i] + v[i] : v[i];
+        }
+    }
+}
+
+// Store phase shared by the conv epilogues: the tile sits in shared memory as stage[pixel n = r*hP + c][channel]
+// (ld floats per pixel); the epilogue threads walk (pixel, 8-channel group) items and
+// write 16-byte pieces: raw fp32 split-K partials, or hi/lo split planes with optional 2x2 max-pool, concat /
+// space-to-depth addressing through emit8().  glog = log2(channel groups per pixel) (4 for a 128-channel tile).
+// `et` = index of the calling thread among the `nthr` threads that share this tile's store phase.
+__device__ __forceinline__ void epilogue_store(const ConvParams &p, const float *stage, int ld, int glog, int b, int y0,
+                                               int x0, int cout0, int zsplit, int et, int nthr) {
+    const int g = et & ((1 << glog) - 1), ps = et >> glog, slots = nthr >> glog;
+    const int rows_valid = min(p.hR, p.H - y0), cols_valid = min(p.hC, p.W - x0);
+    if (p.splits != 1) {
+        const int chn = cout0 + g * 8;
+        if (chn < p.ldp) {
+            const long long mtot = (long long)p.B * p.H * p.W;
+            for (int r = 0; r < rows_valid; ++r) {
+                float *rowp = p.partial + ((long long)zsplit * mtot + ((long long)b * p.H + y0 + r) * p.W + x0) * p.ldp + chn;
+                for (int c = ps; c < cols_valid; c += slots) {
+                    const float4 *src = reinterpret_cast<const float4 *>(stage + (r * p.hP + c) * ld + g * 8);
+                    float4 *dst = reinterpret_cast<float4 *>(rowp + (long long)c * p.ldp);
+                    dst[0] = src[0];
+                    dst[1] = src[1];
+                }
+            }
+        }
+        return;
+    }
+    if (cout0 + g * 8 >= p.Cout) return;
+    // (pixel, group) items are spread over all threads: item -> (row, column) by one division per item
+    if (p.out.hi || p.out.f32) {
+        const int n_it = rows_valid * cols_valid;
+        for (int it = ps; it < n_it; it += slots) {
+            const int r = it / cols_valid, c = it - r * cols_valid;
+            const float4 *src = reinterpret_cast<const float4 *>(stage + (r * p.hP + c) * ld + g * 8);
+            const float4 lo4 = src[0], hi4 = src[1];
+            const float v8[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+            emit8(p.out, b, y0 + r, x0 + c, cout0 + g * 8, p.Cout, v8);
+        }
+    }
+    if (p.pool) {
+        const int pr = rows_valid >> 1, pc = cols_valid >> 1, n_it = pr * pc;
+        for (int it = ps; it < n_it; it += slots) {
+            const int r2 = it / pc, c2 = it - r2 * pc;
+            const float *s0 = stage + (2 * r2 * p.hP + 2 * c2) * ld + g * 8;
+            float v8[8];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float4 a0 = reinterpret_cast<const float4 *>(s0)[h];
+                const float4 a1 = reinterpret_cast<const float4 *>(s0 + ld)[h];
+                const float4 a2 = reinterpret_cast<const float4 *>(s0 + p.hP * ld)[h];
+                const float4 a3 = reinterpret_cast<const float4 *>(s0 + (p.hP + 1) * ld)[h];
+                v8[4 * h + 0] = fmaxf(fmaxf(a0.x, a1.x), fmaxf(a2.x, a3.x));
+                v8[4 * h + 1] = fmaxf(fmaxf(a0.y, a1.y), fmaxf(a2.y, a3.y));
+                v8[4 * h + 2] = fmaxf(fmaxf(a0.z, a1.z), fmaxf(a2.z, a3.z));
+                v8[4 * h + 3] = fmaxf(fmaxf(a0.w, a1.w), fmaxf(a2.w, a3.w));
+            }
+            emit8(p.pout, b, ((y0 >> 1) + r2), ((x0 >> 1) + c2), cout0 + g * 8, p.Cout, v8);
         }
     }
 }

@@ -63,7 +63,9 @@ def test_batch_one_and_float_frames_agree(keras_c2):
     assert (a[0] - b[0]).abs().max().item() < 1e-4
     xf = torch.from_numpy(yolo_oracle.normalize(frames).astype(np.float32)).cuda()
     c = e.forward(xf)
-    assert torch.equal(a, c)                                            # u8 LUT path == float32 input path
+    # uint8 frames take conv_1 through the tensor cores (exact integer operands, 1/255 folded into the scale);
+    # float32 frames through the direct fp32 kernel: same numbers up to fp32 rounding of conv_1
+    assert (a - c).abs().max().item() < 1e-4
 
 
 def test_tcgen05_engine_matches_simt_engine(keras_c2):
