@@ -188,6 +188,8 @@ static void choose_pm_tile(int H, int W, int ksize, bool pool, int row_bytes, bo
     }
 }
 
+static unsigned magic_for(int d) { return d <= 1 ? 0u : (unsigned)((0x100000000ull + (unsigned)d - 1) / (unsigned)d); }
+
 static int choose_splits_halo(int ctas, int cin_chunks, int taps, int n_sm) {
     const char *env = getenv("B2T_SPLITS");
     int best_s = 1;
@@ -768,7 +770,7 @@ static int run_conv(b2t_ctx *c, ConvLayer &l, int B, float *f32_dst, cudaStream_
         p.splits = 1;
         p.dbg = getenv("B2T_DBG") ? atoi(getenv("B2T_DBG")) : 0;
         p.pm_mode = 0;
-        p.pm_n = round_up(l.cout, 16);
+        p.pm_n = round_up(l.cout, 32);
         p.pm_tmem_cols = 4 * p.pm_n <= 128 ? 128 : 4 * p.pm_n <= 256 ? 256 : 512;
         p.pm_stage_ld = p.pm_n + 4;
         p.pm_glog = p.pm_n <= 32 ? 2 : p.pm_n <= 64 ? 3 : 4;
@@ -785,6 +787,7 @@ static int run_conv(b2t_ctx *c, ConvLayer &l, int B, float *f32_dst, cudaStream_
         p.hN = 128;
         p.pw_patch_bytes = 2 * p.h_plane_bytes;
         p.h_tiles_x = (p.W + p.hC - 1) / p.hC; p.h_tiles_y = (p.H + p.hR - 1) / p.hR;
+        p.magic_tx = magic_for(p.h_tiles_x); p.magic_ty = magic_for(p.h_tiles_y);
         if ((rc = launch_conv_pm(c->n_sm, l.tmXp_hi, l.tmXp_lo, l.tmWp_hi, l.tmWp_lo, p, st)))
             return fail(-2, "conv_pm launch (conv %d): %s", l.index, cudaGetErrorString((cudaError_t)rc));
         c->launches += 1;
@@ -879,8 +882,26 @@ static int run_conv1(b2t_ctx *c, const void *frames, int dtype, int B, cudaStrea
         p.pw_stage_bytes = (int)align_up((size_t)128 * 36 * 4, 1024);
         p.pm_w = c->d_blob + c->off_w1pm; p.pm_w_bytes = 3 * 4096;
         p.dbg = getenv("B2T_DBG") ? atoi(getenv("B2T_DBG")) : 0;
+        p.magic_tx = magic_for(p.h_tiles_x); p.magic_ty = magic_for(p.h_tiles_y);
+        static long long *d_trace = nullptr;
+        if (getenv("B2T_TRACE_CONV") && atoi(getenv("B2T_TRACE_CONV")) == 1) {
+            if (!d_trace) cudaMalloc(&d_trace, 64 * 16 * 8);
+            cudaMemsetAsync(d_trace, 0, 64 * 16 * 8, st);
+            p.trace = d_trace;
+        }
         if ((rc = launch_conv_pm(c->n_sm, l.tmXp_hi, l.tmXp_lo, l.tmXp_hi, l.tmXp_lo, p, st)))
             return fail(-2, "conv_pm launch (conv 1): %s", cudaGetErrorString((cudaError_t)rc));
+        if (p.trace) {
+            long long h[64 * 16];
+            cudaStreamSynchronize(st);
+            cudaMemcpy(h, d_trace, sizeof h, cudaMemcpyDeviceToHost);
+            const long long t0 = h[1];
+            fprintf(stderr, "[trace conv_1] item: tma_issue | mma: start acc_ok patch_ok issued | epi: wait acc_full phase1 stored (cycles rel.)\n");
+            for (int j = 0; j < 24; ++j)
+                fprintf(stderr, "  %2d: %7lld | %7lld %7lld %7lld %7lld | %7lld %7lld %7lld %7lld\n", j, h[j * 16] - t0, h[j * 16 + 1] - t0,
+                        h[j * 16 + 2] - t0, h[j * 16 + 3] - t0, h[j * 16 + 4] - t0, h[j * 16 + 5] - t0, h[j * 16 + 6] - t0,
+                        h[j * 16 + 7] - t0, h[j * 16 + 8] - t0);
+        }
         c->launches += 2;
         return 0;
     }

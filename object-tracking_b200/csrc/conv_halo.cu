@@ -106,7 +106,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_consta
     using Cfg = HaloCfg<kSmall>;
     constexpr int kHaloBufs = Cfg::kHaloBufs, kHaloBufBytes = Cfg::kHaloBufBytes, kWStages = Cfg::kWStages;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     uint8_t *s_halo = smem;
     uint8_t *s_w = smem + kHaloBufs * kHaloBufBytes;
     uint8_t *tail = s_w + kWStages * kWStageBytes;
@@ -259,7 +259,7 @@ conv_halo_persist_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
                          const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
                          const ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     uint8_t *tail = smem;                                        // barriers first (fixed offsets)
     uint64_t *patch_full = reinterpret_cast<uint64_t *>(tail);   // [2]
     uint64_t *patch_empty = patch_full + 2;

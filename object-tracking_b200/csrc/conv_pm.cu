@@ -41,7 +41,7 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant
                const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
                const ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     uint64_t *patch_full = reinterpret_cast<uint64_t *>(smem);   // [2]
     uint64_t *patch_empty = patch_full + 2;
     uint64_t *acc_full = patch_empty + 2;
@@ -92,10 +92,12 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
+    // item -> (image, tile row, tile column) with host-made magic multipliers (exact for item < 2^32 / divisor)
     auto decode_item = [&](int item, int &b, int &y0, int &x0) {
-        const int tx = item % p.h_tiles_x;  item /= p.h_tiles_x;
-        const int ty = item % p.h_tiles_y;
-        b = item / p.h_tiles_y;
+        const int t = p.magic_tx ? (int)__umulhi((unsigned)item, p.magic_tx) : item;
+        const int tx = item - t * p.h_tiles_x;
+        b = p.magic_ty ? (int)__umulhi((unsigned)t, p.magic_ty) : t;
+        const int ty = t - b * p.h_tiles_y;
         y0 = ty * p.hR; x0 = tx * p.hC;
     };
 
@@ -123,6 +125,7 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant
                 mbar_wait(&patch_empty[hb], ((g_chunk >> 1) & 1) ^ 1);
                 uint8_t *hdst = s_patch + hb * p.pw_patch_bytes;
                 const bool skip_x = (p.dbg & 2) && g_chunk >= 2;
+                if (p.trace && blockIdx.x == 0 && g_chunk < 64 && lane == 0) p.trace[g_chunk * 16 + 0] = clock64();
                 if (elect_one()) {
                     if (skip_x) mbar_arrive(&patch_full[hb]);
                     else {
@@ -144,8 +147,11 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant
         if (!ints) { mbar_wait(w_full, 0); tc_fence_after(); }
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
             const int ab = j & 1;
+            const bool tr = p.trace && blockIdx.x == 0 && j < 64 && lane == 0;
+            if (tr) p.trace[j * 16 + 1] = clock64();
             mbar_wait(&acc_empty[ab], ((j >> 1) & 1) ^ 1);       // the epilogue has drained this accumulator set
             tc_fence_after();
+            if (tr) p.trace[j * 16 + 2] = clock64();
             const uint32_t t_main = tmem_base + ab * 2 * N, t_corr = t_main + N;
             if (ints) {
                 // conv_1: A rows = pixels (16 B each, SBO 128 B, LBO 16 B -> a row spans 4 pixels = K 32);
@@ -153,6 +159,7 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant
                 const int hb = g_chunk & 1;
                 mbar_wait(&patch_full[hb], (g_chunk >> 1) & 1);
                 tc_fence_after();
+                if (tr) p.trace[j * 16 + 3] = clock64();
                 const uint32_t a_hi = (128u >> 4) | (1u << 14), b_hi = (512u >> 4) | (1u << 14);
                 const uint32_t xa = p16_0 + hb * pb16;                       // LBO field = 1 (16 B) from umma_desc_lo
                 const uint32_t wb = w16 | ((128u >> 4) << 16);
@@ -174,6 +181,7 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant
                     umma_commit(&acc_full[ab]);
                 }
                 __syncwarp();
+                if (tr) p.trace[j * 16 + 4] = clock64();
                 ++g_chunk;
                 continue;
             }
@@ -224,29 +232,38 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant
         for (int item = blockIdx.x + grp * gridDim.x; item < n_items; item += 2 * gridDim.x, ++k) {
             int b, y0, x0;
             decode_item(item, b, y0, x0);
+            const int jj = 2 * k + grp;
+            const bool tr = p.trace && blockIdx.x == 0 && jj < 64 && et == 0;
+            if (tr) p.trace[jj * 16 + 5] = clock64();
             mbar_wait(&acc_full[grp], k & 1);
             tc_fence_after();
-            for (int c0 = 0; c0 < N; c0 += 16) {
-                uint32_t a[16], c2[16];
-                tmem_ld16(t_main + c0, a);
-                tmem_ld16(t_main + N + c0, c2);
+            if (tr) p.trace[jj * 16 + 6] = clock64();
+            for (int c0 = 0; c0 < N; c0 += 32) {               // N is a multiple of 32 here (32 or 64)
+                uint32_t a[32], c2[32];
+                tmem_ld32(t_main + c0, a);
+                tmem_ld32(t_main + N + c0, c2);
                 tmem_ld_wait();
-                float v[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float tv = __uint_as_float(a[i]) + __uint_as_float(c2[i]);
-                    tv = fmaf(tv, s_scale[c0 + i], s_bias[c0 + i]);
-                    v[i] = p.act ? fmaxf(tv, 0.1f * tv) : tv;
-                }
                 float4 *dst = reinterpret_cast<float4 *>(my_stage + n * ld + c0);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                for (int i4 = 0; i4 < 8; ++i4) {
+                    const float4 sc = *reinterpret_cast<const float4 *>(s_scale + c0 + 4 * i4);
+                    const float4 bi = *reinterpret_cast<const float4 *>(s_bias + c0 + 4 * i4);
+                    float4 v;
+                    v.x = fmaf(__uint_as_float(a[4 * i4 + 0]) + __uint_as_float(c2[4 * i4 + 0]), sc.x, bi.x);
+                    v.y = fmaf(__uint_as_float(a[4 * i4 + 1]) + __uint_as_float(c2[4 * i4 + 1]), sc.y, bi.y);
+                    v.z = fmaf(__uint_as_float(a[4 * i4 + 2]) + __uint_as_float(c2[4 * i4 + 2]), sc.z, bi.z);
+                    v.w = fmaf(__uint_as_float(a[4 * i4 + 3]) + __uint_as_float(c2[4 * i4 + 3]), sc.w, bi.w);
+                    if (p.act) { v.x = fmaxf(v.x, 0.1f * v.x); v.y = fmaxf(v.y, 0.1f * v.y); v.z = fmaxf(v.z, 0.1f * v.z); v.w = fmaxf(v.w, 0.1f * v.w); }
+                    dst[i4] = v;
+                }
             }
             tc_fence_before();
             if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
             if (et == 0) mbar_arrive(&acc_empty[grp]);
+            if (tr) p.trace[jj * 16 + 7] = clock64();
             if (!(p.dbg & 4)) epilogue_store(p, my_stage, ld, p.pm_glog, b, y0, x0, 0, 0, et, 128);
             if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+            if (tr) p.trace[jj * 16 + 8] = clock64();
         }
     }
     tc_fence_before();

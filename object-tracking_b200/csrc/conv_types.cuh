@@ -62,6 +62,7 @@ struct ConvParams {
     int pm_glog;            // log2 of the 8-channel groups per pixel in the store phase
     const unsigned char *pm_w;   // mode 1: packed weights [kh][plane][32 cout x 32 k, 128-byte core matrices]
     int pm_w_bytes;
+    unsigned int magic_tx, magic_ty;   // ceil(2^32 / h_tiles_x), ceil(2^32 / h_tiles_y) (0 when the divisor is 1): fast item decode
     int dbg;                // developer experiments (0 in production): 1 = weight TMA only for the first ring pass,
                             // 2 = patch TMA only for the first buffers, 4 = no epilogue stores, 8 = no MMAs (results are wrong)
     long long *trace;       // developer instrumentation (NULL in production): per-item clock64 stamps of CTA 0
@@ -162,11 +163,13 @@ __device__ __forceinline__ void epilogue_store(const ConvParams &p, const float 
         return;
     }
     if (cout0 + g * 8 >= p.Cout) return;
-    // (pixel, group) items are spread over all threads: item -> (row, column) by one division per item
+    // (pixel, group) items are spread over all threads: item -> (row, column) by shift/mask (columns padded to a
+    // power of two, the padding items are skipped)
     if (p.out.hi || p.out.f32) {
-        const int n_it = rows_valid * cols_valid;
+        const int cs = 32 - __clz(cols_valid - 1), n_it = rows_valid << cs;
         for (int it = ps; it < n_it; it += slots) {
-            const int r = it / cols_valid, c = it - r * cols_valid;
+            const int r = it >> cs, c = it & ((1 << cs) - 1);
+            if (c >= cols_valid) continue;
             const float4 *src = reinterpret_cast<const float4 *>(stage + (r * p.hP + c) * ld + g * 8);
             const float4 lo4 = src[0], hi4 = src[1];
             const float v8[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
@@ -174,9 +177,11 @@ __device__ __forceinline__ void epilogue_store(const ConvParams &p, const float 
         }
     }
     if (p.pool) {
-        const int pr = rows_valid >> 1, pc = cols_valid >> 1, n_it = pr * pc;
+        const int pr = rows_valid >> 1, pc = cols_valid >> 1;
+        const int cs = 32 - __clz(max(pc, 1) - 1), n_it = pr << cs;
         for (int it = ps; it < n_it; it += slots) {
-            const int r2 = it / pc, c2 = it - r2 * pc;
+            const int r2 = it >> cs, c2 = it & ((1 << cs) - 1);
+            if (c2 >= pc) continue;
             const float *s0 = stage + (2 * r2 * p.hP + 2 * c2) * ld + g * 8;
             float v8[8];
 #pragma unroll

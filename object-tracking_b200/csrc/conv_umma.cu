@@ -43,7 +43,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     using Cfg = UmmaCfg<BN>;
     constexpr int kStages = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     uint8_t *tail = smem + kStages * Cfg::kStageBytes;
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(tail);
     uint64_t *empty_bar = full_bar + kStages;
