@@ -3,11 +3,13 @@
 
 Workload at N=1 = BASELINE.json configs[1]: TinyTracker = YOLOv2-416 (80 COCO classes, darknet semantics,
 as models_detection/YOLO.py drives it) + LSTM(512) head, one stream, a synthetic 300-frame clip.  One
-"step" = one batch as the reference's config.json sets it: train.batch_size (4) windows of
-model_tracker.sequence_length (4) consecutive frames of the clip = 16 frames (windows are independent: the
-Keras LSTM is stateless across them, TinyTracker.py:26-37).  Per step: one batched detector pass, region
-decode + NMS, detection choice, feature pooling, the LSTM input projection for all 16 frames, 4 sequential
-recurrent steps over the 4 windows, one batched Dense head.  --windows 1 gives the single-window latency case.  N>1: every rank runs its own
+"step" = one batch of --windows (default 9) windows of model_tracker.sequence_length (4) consecutive frames of
+the clip = 36 frames (windows are independent: the Keras LSTM is stateless across them, TinyTracker.py:26-37;
+the detector is stateless per frame).  9 windows are chosen for the machine: 36 images x 8 output-channel tiles
+= 288 work items on the 13x13 layers ~ 2 x 148 SMs; --windows 4 is the reference's config.json train.batch_size.
+Per step: one batched detector pass, region decode + NMS, detection choice, feature pooling, the LSTM input
+projection for all frames, 4 sequential recurrent steps over the windows, one batched Dense head.
+--windows 1 gives the single-window latency case.  N>1: every rank runs its own
 stream(s) -- independent units, no data-path collective; one NCCL broadcast of the packed weights at init.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--windows S] [--impl reference]
@@ -320,8 +322,8 @@ def main_b200(args):
                 # The conv stack is tensor-bound, not HBM-bound: parity needs 3 fp16 MMAs per product (DESIGN.md
                 # section 4), so its tensor floor (3*flops / peak) is above its HBM floor at every batch size.
                 # `achieved` = ALGORITHMIC flops (1x) / measured time; the HBM view is kept beside it.
-                "roofline": {"bound": "tensor", "kernel": "YOLOv2 conv stack = conv1_direct + 22x conv_halo_kernel "
-                                                          "(+ split-K epilogues), one CUDA-graph launch per step",
+                "roofline": {"bound": "tensor", "kernel": "YOLOv2 conv stack = frames_to_c8 + 3x conv_pm_kernel + 20x conv_halo_*"
+                                                          "kernel (+ split-K epilogues), one CUDA-graph launch per step",
                              "achieved": flops_per_fwd / (fwd_ms * 1e-3) / 1e12, "peak": tflops, "unit": "TFLOP/s",
                              "frac": flops_per_fwd / (fwd_ms * 1e-3) / 1e12 / tflops, "traffic": None,
                              "peak_source": src + " (cuBLAS bf16, sustained)", "launch_ms": fwd_ms,
@@ -344,7 +346,9 @@ if __name__ == "__main__":
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--windows", type=int, default=4, help="independent 4-frame windows (streams) per GPU per step")
+    ap.add_argument("--windows", type=int, default=9,
+                    help="independent 4-frame windows per GPU per step (9 x 4 = 36 frames: 36 images x 8 cout tiles = 288 "
+                         "work items ~ 2 x 148 SMs for the 13x13 layers)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()

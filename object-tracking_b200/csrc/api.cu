@@ -818,7 +818,7 @@ static int run_conv(b2t_ctx *c, ConvLayer &l, int B, float *f32_dst, cudaStream_
         { static const int dbg = getenv("B2T_DBG") ? atoi(getenv("B2T_DBG")) : 0; p.dbg = dbg; }
         static long long *d_trace = nullptr;
         const char *tr = getenv("B2T_TRACE_CONV");
-        if (persist && tr && atoi(tr) == l.index) {
+        if (tr && atoi(tr) == l.index) {
             if (!d_trace) cudaMalloc(&d_trace, 64 * 8 * 8);
             cudaMemsetAsync(d_trace, 0, 64 * 8 * 8, st);
             p.trace = d_trace;
@@ -835,8 +835,19 @@ static int run_conv(b2t_ctx *c, ConvLayer &l, int B, float *f32_dst, cudaStream_
                 fprintf(stderr, "  %2d: %7lld | %7lld %7lld %7lld | %7lld %7lld %7lld\n", j, h[j * 8] - t0, h[j * 8 + 1] - t0,
                         h[j * 8 + 2] - t0, h[j * 8 + 3] - t0, h[j * 8 + 4] - t0, h[j * 8 + 5] - t0, h[j * 8 + 6] - t0);
         }
-        if (!persist)
-            rc = launch_conv_halo(l.h_small, l.tmX_hi, l.tmX_lo, l.tmW_hi, l.tmW_lo, p, st);
+        if (!persist) {
+            rc = launch_conv_halo(c->n_sm, l.h_small, l.tmX_hi, l.tmX_lo, l.tmW_hi, l.tmW_lo, p, st);
+            if (p.trace) {
+                long long h[64 * 8];
+                cudaStreamSynchronize(st);
+                cudaMemcpy(h, d_trace, sizeof h, cudaMemcpyDeviceToHost);
+                const long long t0 = h[1];
+                fprintf(stderr, "[trace conv_%d N=%d splits=%d] item: mma: start acc_ok patch_ok issue_end | epi: wait accum_ok done ; last phase1 %lld\n", l.index, p.hN, p.splits, h[511] - t0);
+                for (int j = 0; j < 4; ++j)
+                    fprintf(stderr, "  %2d: %7lld %7lld %7lld %7lld | %7lld %7lld %7lld\n", j, h[j * 8 + 1] - t0, h[j * 8 + 2] - t0,
+                            h[j * 8 + 3] - t0, h[j * 8 + 7] - t0, h[j * 8 + 4] - t0, h[j * 8 + 5] - t0, h[j * 8 + 6] - t0);
+            }
+        }
         if (rc)
             return fail(-2, "conv_halo launch (conv %d): %s", l.index, cudaGetErrorString((cudaError_t)rc));
         c->launches += 1;

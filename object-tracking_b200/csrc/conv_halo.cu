@@ -76,6 +76,7 @@ __device__ __forceinline__ void halo_epilogue(const ConvParams &p, float *stage,
     tc_fence_before();
     asm volatile("bar.sync 1, 256;" ::: "memory");
     if (acc_free && et == 0) mbar_arrive(acc_free);
+    if (p.trace && blockIdx.x == 0 && et == 0) p.trace[511] = clock64();   // last phase-1 completion (developer trace)
     if (p.dbg & 4) return;
     epilogue_store(p, stage, kStageLd, 4, b, y0, x0, cout0, zsplit, et, kEpiThreads);
 }
@@ -114,32 +115,43 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_consta
     uint64_t *halo_empty = halo_full + 2;                       // [2]
     uint64_t *w_full = halo_empty + 2;                          // [kWStages]
     uint64_t *w_empty = w_full + kWStages;                      // [kWStages]
-    uint64_t *accum_bar = w_empty + kWStages;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_bar + 1);
+    uint64_t *accum_bar = w_empty + kWStages;                   // MMA -> epilogue: the item's accumulators are complete
+    uint64_t *acc_empty = accum_bar + 1;                        // epilogue -> MMA: TMEM has been read
+    uint64_t *stage_free = acc_empty + 1;                       // epilogue -> producer: the staged tile has been stored
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(stage_free + 1);
 
     // warp-uniform role index: the shuffle lets the compiler prove uniformity, so the role branches are uniform
     // branches and the MMA issuer's descriptor arithmetic stays in uniform registers (no R2UR / waterfall loops
     // around UTCHMMA -- the single issuing thread is otherwise the kernel's bottleneck)
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
-    int t = blockIdx.x;
-    const int tx = t % p.h_tiles_x;  t /= p.h_tiles_x;
-    const int ty = t % p.h_tiles_y;
-    const int b = t / p.h_tiles_y;
-    const int x0 = tx * p.hC, y0 = ty * p.hR;
-    const int cout0 = blockIdx.y * 128;
     const int pad = p.ksize >> 1, taps = p.ksize * p.ksize;
-    const int per = (p.cin_chunks + p.splits - 1) / p.splits;
-    const int c_begin = blockIdx.z * per, c_end = min(p.cin_chunks, c_begin + per);
-    const int n_chunks = c_end - c_begin;                      // host guarantees >= 1
     const int N = p.hN;
-    const int n_main = max(1, min(min(p.n_main, Cfg::kTmemCols / N - 1), n_chunks * taps));
+    // The CTA is persistent: it walks items (pixel tile, cout tile, K split) blockIdx.x, + gridDim.x, ...  Barriers,
+    // TMEM and the weight ring live across items; the weights of the next item are prefetched during the epilogue
+    // of the current one (the staged tile aliases the patch buffers only, unless N > 248).
+    const int gx = p.B * p.h_tiles_x * p.h_tiles_y, gy = (p.Cout + 127) >> 7;
+    const int n_items = gx * gy * p.splits;
+    const int per = (p.cin_chunks + p.splits - 1) / p.splits;
+    const bool stage_hits_w = N * kStageLd * 4 > kHaloBufs * kHaloBufBytes;
+    auto decode_item = [&](int item, int &b, int &y0, int &x0, int &cout0, int &z, int &c_begin, int &n_chunks) {
+        int t = item % gx;
+        const int rest = item / gx;
+        const int tx = t % p.h_tiles_x;  t /= p.h_tiles_x;
+        const int ty = t % p.h_tiles_y;
+        b = t / p.h_tiles_y;
+        x0 = tx * p.hC; y0 = ty * p.hR;
+        cout0 = (rest % gy) * 128;
+        z = rest / gy;
+        c_begin = z * per;
+        n_chunks = min(p.cin_chunks, c_begin + per) - c_begin;         // host guarantees >= 1
+    };
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmX_hi); tma_prefetch_desc(&tmX_lo);
         tma_prefetch_desc(&tmW_hi); tma_prefetch_desc(&tmW_lo);
         for (int i = 0; i < kHaloBufs; ++i) { mbar_init(&halo_full[i], 1); mbar_init(&halo_empty[i], 1); }
         for (int i = 0; i < kWStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-        mbar_init(accum_bar, 1);
+        mbar_init(accum_bar, 1); mbar_init(acc_empty, 1); mbar_init(stage_free, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -150,92 +162,126 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_consta
 
     if (warp == 0) {
         // ===================== TMA producer (whole warp runs the uniform loops, one elected lane issues) =====
-        int ws = 0;
+        int ws = 0, g_it = 0, k = 0;
         uint32_t wphase = 0;
         const uint32_t halo_tx = 2u * p.h_rows * p.hP * p.kbytes, w_tx = 2u * 128u * p.kbytes;
         const int kelems = p.kbytes / 2;
-        for (int it = 0; it < n_chunks; ++it) {
-            const int ci = c_begin + it, hb = it % kHaloBufs;
-            mbar_wait(&halo_empty[hb], ((it / kHaloBufs) & 1) ^ 1);
-            uint8_t *hdst = s_halo + hb * kHaloBufBytes;
-            const bool skip_x = (p.dbg & 2) && it >= kHaloBufs;
-            if (elect_one()) {
-                if (skip_x) mbar_arrive(&halo_full[hb]);
-                else {
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
+            int b, y0, x0, cout0, z, c_begin, n_chunks;
+            decode_item(item, b, y0, x0, cout0, z, c_begin, n_chunks);
+            // weight tiles are requested strictly in (chunk, tap) order; (w_it, w_tap) is the next one
+            int w_it = 0, w_tap = 0, w_seq = 0;
+            auto issue_next_w = [&]() {
+                mbar_wait(&w_empty[ws], wphase ^ 1);
+                uint8_t *wdst = s_w + ws * kWStageBytes;
+                const int kcoord = (w_tap * p.cin_chunks + c_begin + w_it) * kelems;
+                if (elect_one()) {
+                    mbar_expect_tx(&w_full[ws], w_tx);
+                    tma_load_2d(&tmW_hi, &w_full[ws], wdst, kcoord, cout0, kEvictLast);
+                    tma_load_2d(&tmW_lo, &w_full[ws], wdst + kWTileBytes, kcoord, cout0, kEvictLast);
+                }
+                __syncwarp();
+                ++w_seq;
+                if (++w_tap == taps) { w_tap = 0; ++w_it; }
+                if (++ws == kWStages) { ws = 0; wphase ^= 1; }
+            };
+            if (k > 0) {
+                if (!stage_hits_w) {
+                    const int pf = min(kWStages, n_chunks * taps);
+                    while (w_seq < pf) issue_next_w();
+                }
+                mbar_wait(stage_free, (k - 1) & 1);          // the previous item's staged tile has left the patch buffers
+            }
+            int seq = 0;
+            for (int it = 0; it < n_chunks; ++it, ++g_it) {
+                const int ci = c_begin + it, hb = g_it % kHaloBufs;
+                mbar_wait(&halo_empty[hb], ((g_it / kHaloBufs) & 1) ^ 1);
+                uint8_t *hdst = s_halo + hb * kHaloBufBytes;
+                if (elect_one()) {
                     mbar_expect_tx(&halo_full[hb], halo_tx);
                     tma_load_4d(&tmX_hi, &halo_full[hb], hdst, ci * kelems, x0 - pad, y0 - pad, b, kEvictNormal);
                     tma_load_4d(&tmX_lo, &halo_full[hb], hdst + p.h_plane_bytes, ci * kelems, x0 - pad, y0 - pad, b, kEvictNormal);
                 }
-            }
-            __syncwarp();
-            int kcoord = ci * kelems;
-            for (int tap = 0; tap < taps; ++tap) {
-                mbar_wait(&w_empty[ws], wphase ^ 1);
-                const bool skip_w = (p.dbg & 1) && (it || tap >= kWStages);
-                uint8_t *wdst = s_w + ws * kWStageBytes;
-                if (elect_one()) {
-                    if (skip_w) mbar_arrive(&w_full[ws]);
-                    else {
-                        mbar_expect_tx(&w_full[ws], w_tx);
-                        tma_load_2d(&tmW_hi, &w_full[ws], wdst, kcoord, cout0, kEvictLast);
-                        tma_load_2d(&tmW_lo, &w_full[ws], wdst + kWTileBytes, kcoord, cout0, kEvictLast);
-                    }
-                }
                 __syncwarp();
-                kcoord += p.cin_chunks * kelems;
-                if (++ws == kWStages) { ws = 0; wphase ^= 1; }
+                for (int tap = 0; tap < taps; ++tap, ++seq)
+                    if (seq == w_seq) issue_next_w();
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         // Everything below is warp-uniform (kernel parameters, loop counters, shuffled values): descriptors are
-        // built with uniform-datapath adds and lane 0 only executes the tcgen05 instructions themselves.
+        // built with uniform-datapath adds and one elected lane only executes the tcgen05 instructions themselves.
         const uint32_t idesc = umma_idesc_f16(128, N), dhi = umma_desc_hi(p.kbytes);
-        const uint32_t t_corr = tmem_base + n_main * N;
         const uint32_t kb16 = p.kbytes >> 4, row16 = p.hP * kb16 - (p.ksize - 1) * kb16;
         const uint32_t w16_0 = umma_desc_lo(smem_u32(s_w)), h16_0 = umma_desc_lo(smem_u32(s_halo));
         const uint32_t xl_off = p.h_plane_bytes >> 4;
         const bool k128 = p.kbytes == 128, issue = !(p.dbg & 8);
-        int ws = 0, mi = 0;
-        uint32_t wphase = 0, first = 1, am = 0;
-        for (int it = 0; it < n_chunks; ++it) {
-            const int hb = it % kHaloBufs;
-            mbar_wait(&halo_full[hb], (it / kHaloBufs) & 1);
-            uint32_t xh = h16_0 + hb * (kHaloBufBytes >> 4);
-            int kw = 0;
-            for (int tap = 0; tap < taps; ++tap) {
-                mbar_wait(&w_full[ws], wphase);
-                tc_fence_after();
-                const uint32_t wh = w16_0 + ws * (kWStageBytes >> 4), wl = wh + (kWTileBytes >> 4);
-                const uint32_t xl = xh + xl_off;
-                const uint32_t t_main = tmem_base + mi * N;
-                const uint32_t ac = first ^ 1u;
-                const bool last_tap = tap == taps - 1;
-                if (elect_one()) {
-                    if (issue) {
-                        umma_kstep(t_main, t_corr, wh, wl, xh, xl, dhi, idesc, am, ac);
-                        umma_kstep(t_main, t_corr, wh + 2, wl + 2, xh + 2, xl + 2, dhi, idesc, 1u, 1u);
-                        if (k128) {
-                            umma_kstep(t_main, t_corr, wh + 4, wl + 4, xh + 4, xl + 4, dhi, idesc, 1u, 1u);
-                            umma_kstep(t_main, t_corr, wh + 6, wl + 6, xh + 6, xl + 6, dhi, idesc, 1u, 1u);
+        int ws = 0, g_it = 0, k = 0;
+        uint32_t wphase = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
+            int b, y0, x0, cout0, z, c_begin, n_chunks;
+            decode_item(item, b, y0, x0, cout0, z, c_begin, n_chunks);
+            const int n_main = max(1, min(min(p.n_main, Cfg::kTmemCols / N - 1), n_chunks * taps));
+            const uint32_t t_corr = tmem_base + n_main * N;
+            const bool tr = p.trace && blockIdx.x == 0 && k < 64 && lane == 0;
+            if (tr) p.trace[k * 8 + 1] = clock64();
+            if (k > 0) { mbar_wait(acc_empty, (k - 1) & 1); tc_fence_after(); }   // the epilogue has read the accumulators
+            if (tr) p.trace[k * 8 + 2] = clock64();
+            int mi = 0;
+            uint32_t first = 1, am = 0;
+            for (int it = 0; it < n_chunks; ++it, ++g_it) {
+                const int hb = g_it % kHaloBufs;
+                mbar_wait(&halo_full[hb], (g_it / kHaloBufs) & 1);
+                if (tr && it == 0) p.trace[k * 8 + 3] = clock64();
+                uint32_t xh = h16_0 + hb * (kHaloBufBytes >> 4);
+                int kw = 0;
+                for (int tap = 0; tap < taps; ++tap) {
+                    mbar_wait(&w_full[ws], wphase);
+                    tc_fence_after();
+                    const uint32_t wh = w16_0 + ws * (kWStageBytes >> 4), wl = wh + (kWTileBytes >> 4);
+                    const uint32_t xl = xh + xl_off;
+                    const uint32_t t_main = tmem_base + mi * N;
+                    const uint32_t ac = first ^ 1u;
+                    const bool last_tap = tap == taps - 1;
+                    if (elect_one()) {
+                        if (issue) {
+                            umma_kstep(t_main, t_corr, wh, wl, xh, xl, dhi, idesc, am, ac);
+                            umma_kstep(t_main, t_corr, wh + 2, wl + 2, xh + 2, xl + 2, dhi, idesc, 1u, 1u);
+                            if (k128) {
+                                umma_kstep(t_main, t_corr, wh + 4, wl + 4, xh + 4, xl + 4, dhi, idesc, 1u, 1u);
+                                umma_kstep(t_main, t_corr, wh + 6, wl + 6, xh + 6, xl + 6, dhi, idesc, 1u, 1u);
+                            }
                         }
+                        umma_commit(&w_empty[ws]);
+                        if (last_tap) umma_commit(&halo_empty[hb]);
+                        if (last_tap && it == n_chunks - 1) umma_commit(accum_bar);
                     }
-                    umma_commit(&w_empty[ws]);
-                    if (last_tap) umma_commit(&halo_empty[hb]);
-                    if (last_tap && it == n_chunks - 1) umma_commit(accum_bar);
+                    __syncwarp();
+                    first = 0;
+                    if (++mi == n_main) { mi = 0; am = 1; }          // every main accumulator has been written once
+                    if (++kw == p.ksize) { kw = 0; xh += row16; } else xh += kb16;   // next tap: patch start shifted by (kh*hP + kw) rows
+                    if (++ws == kWStages) { ws = 0; wphase ^= 1; }
                 }
-                __syncwarp();
-                first = 0;
-                if (++mi == n_main) { mi = 0; am = 1; }          // every main accumulator has been written once
-                if (++kw == p.ksize) { kw = 0; xh += row16; } else xh += kb16;   // next tap: patch start shifted by (kh*hP + kw) rows
-                if (++ws == kWStages) { ws = 0; wphase ^= 1; }
             }
+            if (tr) p.trace[k * 8 + 7] = clock64();
         }
     } else {
-        // ===================== epilogue (the operand buffers are dead once accum_bar fires) =====================
-        mbar_wait(accum_bar, 0);
-        tc_fence_after();
-        halo_epilogue(p, reinterpret_cast<float *>(smem), tmem_base, n_main + 1, N, b, y0, x0, cout0, blockIdx.z, nullptr);
+        // ===================== epilogue (the patch buffers are dead once accum_bar fires) =====================
+        int k = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
+            int b, y0, x0, cout0, z, c_begin, n_chunks;
+            decode_item(item, b, y0, x0, cout0, z, c_begin, n_chunks);
+            const int n_main = max(1, min(min(p.n_main, Cfg::kTmemCols / N - 1), n_chunks * taps));
+            const bool tr = p.trace && blockIdx.x == 0 && k < 64 && threadIdx.x == 64;
+            if (tr) p.trace[k * 8 + 4] = clock64();
+            mbar_wait(accum_bar, k & 1);
+            tc_fence_after();
+            if (tr) p.trace[k * 8 + 5] = clock64();
+            halo_epilogue(p, reinterpret_cast<float *>(smem), tmem_base, n_main + 1, N, b, y0, x0, cout0, z, acc_empty);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (threadIdx.x == 64) mbar_arrive(stage_free);
+            if (tr) p.trace[k * 8 + 6] = clock64();
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -445,9 +491,11 @@ int launch_conv_halo_persist(int n_sm, const CUtensorMap &x_hi, const CUtensorMa
     return (int)cudaGetLastError();
 }
 
-int launch_conv_halo(bool small, const CUtensorMap &x_hi, const CUtensorMap &x_lo, const CUtensorMap &w_hi,
+int launch_conv_halo(int n_sm, bool small, const CUtensorMap &x_hi, const CUtensorMap &x_lo, const CUtensorMap &w_hi,
                      const CUtensorMap &w_lo, const ConvParams &p, cudaStream_t st) {
-    dim3 grid(p.B * p.h_tiles_x * p.h_tiles_y, (p.Cout + 127) / 128, p.splits);
+    const int items = p.B * p.h_tiles_x * p.h_tiles_y * ((p.Cout + 127) / 128) * p.splits;
+    const int cap = n_sm * (small ? 2 : 1);
+    const int grid = items < cap ? items : cap;
     if (small)
         conv_halo_kernel<true><<<grid, kHaloThreads, HaloCfg<true>::kSmemBytes, st>>>(x_hi, x_lo, w_hi, w_lo, p);
     else

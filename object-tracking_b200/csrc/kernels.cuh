@@ -84,7 +84,7 @@ int launch_conv_umma(int BN, const CUtensorMap &a_hi, const CUtensorMap &a_lo, c
                      const CUtensorMap &b_lo, const ConvParams &p, cudaStream_t st);
 int conv_umma_init();
 int conv_halo_init();
-int launch_conv_halo(bool small, const CUtensorMap &x_hi, const CUtensorMap &x_lo, const CUtensorMap &w_hi,
+int launch_conv_halo(int n_sm, bool small, const CUtensorMap &x_hi, const CUtensorMap &x_lo, const CUtensorMap &w_hi,
                      const CUtensorMap &w_lo, const ConvParams &p, cudaStream_t st);
 int launch_conv_halo_persist(int n_sm, const CUtensorMap &x_hi, const CUtensorMap &x_lo, const CUtensorMap &w_hi,
                              const CUtensorMap &w_lo, const ConvParams &p, cudaStream_t st);
