@@ -325,7 +325,10 @@ def main_b200(args):
                 "roofline": {"bound": "tensor", "kernel": "YOLOv2 conv stack = frames_to_c8 + 3x conv_pm_kernel + 20x conv_halo_*"
                                                           "kernel (+ split-K epilogues), one CUDA-graph launch per step",
                              "achieved": flops_per_fwd / (fwd_ms * 1e-3) / 1e12, "peak": tflops, "unit": "TFLOP/s",
-                             "frac": flops_per_fwd / (fwd_ms * 1e-3) / 1e12 / tflops, "traffic": None,
+                             "frac": flops_per_fwd / (fwd_ms * 1e-3) / 1e12 / tflops,
+                             # dram__bytes_read+write summed over the stack's 23 conv kernels of one 36-frame launch,
+                             # ncu --set full capture in profiles/ (split-K epilogues and the u8->fp16 copy not included)
+                             "traffic": 2.140e9 if B == 36 else None,
                              "peak_source": src + " (cuBLAS bf16, sustained)", "launch_ms": fwd_ms,
                              "algorithmic_flops_per_launch": flops_per_fwd,
                              "issued_tflops": 3 * flops_per_fwd / (fwd_ms * 1e-3) / 1e12,
