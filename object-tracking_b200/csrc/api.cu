@@ -1075,6 +1075,7 @@ struct b2t_lstm {
     float *d_wp = nullptr, *d_bias = nullptr, *d_wd = nullptr, *d_bd = nullptr;
     float *d_h[2] = {nullptr, nullptr}, *d_c = nullptr;
     float *d_zx = nullptr, *d_hseq = nullptr;      // (max_streams*kMaxT, 4u) / (max_streams*kMaxT, u) sequence scratch
+    unsigned int *d_counter = nullptr;             // grid barrier of lstm_seq_kernel
     int cur = 0;
     bool have = false;
 };
@@ -1090,7 +1091,7 @@ extern "C" int b2t_lstm_create(b2t_ctx *ctx, int n_feat, int n_det, int units, i
         cudaMalloc(&l->d_h[0], (size_t)max_streams * units * 4) || cudaMalloc(&l->d_h[1], (size_t)max_streams * units * 4) ||
         cudaMalloc(&l->d_c, (size_t)max_streams * units * 4) ||
         cudaMalloc(&l->d_zx, (size_t)max_streams * kMaxT * 4 * units * 4) ||
-        cudaMalloc(&l->d_hseq, (size_t)max_streams * kMaxT * units * 4)) {
+        cudaMalloc(&l->d_hseq, (size_t)max_streams * kMaxT * units * 4) || cudaMalloc(&l->d_counter, 256)) {
         b2t_lstm_destroy(l);
         return fail(-2, "b2t_lstm_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
@@ -1105,6 +1106,7 @@ extern "C" void b2t_lstm_destroy(b2t_lstm *l) {
     if (!l) return;
     cudaFree(l->d_wp); cudaFree(l->d_bias); cudaFree(l->d_wd); cudaFree(l->d_bd);
     cudaFree(l->d_h[0]); cudaFree(l->d_h[1]); cudaFree(l->d_c); cudaFree(l->d_zx); cudaFree(l->d_hseq);
+    cudaFree(l->d_counter);
     delete l;
 }
 
@@ -1192,9 +1194,22 @@ extern "C" int b2t_lstm_sequence(b2t_lstm *l, const float *fv, const float *det,
     // (1) input projection of all S*T rows at once: it does not depend on the recurrent state
     p.mode = 1; p.fv = fv; p.det = det; p.fv_stride = l->n_feat; p.det_stride = l->n_det;
     p.S = R; p.zx = l->d_zx; p.zx_stride = 4 * u; p.h_in = l->d_h[l->cur]; p.h_out = l->d_h[l->cur]; p.c = l->d_c;
-    if ((rc = launch_lstm_gates(p, st))) return fail(-2, "lstm launch: %s", cudaGetErrorString((cudaError_t)rc));
-    // (2) T sequential recurrent steps over the S streams (h*U + gates); h_t kept for the Dense head
-    for (int t = 0; t < T; ++t) {
+    rc = launch_lstm_proj(p, st);                                  // one pass over the weights for all rows
+    if (rc == -1) rc = launch_lstm_gates(p, st);
+    if (rc) return fail(-2, "lstm launch: %s", cudaGetErrorString((cudaError_t)rc));
+    // (2) T sequential recurrent steps over the S streams (h*U + gates); h_t kept for the Dense head:
+    //     one fused launch with a grid barrier between steps when the shape allows, else one launch per step
+    p.mode = 2; p.S = S; p.zx = l->d_zx; p.h_seq = l->d_hseq;
+    rc = launch_lstm_seq(p, T, l->d_h[l->cur], l->d_h[l->cur ^ 1], l->d_counter, l->ctx ? l->ctx->n_sm : 132, st);
+    if (rc > 0) return fail(-2, "lstm launch: %s", cudaGetErrorString((cudaError_t)rc));
+    const bool fused = rc == 0;
+    if (fused) {
+        if ((T & 1) && S < l->max_streams)
+            CK(cudaMemcpyAsync(l->d_h[l->cur ^ 1] + (size_t)S * u, l->d_h[l->cur] + (size_t)S * u,
+                               (size_t)(l->max_streams - S) * u * 4, cudaMemcpyDeviceToDevice, st));
+        l->cur ^= (T & 1);
+    }
+    for (int t = 0; t < T && !fused; ++t) {
         const int nxt = l->cur ^ 1;
         p.mode = 2; p.S = S;
         p.zx = l->d_zx + (size_t)t * 4 * u; p.zx_stride = T * 4 * u;
@@ -1209,7 +1224,7 @@ extern "C" int b2t_lstm_sequence(b2t_lstm *l, const float *fv, const float *det,
     // (3) Dense(n_out, sigmoid) on all S*T hidden states
     if ((rc = launch_dense_sigmoid(l->d_hseq, l->d_wd, l->d_bd, u, l->n_out, R, y, l->n_out, st)))
         return fail(-2, "dense launch: %s", cudaGetErrorString((cudaError_t)rc));
-    if (l->ctx) l->ctx->launches += T + 2;
+    if (l->ctx) l->ctx->launches += fused ? 3 : T + 2;
     return 0;
 }
 

@@ -100,6 +100,8 @@ int launch_planes_to_f32(const op_t *hi, long long plane, int pix_stride, int ch
                          float *out, cudaStream_t st);
 int launch_decode(bool darknet, const DecodeParams &p, cudaStream_t st);
 int launch_lstm_gates(const LstmParams &p, cudaStream_t st);
+int launch_lstm_proj(const LstmParams &p, cudaStream_t st);      // -1 = shape not supported, use lstm_gates mode 1
+int launch_lstm_seq(const LstmParams &p, int T, float *h_a, float *h_b, unsigned int *counter, int n_sm, cudaStream_t st);   // -1 = fall back
 int launch_dense_sigmoid(const float *h, const float *wd, const float *bd, int units, int n_out, int S, float *y,
                          int y_stride, cudaStream_t st);
 int launch_pool_features(const PoolParams &p, cudaStream_t st);

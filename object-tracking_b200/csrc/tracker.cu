@@ -111,6 +111,205 @@ __global__ void __launch_bounds__(kLstmThreads) lstm_gates_kernel(const LstmPara
     }
 }
 
+// ---------------------------------------------------------------- batched input projection
+// zx[r] = x[r] * W + b for all R rows (frames) in ONE pass over the weights: a thread keeps its share of the CTA's
+// weight slab (rows rq, rq+64, ... x one float4 of the 16 columns) in registers -- all loads in flight at once -- and
+// walks the rows in groups of 8.  Same thread layout and summation order as lstm_gates_kernel mode 1 (which it
+// replaces when n_feat + n_det <= 64 * kProjMaxK).
+constexpr int kProjMaxK = 17;
+__global__ void __launch_bounds__(kLstmThreads) lstm_proj_kernel(const LstmParams p) {
+    __shared__ float red[8][16][kMaxStreams];
+    __shared__ __align__(16) float xs[kMaxStreams][64 * kProjMaxK];      // the group's input rows (coalesced staging)
+    const int ub = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c4 = lane & 3, rq = threadIdx.x >> 2;
+    const int n_x = p.n_feat + p.n_det, n_rows = n_x + p.units;
+    const float4 *w = reinterpret_cast<const float4 *>(p.wp + (long long)ub * n_rows * 16) + c4;
+    float4 wv[kProjMaxK];
+#pragma unroll
+    for (int j = 0; j < kProjMaxK; ++j) {
+        const int k = rq + 64 * j;
+        wv[j] = k < n_x ? __ldg(w + (long long)k * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int s0 = 0; s0 < p.S; s0 += kMaxStreams) {
+        const int nS = min(kMaxStreams, p.S - s0);
+        if (((p.n_feat | p.fv_stride) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.fv) & 15) == 0) {
+            // one float4 per thread and row, the group's loads all in flight before the first store
+            for (int k = threadIdx.x * 4; k < p.n_feat; k += kLstmThreads * 4) {
+                float4 v[kMaxStreams];
+#pragma unroll
+                for (int s = 0; s < kMaxStreams; ++s)
+                    if (s < nS) v[s] = __ldg(reinterpret_cast<const float4 *>(p.fv + (long long)(s0 + s) * p.fv_stride + k));
+#pragma unroll
+                for (int s = 0; s < kMaxStreams; ++s)
+                    if (s < nS) *reinterpret_cast<float4 *>(&xs[s][k]) = v[s];
+            }
+        } else {
+            for (int i = threadIdx.x; i < nS * p.n_feat; i += kLstmThreads) {
+                const int s = i / p.n_feat, k = i - s * p.n_feat;
+                xs[s][k] = __ldg(p.fv + (long long)(s0 + s) * p.fv_stride + k);
+            }
+        }
+        for (int i = threadIdx.x; i < nS * p.n_det; i += kLstmThreads) {
+            const int s = i / p.n_det, k = i - s * p.n_det;
+            xs[s][p.n_feat + k] = __ldg(p.det + (long long)(s0 + s) * p.det_stride + k);
+        }
+        __syncthreads();
+        float acc[kMaxStreams][4];
+#pragma unroll
+        for (int s = 0; s < kMaxStreams; ++s)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[s][j] = 0.f;
+#pragma unroll
+        for (int j = 0; j < kProjMaxK; ++j) {
+            const int k = rq + 64 * j;
+            if (k < n_x) {
+#pragma unroll
+                for (int s = 0; s < kMaxStreams; ++s)
+                    if (s < nS) {
+                        const float xv = xs[s][k];
+                        acc[s][0] = fmaf(xv, wv[j].x, acc[s][0]);
+                        acc[s][1] = fmaf(xv, wv[j].y, acc[s][1]);
+                        acc[s][2] = fmaf(xv, wv[j].z, acc[s][2]);
+                        acc[s][3] = fmaf(xv, wv[j].w, acc[s][3]);
+                    }
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < kMaxStreams; ++s)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float v = acc[s][j];
+                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                v += __shfl_xor_sync(0xffffffffu, v, 8);
+                v += __shfl_xor_sync(0xffffffffu, v, 16);
+                if (lane < 4) red[warp][c4 * 4 + j][s] = v;
+            }
+        __syncthreads();
+        if (threadIdx.x < kUnitsPerBlock * nS) {
+            const int uu = threadIdx.x % kUnitsPerBlock, s = s0 + threadIdx.x / kUnitsPerBlock;
+            const int unit = ub * kUnitsPerBlock + uu;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                float t = 0.f;
+                for (int r = 0; r < 8; ++r) t += red[r][g * 4 + uu][s - s0];
+                p.zx[(long long)s * p.zx_stride + g * p.units + unit] = t + p.bias[g * p.units + unit];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------- fused recurrent steps
+// T sequential steps h_t = LSTM(zx_t + h_{t-1} U) for S streams in ONE launch: units/4 CTAs (all co-resident: one per
+// SM), each keeps its U slab in registers for the whole sequence; between steps the CTAs meet at a counter barrier in
+// global memory (h_{t-1} is read with ld.cg after it).  Same summation order as lstm_gates_kernel mode 2.
+constexpr int kSeqMaxStreams = 16;
+constexpr int kSeqMaxK = 8;              // units <= 512
+__global__ void __launch_bounds__(kLstmThreads) lstm_seq_kernel(const LstmParams p, int T, float *h_a, float *h_b,
+                                                                unsigned int *counter) {
+    __shared__ float red[8][16][kSeqMaxStreams];
+    __shared__ __align__(16) float hs[kSeqMaxStreams][64 * kSeqMaxK];     // h_{t-1} of every stream
+    const int ub = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c4 = lane & 3, rq = threadIdx.x >> 2;
+    const int n_x = p.n_feat + p.n_det, n_rows = n_x + p.units;
+    const float4 *w = reinterpret_cast<const float4 *>(p.wp + ((long long)ub * n_rows + n_x) * 16) + c4;
+    float4 wv[kSeqMaxK];
+#pragma unroll
+    for (int j = 0; j < kSeqMaxK; ++j) {
+        const int k = rq + 64 * j;
+        wv[j] = k < p.units ? __ldg(w + (long long)k * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int t = 0; t < T; ++t) {
+        const float *h_in = (t & 1) ? h_b : h_a;
+        float *h_out = (t & 1) ? h_a : h_b;
+        {   // coalesced float4 loads from L2 (other CTAs wrote h), all in flight before the first store
+            const int n4 = p.S * p.units / 4;                              // units is a multiple of 4
+            float4 v[kSeqMaxStreams * 64 * kSeqMaxK / 4 / kLstmThreads];
+#pragma unroll
+            for (int r = 0; r < kSeqMaxStreams * 64 * kSeqMaxK / 4 / kLstmThreads; ++r) {
+                const int i4 = threadIdx.x + r * kLstmThreads;
+                if (i4 < n4) v[r] = __ldcg(reinterpret_cast<const float4 *>(h_in) + i4);
+            }
+#pragma unroll
+            for (int r = 0; r < kSeqMaxStreams * 64 * kSeqMaxK / 4 / kLstmThreads; ++r) {
+                const int i4 = threadIdx.x + r * kLstmThreads;
+                if (i4 < n4) {
+                    const int i = i4 * 4, sidx = i / p.units, k = i - sidx * p.units;
+                    *reinterpret_cast<float4 *>(&hs[sidx][k]) = v[r];
+                }
+            }
+        }
+        __syncthreads();
+        float acc[kSeqMaxStreams][4];
+#pragma unroll
+        for (int s = 0; s < kSeqMaxStreams; ++s)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[s][j] = 0.f;
+#pragma unroll
+        for (int j = 0; j < kSeqMaxK; ++j) {
+            const int k = rq + 64 * j;
+            if (k < p.units) {
+#pragma unroll
+                for (int s = 0; s < kSeqMaxStreams; ++s)
+                    if (s < p.S) {
+                        const float hv = hs[s][k];
+                        acc[s][0] = fmaf(hv, wv[j].x, acc[s][0]);
+                        acc[s][1] = fmaf(hv, wv[j].y, acc[s][1]);
+                        acc[s][2] = fmaf(hv, wv[j].z, acc[s][2]);
+                        acc[s][3] = fmaf(hv, wv[j].w, acc[s][3]);
+                    }
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < kSeqMaxStreams; ++s)
+            if (s < p.S) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float v = acc[s][j];
+                    v += __shfl_xor_sync(0xffffffffu, v, 4);
+                    v += __shfl_xor_sync(0xffffffffu, v, 8);
+                    v += __shfl_xor_sync(0xffffffffu, v, 16);
+                    if (lane < 4) red[warp][c4 * 4 + j][s] = v;
+                }
+            }
+        __syncthreads();
+        if (threadIdx.x < kUnitsPerBlock * p.S) {
+            const int uu = threadIdx.x % kUnitsPerBlock, s = threadIdx.x / kUnitsPerBlock;
+            const int unit = ub * kUnitsPerBlock + uu;
+            float z[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                float tt = 0.f;
+                for (int r = 0; r < 8; ++r) tt += red[r][g * 4 + uu][s];
+                z[g] = tt + p.zx[((long long)s * T + t) * 4 * p.units + g * p.units + unit];
+            }
+            const float i = p.hard_sigmoid ? hard_sigmoid_f(z[0]) : sigmoid_f(z[0]);
+            const float f = p.hard_sigmoid ? hard_sigmoid_f(z[1]) : sigmoid_f(z[1]);
+            const float o = p.hard_sigmoid ? hard_sigmoid_f(z[3]) : sigmoid_f(z[3]);
+            const float cn = fmaf(f, p.c[(long long)s * p.units + unit], i * tanhf(z[2]));
+            const float hn = o * tanhf(cn);
+            p.c[(long long)s * p.units + unit] = cn;
+            h_out[(long long)s * p.units + unit] = hn;
+            if (p.h_seq) p.h_seq[((long long)s * T + t) * p.units + unit] = hn;
+        }
+        if (t + 1 < T) {                     // every CTA has published h_t before anyone reads it
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence();
+                atomicAdd(counter, 1u);
+                const unsigned int target = gridDim.x * (unsigned)(t + 1);
+                unsigned int seen;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+                } while (seen < target);
+            }
+            __syncthreads();
+        }
+    }
+}
+
 // y[s][j] = sigmoid(sum_k h[s][k] * Wd[k][j] + bd[j]); one warp per output, lanes over k
 __global__ void dense_sigmoid_kernel(const float *h, const float *wd, const float *bd, int units, int n_out, int S,
                                      float *y, int y_stride) {
@@ -282,6 +481,18 @@ __global__ void convlstm_gates_kernel(const ConvLstmGateParams p) {
 int launch_lstm_gates(const LstmParams &p, cudaStream_t st) {
     dim3 grid(p.units / kUnitsPerBlock, (p.S + kMaxStreams - 1) / kMaxStreams);
     lstm_gates_kernel<<<grid, kLstmThreads, 0, st>>>(p);
+    return (int)cudaGetLastError();
+}
+int launch_lstm_proj(const LstmParams &p, cudaStream_t st) {
+    if (p.n_feat + p.n_det > 64 * kProjMaxK) return -1;          // caller falls back to lstm_gates_kernel mode 1
+    lstm_proj_kernel<<<p.units / kUnitsPerBlock, kLstmThreads, 0, st>>>(p);
+    return (int)cudaGetLastError();
+}
+int launch_lstm_seq(const LstmParams &p, int T, float *h_a, float *h_b, unsigned int *counter, int n_sm, cudaStream_t st) {
+    if (p.S > kSeqMaxStreams || p.units > 64 * kSeqMaxK || p.units / kUnitsPerBlock > n_sm) return -1;   // fall back
+    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), st);
+    if (e != cudaSuccess) return (int)e;
+    lstm_seq_kernel<<<p.units / kUnitsPerBlock, kLstmThreads, 0, st>>>(p, T, h_a, h_b, counter);
     return (int)cudaGetLastError();
 }
 int launch_dense_sigmoid(const float *h, const float *wd, const float *bd, int units, int n_out, int S, float *y,
