@@ -159,6 +159,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    griddep_launch();            // the next kernel of the stream may start its own prologue on SMs we have left
 
     if (warp == 0) {
         // ===================== TMA producer (whole warp runs the uniform loops, one elected lane issues) =====
@@ -191,6 +192,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_consta
                     while (w_seq < pf) issue_next_w();
                 }
                 mbar_wait(stage_free, (k - 1) & 1);          // the previous item's staged tile has left the patch buffers
+            } else {
+                // first item: the weights do not depend on the previous layer -- request them, then wait for the
+                // previous kernel of the stream (programmatic dependent launch) before touching its output
+                const int pf = min(kWStages, n_chunks * taps);
+                while (w_seq < pf) issue_next_w();
+                griddep_wait();
             }
             int seq = 0;
             for (int it = 0; it < n_chunks; ++it, ++g_it) {
@@ -342,6 +349,7 @@ conv_halo_persist_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    griddep_launch();
 
     auto decode_item = [&](int item, int &b, int &y0, int &x0, int &cout0) {
         const int ct = item % n_ct;  item /= n_ct;
@@ -368,6 +376,7 @@ conv_halo_persist_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
             for (int ci = 0; ci < p.cin_chunks; ++ci)
                 for (int tap = 0; tap < taps; ++tap) load_w(ci * taps + tap, ci, tap, 0);
         __syncwarp();
+        griddep_wait();          // the activations come from the previous kernel of the stream (weights do not)
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             int b, y0, x0, cout0;
             decode_item(item, b, y0, x0, cout0);
@@ -487,8 +496,7 @@ int launch_conv_halo_persist(int n_sm, const CUtensorMap &x_hi, const CUtensorMa
                              const CUtensorMap &w_lo, const ConvParams &p, cudaStream_t st) {
     const int items = p.B * p.h_tiles_x * p.h_tiles_y * ((p.Cout + 127) / 128);
     const int smem = 1024 /*align*/ + 1024 /*barriers*/ + 2 * p.pw_patch_bytes + p.pw_stage_bytes + p.pw_stages * p.pw_tile_bytes;
-    conv_halo_persist_kernel<<<items < n_sm ? items : n_sm, kHaloThreads, smem, st>>>(x_hi, x_lo, w_hi, w_lo, p);
-    return (int)cudaGetLastError();
+    return (int)launch_pdl(conv_halo_persist_kernel, dim3(items < n_sm ? items : n_sm), dim3(kHaloThreads), smem, st, x_hi, x_lo, w_hi, w_lo, p);
 }
 
 int launch_conv_halo(int n_sm, bool small, const CUtensorMap &x_hi, const CUtensorMap &x_lo, const CUtensorMap &w_hi,
@@ -497,10 +505,8 @@ int launch_conv_halo(int n_sm, bool small, const CUtensorMap &x_hi, const CUtens
     const int cap = n_sm * (small ? 2 : 1);
     const int grid = items < cap ? items : cap;
     if (small)
-        conv_halo_kernel<true><<<grid, kHaloThreads, HaloCfg<true>::kSmemBytes, st>>>(x_hi, x_lo, w_hi, w_lo, p);
-    else
-        conv_halo_kernel<false><<<grid, kHaloThreads, HaloCfg<false>::kSmemBytes, st>>>(x_hi, x_lo, w_hi, w_lo, p);
-    return (int)cudaGetLastError();
+        return (int)launch_pdl(conv_halo_kernel<true>, dim3(grid), dim3(kHaloThreads), HaloCfg<true>::kSmemBytes, st, x_hi, x_lo, w_hi, w_lo, p);
+    return (int)launch_pdl(conv_halo_kernel<false>, dim3(grid), dim3(kHaloThreads), HaloCfg<false>::kSmemBytes, st, x_hi, x_lo, w_hi, w_lo, p);
 }
 
 }  // namespace b2t

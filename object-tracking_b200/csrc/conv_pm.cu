@@ -91,6 +91,7 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    griddep_launch();
 
     // item -> (image, tile row, tile column) with host-made magic multipliers (exact for item < 2^32 / divisor)
     auto decode_item = [&](int item, int &b, int &y0, int &x0) {
@@ -116,6 +117,7 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant
                 }
         }
         __syncwarp();
+        griddep_wait();          // the activations / the frame copy come from the previous kernel of the stream
         int g_chunk = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             int b, y0, x0;
@@ -305,8 +307,7 @@ int launch_conv_pm(int n_sm, const CUtensorMap &x_hi, const CUtensorMap &x_lo, c
     // per-tile barrier and store latencies
     const int per_sm = (2 * (smem + 1024) <= 227 * 1024 && 2 * p.pm_tmem_cols <= 512) ? 2 : 1;
     const int grid = items < n_sm * per_sm ? items : n_sm * per_sm;
-    conv_pm_kernel<<<grid, kPmThreads, smem, st>>>(x_hi, x_lo, w_hi, w_lo, p);
-    return (int)cudaGetLastError();
+    return (int)launch_pdl(conv_pm_kernel, dim3(grid), dim3(kPmThreads), smem, st, x_hi, x_lo, w_hi, w_lo, p);
 }
 
 int launch_frames_to_c8(const void *frames, void *dst, long long npix, cudaStream_t st) {

@@ -219,6 +219,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 // optional 2x2 max-pool, hi/lo split, same destinations as the fused epilogue.  One thread = 8 channels
 // of one pixel (or of one 2x2 quad when pooling).
 __global__ void __launch_bounds__(256) splitk_epilogue_kernel(const ConvParams p) {
+    griddep_launch();
+    griddep_wait();              // the partials come from the previous kernel of the stream
     const int cgroups = (p.Cout + 7) / 8;
     const int Hq = p.pool ? p.H / 2 : p.H, Wq = p.pool ? p.W / 2 : p.W;
     const long long total = (long long)p.B * Hq * Wq * cgroups;
@@ -474,8 +476,7 @@ int launch_splitk_epilogue(const ConvParams &p, cudaStream_t st) {
     const int cgroups = (p.Cout + 7) / 8;
     const long long total = (long long)p.B * (p.pool ? p.H / 2 : p.H) * (p.pool ? p.W / 2 : p.W) * cgroups;
     const int blocks = (int)min((long long)148 * 16, (total + 255) / 256);
-    splitk_epilogue_kernel<<<blocks, 256, 0, st>>>(p);
-    return (int)cudaGetLastError();
+    return (int)launch_pdl(splitk_epilogue_kernel, dim3(blocks), dim3(256), 0, st, p);
 }
 int launch_conv_simt(const SimtView &v, const ConvParams &p, cudaStream_t st) {
     const long long mtot = (long long)p.B * p.H * p.W;

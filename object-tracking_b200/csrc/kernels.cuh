@@ -2,6 +2,7 @@
 // translation units and api.cu).
 #pragma once
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "conv_types.cuh"
 
@@ -79,6 +80,20 @@ struct ConvLstmGateParams {
     int t;                // time-step slot (batch index in h_seq)
     int hard_sigmoid;
 };
+
+// Launch with programmatic stream serialization (the kernel MUST call griddep_wait() before touching anything its
+// predecessor wrote).  B2T_PDL=0 falls back to a plain launch.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+    static const bool pdl = !(getenv("B2T_PDL") && atoi(getenv("B2T_PDL")) == 0);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 int launch_conv_umma(int BN, const CUtensorMap &a_hi, const CUtensorMap &a_lo, const CUtensorMap &b_hi,
                      const CUtensorMap &b_lo, const ConvParams &p, cudaStream_t st);

@@ -414,3 +414,51 @@ def test_keras_yolo_and_multiobj_plugins(tmp_path):
     x = np.stack([cv2.resize(cv2.imread(p), (416, 416)) for p in paths])
     trk2, det2 = mt.track_window(x)
     assert [len(b) for b in trk2] == [len(b) for b in trk]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("S", [9, 12, 17])
+def test_lstm_fused_sequence_many_streams(S):
+    """b2t_lstm_sequence (batched projection + fused recurrent steps with a grid barrier for S <= 16, per-step launches
+    above) against the one-step entry point, and against the numpy restatement of the Keras LSTM."""
+    from object_tracking_b200.engine import DetectorEngine, LstmHead
+    eng = DetectorEngine(n_class=2, max_batch=1)
+    w = W.synthetic_lstm_weights(1028, 512, 4, seed=3)
+    rng = np.random.default_rng(S)
+    T = 4
+    fv = rng.standard_normal((S, T, 1024)).astype(np.float32)
+    det = rng.uniform(0, 1, (S, T, 4)).astype(np.float32)
+    head = LstmHead(eng, 1024, 4, 512, 4, max_streams=S)
+    head.set_weights(w)
+    y = head.sequence(torch.from_numpy(fv).cuda(), torch.from_numpy(det).cuda(), reset=True).cpu().numpy()
+    head.reset()
+    fvd, detd = torch.from_numpy(fv).cuda(), torch.from_numpy(det).cuda()
+    for t in range(T):
+        yt = head.step(fvd[:, t], detd[:, t]).cpu().numpy()
+        assert np.abs(yt - y[:, t]).max() < 1e-6, t
+    w64 = {k: v.astype(np.float64) for k, v in w.items()}
+    h = np.zeros((S, 512)); c = np.zeros((S, 512))
+    for t in range(T):
+        ref, h, c = tracker_oracle.tracker_step(fv[:, t].astype(np.float64), det[:, t].astype(np.float64), h, c, w64)
+        assert np.abs(y[:, t] - ref).max() < 2e-5, t
+
+
+@pytest.mark.gpu
+def test_odd_batch_uint8_conv1_tensor_core_path(keras_c2):
+    """conv_1 / conv_2 / conv_4 run pixel-major on the tensor cores for uint8 frames (conv_pm_kernel): an odd batch
+    (tiles of the last image end mid-grid) against the fp64 oracle, layer by layer."""
+    z, w, frames, e = keras_c2
+    from object_tracking_b200.engine import DetectorEngine
+    rng = np.random.default_rng(77)
+    fr = rng.integers(0, 256, (3, 416, 416, 3), dtype=np.uint8)
+    eng = DetectorEngine(n_class=2, max_batch=3, keep_prepool=True)
+    eng.set_weights(w)
+    eng.finalize()
+    names = ["norm_1", "norm_2", "norm_3", "norm_4", "norm_5"]
+    o = yolo_oracle.yolo_forward(yolo_oracle.normalize(fr), w, 2, dtype=np.float64, want=names)
+    got = eng.forward(torch.from_numpy(fr).cuda()).cpu().numpy()
+    for n in names:
+        a = eng.extract(n, 3).cpu().numpy()
+        rel = np.abs(a - o[n]).max() / np.abs(o[n]).max()
+        assert rel < 5e-6, (n, rel)
+    assert np.abs(got - o["logits"]).max() < 5e-4
