@@ -200,7 +200,8 @@ static int choose_splits_halo(int ctas, int cin_chunks, int taps, int n_sm) {
         if ((cin_chunks + per - 1) / per != s) continue;
         if (env && atoi(env) > 0 && s != atoi(env) && s != max_s) continue;
         // the tensor core truncates addends to the accumulator's exponent: keep one accumulation chain short
-        if (per * taps * 4 > 320 && s < max_s) continue;
+        static const int chain_cap = getenv("B2T_CHAIN") ? atoi(getenv("B2T_CHAIN")) : 320;
+        if (per * taps * 4 > chain_cap && s < max_s) continue;
         const long waves = ((long)ctas * s + n_sm - 1) / n_sm;
         const double cost = (double)waves * (per * taps + 10.0) + (s > 1 ? 3.0 * s : 0.0);
         if (cost < best_cost - 1e-9) { best_cost = cost; best_s = s; }
