@@ -242,7 +242,14 @@ static ConvLayer &new_conv(b2t_ctx *c, int index, int k, int cin, int cout, bool
     l.BN = cout >= 128 ? 128 : 64;
     choose_tile(H, W, pool, l.TW, l.TH);
     choose_halo_tile(H, W, k, pool, l);
-    if (cout <= 64 && c->cfg.engine == B2T_ENGINE_TCGEN05) choose_pm_tile(H, W, k, pool, index == 1 ? 16 : l.kchunk * 2, index == 1, l);
+    if (cout <= 64 && c->cfg.engine == B2T_ENGINE_TCGEN05 && index != 1) choose_pm_tile(H, W, k, pool, l.kchunk * 2, false, l);
+    if (index == 1 && c->cfg.engine == B2T_ENGINE_TCGEN05) {
+        // conv_1 (conv_pm.cu mode 1): an item is two image rows x pmC columns (columns on the MMA's M), patch = 4 rows
+        const int nt = (W + 125) / 126;
+        l.pmC = ((W + nt - 1) / nt + 1) & ~1;
+        l.pmP = l.pmC + 2; l.pmR = 2; l.pm_rows = 4;
+        l.pm_plane_bytes = (int)align_up((size_t)(3 * l.pmP + 128 + 8) * 16, 1024);   // last operand row: pixels 3P+127 .. +3
+    }
     if ((int)c->conv.size() <= index) c->conv.resize(index + 1);
     c->conv[index] = l;
     return c->conv[index];
@@ -506,14 +513,16 @@ extern "C" int b2t_set_conv_weights(b2t_ctx *c, int idx, const float *ker, const
                 if (shift > 40) shift = 40;
                 if (shift < -8) shift = -8;
             }
-            const float up = ldexpf(1.f, shift);
+            // channels with a negative folded-BN scale get negated weights and |scale|: BN + LeakyReLU are then
+            // increasing in the raw sum for every channel, which lets the kernel max-pool before applying them
+            const float up = s1[co] < 0.f ? -ldexpf(1.f, shift) : ldexpf(1.f, shift);
             for (int kh = 0; kh < 3; ++kh)
                 for (int kw = 0; kw < 3; ++kw)
                     for (int ci = 0; ci < 3; ++ci) {
                         const size_t d = (size_t)kh * 2048 + (size_t)((co / 8) * 4 + kw) * 64 + (co % 8) * 8 + ci;   // fp16 elements
                         split_f16(ker[((kh * 3 + kw) * 3 + ci) * 32 + co] * up, wp[d], wp[d + 1024]);
                     }
-            s1pm[co] = (float)((double)s1[co] * (double)ldexpf(1.f, -shift) / 255.0);
+            s1pm[co] = (float)(fabs((double)s1[co]) * (double)ldexpf(1.f, -shift) / 255.0);
         }
     } else {
         std::vector<float> un;

@@ -17,6 +17,9 @@
 //   (row m at 16*m bytes: SBO = 128 B, K group j at +16*j bytes: LBO = 16 B) the operand row of pixel m covers the
 //   pixels m .. m+3 of the patch: the kw taps of the 3x3 window are folded into K by the descriptor itself (an
 //   im2col that costs nothing), one K = 32 step per kernel row kh.  1/255 is folded into the epilogue scale.
+//   An item is a PAIR of image rows x up to 126 columns (M = columns): two accumulator pairs, one per row, so the
+//   2x2 max-pool happens in registers (rows in-thread, columns by one shuffle), BN + LeakyReLU are applied after the
+//   pool (monotonic per channel) and every thread writes 32 contiguous bytes per plane -- no shared-memory staging.
 // * TMEM holds two accumulator sets (main + correction, N columns each) so the 8-warp epilogue of tile j overlaps
 //   the MMAs of tile j+1; the epilogue thread owns one pixel (TMEM lane) and half of the channels, stages
 //   [pixel][channel] in shared memory and shares the coalesced store phase (2x2 max-pool, hi/lo split) with
@@ -165,18 +168,25 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant
                 const uint32_t a_hi = (128u >> 4) | (1u << 14), b_hi = (512u >> 4) | (1u << 14);
                 const uint32_t xa = p16_0 + hb * pb16;                       // LBO field = 1 (16 B) from umma_desc_lo
                 const uint32_t wb = w16 | ((128u >> 4) << 16);
+                // the item is a pair of image rows (one pooled row): output row r uses patch rows r + kh and
+                // accumulates into columns [r*N, r*N + N) of the item's TMEM buffer.  u*w_hi and u*w_lo share the
+                // accumulator here: the chain is 12 MMAs short, so the w_lo terms (2^-11 of the sum) keep 13 bits
+                const uint32_t t_buf = tmem_base + ab * 2 * N;
                 if (elect_one()) {
 #pragma unroll
-                    for (int kh = 0; kh < 3; ++kh) {
+                    for (int r = 0; r < 2; ++r) {
 #pragma unroll
-                        for (int ks = 0; ks < 2; ++ks) {
-                            const uint64_t da = umma_desc_make(xa + kh * p.hP + 2 * ks, a_hi);
-                            const uint64_t dwh = umma_desc_make(wb + kh * (4096 >> 4) + ks * (256 >> 4), b_hi);
-                            const uint64_t dwl = umma_desc_make(wb + kh * (4096 >> 4) + (2048 >> 4) + ks * (256 >> 4), b_hi);
-                            const uint32_t acc = (kh | ks) ? 1u : 0u;
-                            if (p.dbg & 8) continue;
-                            umma_f16(t_corr, da, dwl, idesc, acc);
-                            umma_f16(t_main, da, dwh, idesc, acc);
+                        for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+                            for (int ks = 0; ks < 2; ++ks) {
+                                const uint64_t da = umma_desc_make(xa + (r + kh) * p.hP + 2 * ks, a_hi);
+                                const uint64_t dwh = umma_desc_make(wb + kh * (4096 >> 4) + ks * (256 >> 4), b_hi);
+                                const uint64_t dwl = umma_desc_make(wb + kh * (4096 >> 4) + (2048 >> 4) + ks * (256 >> 4), b_hi);
+                                const uint32_t acc = (kh | ks) ? 1u : 0u;
+                                if (p.dbg & 8) continue;
+                                umma_f16(t_buf + r * N, da, dwh, idesc, acc);
+                                umma_f16(t_buf + r * N, da, dwl, idesc, 1u);
+                            }
                         }
                     }
                     umma_commit(&patch_empty[hb]);
@@ -240,6 +250,72 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant
             mbar_wait(&acc_full[grp], k & 1);
             tc_fence_after();
             if (tr) p.trace[jj * 16 + 6] = clock64();
+            if (ints) {
+                // conv_1: the item is one pooled row.  TMEM lane = image column c; the item's buffer holds
+                // [row 0 main | row 0 corr | row 1 main | row 1 corr] x 32 channels.  The 2x2 max-pool runs in
+                // registers: vertical = the two rows of the same lane, horizontal = lane pairs (shuffle).  The host
+                // negates the weights of channels whose folded-BN scale is negative and passes |scale|, so BN +
+                // LeakyReLU are increasing in the raw sum for every channel and can be applied AFTER the pool to
+                // max(raw) -- bit-identical to pooling the activated values.
+                // Even lanes then finish channels 0..15, odd lanes 16..31, and write 32 contiguous bytes per plane.
+                const uint32_t t_buf = tmem_base + grp * 2 * N + (uint32_t(q * 32) << 16);
+                const int c = n, xq = (x0 + c) >> 1;
+                const bool valid = c < p.hC && x0 + c < p.W;
+                const int half_mine = lane & 1;
+                float keep[16];
+#pragma unroll
+                for (int g8 = 0; g8 < 4; ++g8) {                 // 8 channels at a time keeps the live set small
+                    uint32_t ua[8], ub[8];
+                    tmem_ld8(t_buf + 8 * g8, ua);
+                    tmem_ld8(t_buf + N + 8 * g8, ub);
+                    tmem_ld_wait();
+                    if (p.out.hi && valid) {              // full-resolution copy requested (keep_prepool): both rows
+                        float v8[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { const float tv = fmaf(__uint_as_float(ua[i]), s_scale[8 * g8 + i], s_bias[8 * g8 + i]); v8[i] = fmaxf(tv, 0.1f * tv); }
+                        emit8(p.out, b, y0, x0 + c, 8 * g8, p.Cout, v8);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { const float tv = fmaf(__uint_as_float(ub[i]), s_scale[8 * g8 + i], s_bias[8 * g8 + i]); v8[i] = fmaxf(tv, 0.1f * tv); }
+                        emit8(p.out, b, y0 + 1, x0 + c, 8 * g8, p.Cout, v8);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float mx = fmaxf(__uint_as_float(ua[i]), __uint_as_float(ub[i]));
+                        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                        if ((g8 >> 1) == half_mine) keep[8 * (g8 & 1) + i] = mx;
+                    }
+                }
+                tc_fence_before();
+                if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+                if (et == 0) mbar_arrive(&acc_empty[grp]);             // TMEM buffer drained by all four warps
+                if (tr) p.trace[jj * 16 + 7] = clock64();
+                if (valid && !(p.dbg & 4)) {
+                    const int ch0 = 16 * half_mine;
+                    uint32_t hw[8], lw[8];                       // 16 channels as packed fp16 pairs (hi plane, lo plane)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float t2[2];
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const float tv = fmaf(keep[2 * i + e], s_scale[ch0 + 2 * i + e], s_bias[ch0 + 2 * i + e]);
+                            t2[e] = fminf(fmaxf(fmaxf(tv, 0.1f * tv), -65504.f), 65504.f);
+                        }
+                        const __half2 h2 = __floats2half2_rn(t2[0], t2[1]);
+                        const float2 hf = __half22float2(h2);
+                        const __half2 l2 = __floats2half2_rn(t2[0] - hf.x, t2[1] - hf.y);
+                        hw[i] = *reinterpret_cast<const uint32_t *>(&h2);
+                        lw[i] = *reinterpret_cast<const uint32_t *>(&l2);
+                    }
+                    op_t *dst = p.pout.hi + (((long long)b * (p.H >> 1) + (y0 >> 1)) * (p.W >> 1) + xq) * p.pout.pix_stride_b +
+                                p.pout.ch_off_b + ch0;
+                    reinterpret_cast<uint4 *>(dst)[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                    reinterpret_cast<uint4 *>(dst)[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+                    reinterpret_cast<uint4 *>(dst + p.pout.plane_stride)[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                    reinterpret_cast<uint4 *>(dst + p.pout.plane_stride)[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+                }
+                if (tr) p.trace[jj * 16 + 8] = clock64();
+                continue;
+            }
             for (int c0 = 0; c0 < N; c0 += 32) {               // N is a multiple of 32 here (32 or 64)
                 uint32_t a[32], c2[32];
                 tmem_ld32(t_main + c0, a);
