@@ -157,6 +157,16 @@ def reference_runner():
     return run, "port", "oracle port: torch-CPU fp32 forward + numpy region decode/NMS + numpy LSTM step"
 
 
+def workload_config(S: int, world: int) -> dict:
+    """`config` of the JSON line -- the same object for the B200 arm and the reference arm."""
+    return {"workload": "TinyTracker YOLOv2-416 C=80 (darknet semantics) + LSTM(512), 1 stream/window "
+                        "per GPU x %d, synthetic 300-frame clip" % S,
+            "frames_per_step": S * SEQ, "window": SEQ, "windows_per_step": S,
+            "l2": "inputs cycle through a 156 MB clip per stream and the 204 MB weight blob is streamed "
+                  "every step (both > 126 MB L2); no explicit flush",
+            "weights": "random-init (reference ships none), seed 0", "parallelism": f"streams x{world}"}
+
+
 def time_reference(steps: int, warmup: int):
     run, kind, what = reference_runner()
     rng = np.random.default_rng(1234)
@@ -179,8 +189,9 @@ def main_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "TinyTracker YOLOv2-416 C=80 + LSTM(512), 1 stream, synthetic clip",
-                       "step": "1 frame (bounded sample of the 4-frame window)"},
+            "config": dict(workload_config(args.windows, max(1, args.gpus)),
+                           reference_step="1 frame per step: a bounded sample of the %d-frame step, same frames/s metric"
+                                          % (args.windows * SEQ)),
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": kind,
                              "sample": f"{args.steps} single frames after {args.warmup} warm-up; {what}"},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -308,12 +319,7 @@ def main_b200(args):
         line = {"metric": METRIC, "value": total_frames / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f16x2-split operands, f32 accumulate", "data": "synthetic",
-                "config": {"workload": "TinyTracker YOLOv2-416 C=80 (darknet semantics) + LSTM(512), 1 stream/window "
-                                       "per GPU x %d, synthetic 300-frame clip" % S,
-                           "frames_per_step": frames_per_step, "window": T, "windows_per_step": S,
-                           "l2": "inputs cycle through a 156 MB clip per stream and the 204 MB weight blob is streamed "
-                                 "every step (both > 126 MB L2); no explicit flush",
-                           "weights": "random-init (reference ships none), seed 0", "parallelism": f"streams x{world}"},
+                "config": workload_config(S, world),
                 "e2e": {"value": total_frames / (e2e_ms * 1e-3), "unit": UNIT,
                         "h2d_bytes_per_step": frames_per_step * IMAGE * IMAGE * 3,
                         "d2h_bytes_per_step": frames_per_step * 4 * 4},

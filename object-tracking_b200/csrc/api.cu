@@ -77,6 +77,8 @@ struct ConvLayer {
     bool pm = false, pm_flat = false;             // flat: 1x1 conv over the pixel list of the whole batch
     int pmC = 0, pmP = 0, pmR = 0, pm_rows = 0, pm_plane_bytes = 0;
     CUtensorMap tmXp_hi, tmXp_lo;
+    bool flat1x1 = false;                         // 1x1 conv, plain destination, no pool: persistent kernel over the flat pixel list
+    CUtensorMap tmXf_hi, tmXf_lo;                 // its patch view: [cin_pad][MB*H*W] with a box of 128 pixels
     bool have_weights = false;
 };
 
@@ -682,6 +684,21 @@ extern "C" int b2t_finalize(b2t_ctx *c, int upload, void *stream) {
         cuuint32_t wbox3[2] = {(cuuint32_t)l.kchunk, (cuuint32_t)l.w_rows};
         if ((rc = make_tmap(c, &l.tmWp_hi, c->d_blob + l.off_whi, 2, wd, wst, wbox3, sw64))) return rc;
         if ((rc = make_tmap(c, &l.tmWp_lo, c->d_blob + l.off_wlo, 2, wd, wst, wbox3, sw64))) return rc;
+        // 1x1 layers without pooling and with a plain destination: tiles of exactly 128 pixels of the flat pixel list
+        // of the whole batch, persistent kernel (TMEM double buffering: the epilogue overlaps the next tile's MMAs)
+        static const int flat_mode = getenv("B2T_FLAT") ? atoi(getenv("B2T_FLAT")) : 1;
+        // (measured: a win up to K = 512; longer K re-streams too many weight bytes per 128-pixel tile -- the
+        // shared-memory port saturates -- and the N = 192 whole-image tiles of conv_halo_kernel stay faster)
+        l.flat1x1 = flat_mode && l.k == 1 && !l.pool && l.out_mode == DEST_PLAIN && l.kchunk == 64 && nb == MB &&
+                    l.cin_pad <= 512 && c->cfg.engine == B2T_ENGINE_TCGEN05;
+        if (l.flat1x1) {
+            const cuuint64_t npx = (cuuint64_t)MB * l.H * l.W;
+            cuuint64_t fd[4] = {(cuuint64_t)l.cin_pad, npx, 1, 1};
+            cuuint64_t fs[3] = {(cuuint64_t)in.C * 2, (cuuint64_t)in.C * 2 * npx, (cuuint64_t)in.C * 2 * npx};
+            cuuint32_t fb[4] = {64, 128, 1, 1};
+            if ((rc = make_tmap(c, &l.tmXf_hi, in.hi + l.in_ch_off, 4, fd, fs, fb))) return rc;
+            if ((rc = make_tmap(c, &l.tmXf_lo, in.hi + in.plane + l.in_ch_off, 4, fd, fs, fb))) return rc;
+        }
         // pixel-major variant: narrow layers whose weights all stay resident in shared memory
         static const int pm_mode = getenv("B2T_PM") ? atoi(getenv("B2T_PM")) : 1;
         l.pm = false;
@@ -802,6 +819,26 @@ static int run_conv(b2t_ctx *c, ConvLayer &l, int B, float *f32_dst, cudaStream_
             return fail(-2, "conv_pm launch (conv %d): %s", l.index, cudaGetErrorString((cudaError_t)rc));
         c->launches += 1;
         return 0;
+    }
+    if (c->cfg.engine == B2T_ENGINE_TCGEN05 && l.flat1x1) {
+        const int npx = B * l.H * l.W;
+        const int items = ((npx + 127) / 128) * ((l.cout + 127) / 128);
+        if (items >= c->n_sm) {                 // enough tiles to fill the machine without a K split
+            p.splits = 1;
+            p.B = 1; p.H = 1; p.W = npx;
+            p.hC = 128; p.hP = 128; p.hR = 1; p.hN = 128; p.h_rows = 1; p.h_plane_bytes = 128 * p.kbytes;
+            p.h_tiles_x = (npx + 127) / 128; p.h_tiles_y = 1;
+            p.pw_patch_bytes = 2 * p.h_plane_bytes;
+            p.pw_stage_bytes = (int)align_up((size_t)128 * 132 * 4, 1024);
+            p.pw_tile_bytes = 2 * l.w_rows * p.kbytes;
+            const int room = 222 * 1024 - 1024 - 1024 - 2 * p.pw_patch_bytes - p.pw_stage_bytes;
+            p.pw_stages = room / p.pw_tile_bytes > 16 ? 16 : room / p.pw_tile_bytes;
+            { static const int dbg = getenv("B2T_DBG") ? atoi(getenv("B2T_DBG")) : 0; p.dbg = dbg; }
+            if ((rc = launch_conv_halo_persist(c->n_sm, l.tmXf_hi, l.tmXf_lo, l.tmWp_hi, l.tmWp_lo, p, st)))
+                return fail(-2, "conv_halo_persist launch (conv %d): %s", l.index, cudaGetErrorString((cudaError_t)rc));
+            c->launches += 1;
+            return 0;
+        }
     }
     if (c->cfg.engine == B2T_ENGINE_TCGEN05) {
         p.hC = l.hC; p.hP = l.hP; p.hR = l.hR; p.hN = l.hN; p.h_rows = l.h_rows; p.h_plane_bytes = l.h_plane_bytes;
