@@ -226,11 +226,11 @@ def main_b200(args):
     # synthetic clip(s): S streams x 300 frames, seeded per global stream id; resident copy + pinned host copy
     n_win = CLIP // T
     from object_tracking_b200.sharding import shard_streams
-    clips = []
-    for gid in shard_streams(world * S, rank, world):          # global stream ids owned by this rank
+    gids = list(shard_streams(world * S, rank, world))         # global stream ids owned by this rank
+    host = torch.empty((len(gids), CLIP, IMAGE, IMAGE, 3), dtype=torch.uint8, pin_memory=True)   # (S, 300, H, W, 3)
+    for s_local, gid in enumerate(gids):                       # filled stream by stream: no second host copy
         rng = np.random.default_rng(1234 + gid)
-        clips.append(rng.integers(0, 256, (CLIP, IMAGE, IMAGE, 3), dtype=np.uint8))
-    host = torch.from_numpy(np.stack(clips)).pin_memory()            # (S, 300, H, W, 3)
+        host[s_local].numpy()[...] = rng.integers(0, 256, (CLIP, IMAGE, IMAGE, 3), dtype=np.uint8)
     dev = host.cuda(non_blocking=True)
     torch.cuda.synchronize()
 

@@ -20,7 +20,10 @@
 // * epilogue: threads own one output channel each (TMEM lane), apply scale/bias (folded BN) + LeakyReLU and stage
 //   the tile [pixel][channel] in the (now dead) operand buffers; then (pixel, 8-channel) items are written with
 //   16-byte stores: optional 2x2 max-pool, hi/lo split, concat / space-to-depth addressing.
-// * split-K over channel chunks (gridDim.z): raw fp32 partials, finished by splitk_epilogue_kernel.
+// * split-K over channel chunks: raw fp32 partials, finished by splitk_epilogue_kernel.
+// * persistent: one CTA per SM walks a static list of (pixel tile, cout tile, K split) items; one elected thread per
+//   role issues (TMA producer warp, MMA warp), all role arithmetic is warp-uniform so that ptxas keeps descriptors in
+//   uniform registers and emits back-to-back UTCHMMA ('The issuing thread').
 #include "kernels.cuh"
 
 namespace b2t {
