@@ -301,8 +301,12 @@ __global__ void __launch_bounds__(kLstmThreads) lstm_seq_kernel(const LstmParams
                 atomicAdd(counter, 1u);
                 const unsigned int target = gridDim.x * (unsigned)(t + 1);
                 unsigned int seen;
+                const long long t_start = clock64();
                 do {
                     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+                    // all CTAs are co-resident by construction (grid <= SM count, launched alone on the stream); if
+                    // that ever fails, fail loudly instead of hanging the device
+                    if (seen < target && clock64() - t_start > (1ll << 31)) __trap();
                 } while (seen < target);
             }
             __syncthreads();
