@@ -127,6 +127,11 @@ int  b2t_lstm_step(b2t_lstm *l, const float *fv_dev, int fv_stride, const float 
  * launch.  reset != 0 zeroes (h,c) first = Keras' stateless windows. T <= 16. */
 int  b2t_lstm_sequence(b2t_lstm *l, const float *fv_dev, const float *det_dev, int n_streams, int n_steps,
                        float *y_dev, int reset, int hard_sigmoid, void *stream);
+/* Frame ingest: cv2.resize(frame, (dst_w, dst_h)) -- KerasYOLO.py:526, MultiObjDetTracker.py:300 -- for a batch of
+ * (src_h, src_w, 3) uint8 frames on the device; bit-identical to OpenCV's INTER_LINEAR for 8-bit images.
+ * Not capturable in a CUDA graph the first time a (src, dst) geometry is seen (coefficient tables are uploaded). */
+int  b2t_resize_frames(b2t_ctx *ctx, const unsigned char *src_dev, int src_h, int src_w, int batch,
+                       unsigned char *dst_dev, int dst_h, int dst_w, void *stream);
 /* pooled feature of the last forward's conv layer `name` for frames [0,batch): Global -> (B,C);
  * Max -> (B,(H/4)*(W/4)*C).  chw_view=1 reproduces preprocessing.py:419 (CHW buffer viewed as HWC). */
 int  b2t_pool_features(b2t_ctx *ctx, const char *name, int batch, int pool_mode, int chw_view,

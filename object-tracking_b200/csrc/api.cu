@@ -108,6 +108,9 @@ struct b2t_ctx {
     long launches = 0;
     int n_sm = 148;
     PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+    // b2t_resize_frames: coefficient tables of the last (src, dst) geometry
+    int rs_geom[4] = {0, 0, 0, 0};
+    int4 *d_rs_tab = nullptr;
 };
 
 static int add_buf(b2t_ctx *c, const std::string &name, int H, int W, int C) {
@@ -422,6 +425,7 @@ extern "C" void b2t_destroy(b2t_ctx *c) {
     if (!c) return;
     if (c->own_blob && c->d_blob) cudaFree(c->d_blob);
     if (c->own_ws && c->d_ws) cudaFree(c->d_ws);
+    if (c->d_rs_tab) cudaFree(c->d_rs_tab);
     delete c;
 }
 
@@ -1272,6 +1276,50 @@ extern "C" int b2t_lstm_sequence(b2t_lstm *l, const float *fv, const float *det,
     if ((rc = launch_dense_sigmoid(l->d_hseq, l->d_wd, l->d_bd, u, l->n_out, R, y, l->n_out, st)))
         return fail(-2, "dense launch: %s", cudaGetErrorString((cudaError_t)rc));
     if (l->ctx) l->ctx->launches += fused ? 3 : T + 2;
+    return 0;
+}
+
+// cv2.resize(frame, (dst_w, dst_h)) for (B, src_h, src_w, 3) uint8 frames on the device, bit-identical to OpenCV's
+// INTER_LINEAR (KerasYOLO.py:526, MultiObjDetTracker.py:300); see csrc/ingest.cu for the algorithm.
+extern "C" int b2t_resize_frames(b2t_ctx *c, const unsigned char *src_dev, int src_h, int src_w, int B,
+                                 unsigned char *dst_dev, int dst_h, int dst_w, void *stream) {
+    if (!c || !src_dev || !dst_dev) return fail(-1, "b2t_resize_frames: null argument");
+    if (src_h < 1 || src_w < 1 || dst_h < 1 || dst_w < 1 || B < 1) return fail(-1, "b2t_resize_frames: bad geometry");
+    if (dst_h > 8192 || dst_w > 8192) return fail(-1, "b2t_resize_frames: destination larger than 8192");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(c->cfg.device));
+    if (!c->d_rs_tab) CK(cudaMalloc(&c->d_rs_tab, 2 * 8192 * sizeof(int4)));
+    if (c->rs_geom[0] != src_h || c->rs_geom[1] != src_w || c->rs_geom[2] != dst_h || c->rs_geom[3] != dst_w) {
+        std::vector<int4> tab(dst_w + dst_h);
+        const double scale_x = 1.0 / ((double)dst_w / src_w), scale_y = 1.0 / ((double)dst_h / src_h);
+        for (int dx = 0; dx < dst_w; ++dx) {
+            float fx = (float)((dx + 0.5) * scale_x - 0.5);
+            int sx = (int)floorf(fx);
+            fx -= sx;
+            if (sx < 0) { fx = 0.f; sx = 0; }
+            if (sx >= src_w - 1) { fx = 0.f; sx = src_w - 1; }
+            const int a0 = (int)lrintf((1.f - fx) * 2048.f), a1 = (int)lrintf(fx * 2048.f);
+            tab[dx] = make_int4(sx, sx + 1 < src_w ? sx + 1 : src_w - 1, a0, a1);
+        }
+        for (int dy = 0; dy < dst_h; ++dy) {
+            float fy = (float)((dy + 0.5) * scale_y - 0.5);
+            const int sy = (int)floorf(fy);
+            fy -= sy;
+            const int b0 = (int)lrintf((1.f - fy) * 2048.f), b1 = (int)lrintf(fy * 2048.f);
+            const int s0 = sy < 0 ? 0 : (sy > src_h - 1 ? src_h - 1 : sy);
+            const int s1 = sy + 1 < 0 ? 0 : (sy + 1 > src_h - 1 ? src_h - 1 : sy + 1);
+            tab[dst_w + dy] = make_int4(s0, s1, b0, b1);
+        }
+        CK(cudaMemcpyAsync(c->d_rs_tab, tab.data(), tab.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));                  // `tab` is a host temporary
+        c->rs_geom[0] = src_h; c->rs_geom[1] = src_w; c->rs_geom[2] = dst_h; c->rs_geom[3] = dst_w;
+    }
+    ResizeParams p;
+    p.src = src_dev; p.dst = dst_dev; p.B = B; p.src_h = src_h; p.src_w = src_w; p.dst_h = dst_h; p.dst_w = dst_w;
+    p.xtab = c->d_rs_tab; p.ytab = c->d_rs_tab + dst_w;
+    const int rc = launch_resize_bilinear_u8(p, st);
+    if (rc) return fail(-2, "resize launch: %s", cudaGetErrorString((cudaError_t)rc));
+    c->launches += 1;
     return 0;
 }
 

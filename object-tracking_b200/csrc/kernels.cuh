@@ -71,6 +71,14 @@ struct SelectParams {
     int *chosen;        // (B) row index or -1
 };
 
+struct ResizeParams {
+    const unsigned char *src;   // (B, src_h, src_w, 3) uint8
+    unsigned char *dst;         // (B, dst_h, dst_w, 3) uint8
+    int B, src_h, src_w, dst_h, dst_w;
+    const int4 *xtab;           // per destination column: source column, next source column, a0, a1 (2048 = 1.0)
+    const int4 *ytab;           // per destination row:    source row,    next source row,    b0, b1
+};
+
 struct ConvLstmGateParams {
     const float *g;       // (M, 4u) pre-activations (input conv + bias + recurrent conv)
     float *c;             // (M, u) cell state, in place
@@ -123,6 +131,7 @@ int launch_pool_features(const PoolParams &p, cudaStream_t st);
 int launch_heatmap_from_box(const float *xywh, int n, int size, float *heat, cudaStream_t st);
 int launch_select_detection(const SelectParams &p, cudaStream_t st);
 int launch_box_from_heatmap(const float *heat, int n, int size, float thresh, int *rect, cudaStream_t st);
+int launch_resize_bilinear_u8(const ResizeParams &p, cudaStream_t st);
 int launch_convlstm_gates(const ConvLstmGateParams &p, cudaStream_t st);
 
 }  // namespace b2t

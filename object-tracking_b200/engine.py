@@ -191,6 +191,19 @@ class DetectorEngine:
                                            dets.data_ptr(), counts.data_ptr(), md, _stream()))
         return dets, counts
 
+    # ---------------------------------------------------------------- frame ingest
+    def resize_frames(self, frames: torch.Tensor, size: Optional[int] = None) -> torch.Tensor:
+        """cv2.resize(frame, (size, size)) on the device (KerasYOLO.py:526), bit-identical to OpenCV's INTER_LINEAR.
+        frames: (B,H,W,3) uint8 CUDA tensor -> (B,size,size,3) uint8."""
+        size = size or self.image_size
+        if frames.dim() != 4 or frames.shape[3] != 3 or frames.dtype != torch.uint8 or not frames.is_cuda:
+            raise ValueError("resize_frames expects a (B,H,W,3) uint8 CUDA tensor")
+        frames = frames.contiguous()
+        B, H, W = frames.shape[0], frames.shape[1], frames.shape[2]
+        out = torch.empty((B, size, size, 3), dtype=torch.uint8, device=frames.device)
+        N.check(self.lib.b2t_resize_frames(self.h, frames.data_ptr(), H, W, B, out.data_ptr(), size, size, _stream()))
+        return out
+
     # ---------------------------------------------------------------- tracker helpers
     def pool_features(self, name: str, B: int, pool: str = "Global", chw_view: bool = False) -> torch.Tensor:
         h, w, c = self.layer_dims(name)

@@ -99,12 +99,17 @@ class KerasYOLO:
 
     # ------------------------------------------------------------------ reference API
     def _load(self, input_path):
+        """cv2.imread on the host (KerasYOLO.py:525), cv2.resize on the device (:526, engine.resize_frames --
+        bit-identical to OpenCV's INTER_LINEAR); returns (original HWC uint8 array, resized CUDA tensor)."""
         image = load_frame(input_path)
-        return image, load_frame(image, self.IMAGE_H)
+        t = torch.from_numpy(np.ascontiguousarray(image[None])).to(self.model.device)
+        if image.shape[0] == self.IMAGE_H and image.shape[1] == self.IMAGE_W:
+            return image, t[0]
+        return image, self.model.resize_frames(t, self.IMAGE_H)[0]
 
     def extract(self, input_path, layer):
         _, resized = self._load(input_path)
-        self.model.forward(torch.from_numpy(np.ascontiguousarray(resized[None])).to(self.model.device))
+        self.model.forward(resized[None].contiguous())
         return self.model.extract(layer, 1)[0].cpu().numpy()
 
     def predict(self, input_path, output_path):

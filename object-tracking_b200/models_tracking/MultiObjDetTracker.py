@@ -84,7 +84,11 @@ class MultiObjDetTracker:
         """MultiObjDetTracker.py:295-315 (with its evident intent: one window of SEQUENCE_LENGTH frames)."""
         assert len(input_paths) == self.SEQUENCE_LENGTH and len(output_paths) == self.SEQUENCE_LENGTH
         images = [load_frame(p) for p in input_paths]
-        x = np.stack([load_frame(im, self.IMAGE_H) for im in images])
+        # cv2.resize (MultiObjDetTracker.py:300) on the device, bit-identical to OpenCV's INTER_LINEAR
+        dev = self.model.device
+        x = torch.cat([self.model.resize_frames(torch.from_numpy(np.ascontiguousarray(im[None])).to(dev), self.IMAGE_H)
+                       if im.shape[:2] != (self.IMAGE_H, self.IMAGE_H) else torch.from_numpy(np.ascontiguousarray(im[None])).to(dev)
+                       for im in images])
         trk, _ = self.track_window(x)
         import cv2
         for image, boxes, path in zip(images, trk, output_paths):

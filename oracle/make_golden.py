@@ -164,9 +164,30 @@ def make_tracker_golden():
     print(f"[tracker] {len(out)} arrays written")
 
 
+def make_resize_golden():
+    """Outputs of the installed OpenCV's cv2.resize (the reference's ingest step, KerasYOLO.py:526) on seeded images."""
+    import cv2
+    from oracle import ingest_oracle
+    out, bad = {"cv2_version": np.array(cv2.__version__)}, 0
+    for seed, h, w, dst in ingest_oracle.RESIZE_CASES:
+        img = ingest_oracle.resize_case(seed, h, w)
+        ref = cv2.resize(img, (dst, dst))
+        out[f"case{seed}"] = ref
+        bad += int((ingest_oracle.resize_linear_u8(img, dst, dst) != ref).sum())
+    # wider sweep, not stored: the restatement must reproduce cv2 bit for bit
+    rng = np.random.default_rng(7)
+    for h, w in [(576, 768), (480, 640), (1080, 1920), (417, 415), (100, 1000), (720, 1280), (300, 500)]:
+        for dst in (416, 608):
+            img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+            bad += int((ingest_oracle.resize_linear_u8(img, dst, dst) != cv2.resize(img, (dst, dst))).sum())
+    assert bad == 0, f"ingest oracle differs from cv2.resize in {bad} bytes"
+    np.savez_compressed(os.path.join(GOLD, "resize_cases.npz"), **out)
+    print(f"[resize] {len(out) - 1} cv2 outputs written (cv2 {cv2.__version__}); restatement bit-exact on the sweep")
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    what = sys.argv[1:] or ["decode", "darknet", "keras", "tracker"]
+    what = sys.argv[1:] or ["decode", "darknet", "keras", "tracker", "resize"]
     if "decode" in what:
         make_decode_goldens()
     if "darknet" in what:
@@ -175,3 +196,5 @@ if __name__ == "__main__":
         make_keras_golden()
     if "tracker" in what:
         make_tracker_golden()
+    if "resize" in what:
+        make_resize_golden()

@@ -498,3 +498,23 @@ def test_benchmark_batch_bbox_parity():
             worst = max(worst, np.abs(rows[:, :4] - ref[:, :4]).max())
     assert checked >= B - 2, checked                                    # at most two frames with a threshold flip
     assert worst < 1e-3, worst
+
+
+@pytest.mark.gpu
+def test_device_resize_is_bit_identical_to_cv2():
+    """b2t_resize_frames (frame ingest, KerasYOLO.py:526) against the committed cv2.resize outputs and against the
+    oracle restatement at the network's input sizes, batched."""
+    from object_tracking_b200.engine import DetectorEngine
+    from oracle import ingest_oracle
+    eng = DetectorEngine(n_class=2, max_batch=1)
+    z = np.load(os.path.join(GOLD, "resize_cases.npz"))
+    for seed, h, w, dst in ingest_oracle.RESIZE_CASES:
+        img = ingest_oracle.resize_case(seed, h, w)
+        got = eng.resize_frames(torch.from_numpy(img[None]).cuda(), dst).cpu().numpy()[0]
+        assert np.array_equal(got, z[f"case{seed}"]), (seed, h, w, dst)
+    rng = np.random.default_rng(21)
+    for (h, w), dst in (((576, 768), 416), ((480, 640), 608), ((417, 415), 416), ((1080, 1920), 416)):
+        imgs = rng.integers(0, 256, (3, h, w, 3), dtype=np.uint8)
+        got = eng.resize_frames(torch.from_numpy(imgs).cuda(), dst).cpu().numpy()
+        for b in range(3):
+            assert np.array_equal(got[b], ingest_oracle.resize_linear_u8(imgs[b], dst, dst)), (h, w, dst, b)

@@ -120,3 +120,21 @@ def test_u8_normalisation_needs_no_table():
     # conv_1 computes float(u)/255.f in fp32; the reference computes image/255. in float64 and Keras casts to fp32
     u = np.arange(256)
     assert np.array_equal((u.astype(np.float64) / 255.0).astype(np.float32), u.astype(np.float32) / np.float32(255.0))
+
+
+def test_ingest_oracle_matches_cv2_resize_goldens():
+    """Frame ingest (KerasYOLO.py:526 cv2.resize): the restatement against outputs of OpenCV itself (committed), and
+    against the installed cv2 when there is one."""
+    from oracle import ingest_oracle
+    z = np.load(os.path.join(GOLD, "resize_cases.npz"))
+    for seed, h, w, dst in ingest_oracle.RESIZE_CASES:
+        img = ingest_oracle.resize_case(seed, h, w)
+        got = ingest_oracle.resize_linear_u8(img, dst, dst)
+        assert np.array_equal(got, z[f"case{seed}"]), (seed, h, w, dst)
+    try:
+        import cv2
+    except ImportError:
+        return
+    img = np.random.default_rng(3).integers(0, 256, (211, 333, 3), dtype=np.uint8)
+    for dst in (416, 608):
+        assert np.array_equal(ingest_oracle.resize_linear_u8(img, dst, dst), cv2.resize(img, (dst, dst)))
