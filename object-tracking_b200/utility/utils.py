@@ -144,6 +144,29 @@ def generate_rectangle_from_heatmap(heat_map, thresh=0.75, hmap_size=32):
     return int(r[0]), int(r[1]), int(r[2]), int(r[3])
 
 
+def overlap_score(y_true, y_pred):
+    """utility/utils.py:82-101: IoU of two corner boxes (x1, y1, x2, y2) as the reference's tracking metric computes
+    it (|dx*dy| products, no clamping of an empty intersection).  Host arithmetic in Python floats, like the
+    reference: it runs once per evaluated frame, after the accelerated path."""
+    x1 = max(y_true[0], y_pred[0])
+    y1 = max(y_true[1], y_pred[1])
+    x2 = min(y_true[2], y_pred[2])
+    y2 = min(y_true[3], y_pred[3])
+    intersection = float(abs((x1 - x2) * (y1 - y2)))
+    union = float(abs((y_true[0] - y_true[2]) * (y_true[1] - y_true[3]))) + \
+        float(abs((y_pred[0] - y_pred[2]) * (y_pred[1] - y_pred[3]))) - intersection
+    return intersection / union
+
+
+def average_overlap_score(y_true, y_pred):
+    """utility/utils.py:103-110 (mean of overlap_score over the paired samples)."""
+    score, total = 0.0, 0
+    for i, (t, p) in enumerate(zip(y_true, y_pred)):
+        score += overlap_score(t, p)
+        total = i
+    return score / (total + 1)
+
+
 def draw_boxes(image, boxes, labels):
     """utility/utils.py:190-206 (host, OpenCV): out of the accelerated path, kept for predict()."""
     import cv2

@@ -103,3 +103,23 @@ def test_weight_broadcast_protocol_world_size_2_gloo(tmp_path):
                        capture_output=True, text=True, timeout=170, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "OK" in r.stdout
+
+
+def test_overlap_metrics_match_reference_source():
+    """utility/utils.py:82-110 (tracking metric helpers, callers after the path): same numbers as the reference's own
+    functions exec'd from its source when /root/reference is present, fixed known answers otherwise."""
+    import importlib
+    U = importlib.import_module("object_tracking_b200.utility.utils")
+    a, b = (10., 20., 50., 80.), (30., 40., 70., 100.)
+    assert abs(U.overlap_score(a, b) - (20. * 40.) / (40. * 60. * 2 - 20. * 40.)) < 1e-12
+    assert U.average_overlap_score([a, a], [a, b]) == (1.0 + U.overlap_score(a, b)) / 2
+    ref_path = "/root/reference/utility/utils.py"
+    if os.path.exists(ref_path):
+        src = open(ref_path).read().split("\n")
+        ns = {}
+        exec(compile("\n".join(src[81:110]), "ref_utils_metrics", "exec"), ns)     # overlap_score, average_overlap_score
+        rng = np.random.default_rng(0)
+        for _ in range(50):
+            t = np.sort(rng.uniform(0, 100, 4)); p = np.sort(rng.uniform(0, 100, 4))
+            t = (t[0], t[1], t[2], t[3]); p = (p[0], p[1], p[2], p[3])
+            assert U.overlap_score(t, p) == ns["overlap_score"](t, p)
