@@ -267,7 +267,8 @@ def main_b200(args):
 
     # ---- e2e: through the plugin call (TinyTracker.track_windows) with HOST buffers: every step's frames travel
     # pinned host -> device inside the timed region and every step's result is read back to the host.  The copy of
-    # step i+1 is issued on a second stream while step i computes (double-buffered device staging).
+    # step i+1 is issued on a second stream while step i computes (double-buffered device staging); the host reads
+    # step i-1's boxes (async D2H into pinned memory + event) while step i runs, and the last step's before the clock stops.
     copy_stream = torch.cuda.Stream()
     stage = [torch.empty((S, T, IMAGE, IMAGE, 3), dtype=torch.uint8, device="cuda") for _ in range(2)]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
@@ -281,17 +282,19 @@ def main_b200(args):
                 stage[slot][s].copy_(w[s], non_blocking=True)
             ready[slot].record(copy_stream)
 
-    y_host = torch.empty((S, T, 4), dtype=torch.float32).pin_memory()
+    y_host = [torch.empty((S, T, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
+    y_done = [torch.cuda.Event(), torch.cuda.Event()]
     for slot in range(2):
         consumed[slot].record()
     for i in range(2):                                              # warm the path (graphs exist already)
         upload(i, i & 1)
         torch.cuda.current_stream().wait_event(ready[i & 1])
-        y_host.copy_(trk.track_windows(stage[i & 1]))
+        y_host[i & 1].copy_(trk.track_windows(stage[i & 1]))
         consumed[i & 1].record()
     barrier()
     t0 = time.perf_counter()
     upload(args.warmup, 0)
+    checksum = 0.0
     for i in range(args.steps):
         slot = i & 1
         if i + 1 < args.steps:
@@ -299,7 +302,13 @@ def main_b200(args):
         torch.cuda.current_stream().wait_event(ready[slot])
         y = trk.track_windows(stage[slot])
         consumed[slot].record()
-        y_host.copy_(y)                                             # D2H + sync: the host has this step's boxes
+        y_host[slot].copy_(y, non_blocking=True)                    # D2H of this step's boxes into pinned memory
+        y_done[slot].record()
+        if i:                                                       # the host reads step i-1's boxes while step i runs
+            y_done[slot ^ 1].synchronize()
+            checksum += float(y_host[slot ^ 1][0, 0, 0])
+    y_done[(args.steps - 1) & 1].synchronize()
+    checksum += float(y_host[(args.steps - 1) & 1][0, 0, 0])
     barrier()
     e2e_s = time.perf_counter() - t0
 
