@@ -941,7 +941,7 @@ static int run_conv1(b2t_ctx *c, const void *frames, int dtype, int B, cudaStrea
         p.h_tiles_x = (l.W + p.hC - 1) / p.hC; p.h_tiles_y = (l.H + p.hR - 1) / p.hR;
         p.pm_mode = 1; p.pm_n = 32; p.pm_tmem_cols = 128; p.pm_stage_ld = 36; p.pm_glog = 2;
         p.pw_patch_bytes = l.pm_plane_bytes;
-        p.pw_stage_bytes = (int)align_up((size_t)128 * 36 * 4, 1024);
+        p.pw_stage_bytes = 0;                                  // mode 1 pools in registers: no staging buffers
         p.pm_w = c->d_blob + c->off_w1pm; p.pm_w_bytes = 3 * 4096;
         p.dbg = getenv("B2T_DBG") ? atoi(getenv("B2T_DBG")) : 0;
         p.magic_tx = magic_for(p.h_tiles_x); p.magic_ty = magic_for(p.h_tiles_y);
