@@ -246,8 +246,9 @@ def main_b200(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    PIPE = not args.no_pipeline          # tracker tail of step i overlaps conv_1..8 of step i+1 (BaseTracker.track_windows)
     for i in range(args.warmup):
-        trk.track_windows(window(dev, i))
+        trk.track_windows(window(dev, i), pipeline=PIPE)
     eng.forward_events = []
     barrier()
     sampler.mark_start()
@@ -255,7 +256,9 @@ def main_b200(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
-        out = trk.track_windows(window(dev, args.warmup + i))
+        out = trk.track_windows(window(dev, args.warmup + i), pipeline=PIPE)
+    if PIPE:
+        torch.cuda.current_stream().wait_event(trk.tail_done)       # the last step's tail is inside the timed region
     e1.record()
     barrier()
     sampler.mark_end()
@@ -289,8 +292,10 @@ def main_b200(args):
     for i in range(2):                                              # warm the path (graphs exist already)
         upload(i, i & 1)
         torch.cuda.current_stream().wait_event(ready[i & 1])
-        y_host[i & 1].copy_(trk.track_windows(stage[i & 1]))
+        y = trk.track_windows(stage[i & 1], pipeline=PIPE)
         consumed[i & 1].record()
+        with torch.cuda.stream(trk.tail_stream if PIPE else torch.cuda.current_stream()):
+            y_host[i & 1].copy_(y)
     barrier()
     t0 = time.perf_counter()
     upload(args.warmup, 0)
@@ -300,10 +305,11 @@ def main_b200(args):
         if i + 1 < args.steps:
             upload(args.warmup + i + 1, slot ^ 1)
         torch.cuda.current_stream().wait_event(ready[slot])
-        y = trk.track_windows(stage[slot])
+        y = trk.track_windows(stage[slot], pipeline=PIPE)
         consumed[slot].record()
-        y_host[slot].copy_(y, non_blocking=True)                    # D2H of this step's boxes into pinned memory
-        y_done[slot].record()
+        with torch.cuda.stream(trk.tail_stream if PIPE else torch.cuda.current_stream()):
+            y_host[slot].copy_(y, non_blocking=True)                # D2H of this step's boxes into pinned memory
+            y_done[slot].record()
         if i:                                                       # the host reads step i-1's boxes while step i runs
             y_done[slot ^ 1].synchronize()
             checksum += float(y_host[slot ^ 1][0, 0, 0])
@@ -369,6 +375,7 @@ if __name__ == "__main__":
                          "work items ~ 2 x 148 SMs for the 13x13 layers)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="run the tracker tail of a step before the next step starts")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
     sys.exit(main_reference(a) if a.impl == "reference" else main_b200(a))

@@ -83,6 +83,11 @@ int  b2t_finalize(b2t_ctx *ctx, int upload, void *stream);
  * (the context keeps its own copy, see b2t_logits).  Asynchronous on `stream`. */
 int  b2t_yolo_forward(b2t_ctx *ctx, const void *frames_dev, int frame_dtype, int batch,
                       float *logits_dev, void *stream);
+/* conv_first .. conv_last (1..23) of the same pass; frames_dev is read only when conv_first == 1, logits_dev is
+ * written only when conv_last == 23.  For host pipelines that overlap the tracker tail of step i with the first
+ * layers of step i+1 (BaseTracker.track_windows(pipeline=True)). */
+int  b2t_yolo_forward_range(b2t_ctx *ctx, const void *frames_dev, int frame_dtype, int batch, int conv_first,
+                            int conv_last, float *logits_dev, void *stream);
 const float *b2t_logits(const b2t_ctx *ctx);          /* device (max_batch,G,G,5*(5+C)) of the last forward */
 /* KerasYOLO.extract (KerasYOLO.py:509-520) / network_extract_feat (network.c:589-598): copy a layer's
  * post-activation output (pre-pool), NHWC float32, into out_dev.  name: "norm_1".."norm_22", "conv_23",

@@ -983,27 +983,37 @@ static int run_conv1(b2t_ctx *c, const void *frames, int dtype, int B, cudaStrea
 }
 
 static int forward_impl(b2t_ctx *c, const void *frames, int dtype, int B, float *logits_user, cudaStream_t st,
-                        cudaEvent_t *ev /* 24 events or NULL */) {
+                        cudaEvent_t *ev /* 24 events or NULL */, int first = 1, int last = 23) {
     if (!c || !c->finalized) return fail(-1, "b2t_yolo_forward: context not finalized");
-    if (!frames) return fail(-1, "b2t_yolo_forward: null frames");
+    if (first < 1 || last > 23 || first > last) return fail(-1, "b2t_yolo_forward: bad layer range [%d, %d]", first, last);
+    if (first == 1 && !frames) return fail(-1, "b2t_yolo_forward: null frames");
     if (B < 1 || B > c->cfg.max_batch) return fail(-1, "batch %d outside [1, max_batch=%d]", B, c->cfg.max_batch);
     if (dtype != B2T_FRAME_U8 && dtype != B2T_FRAME_F32) return fail(-1, "bad frame dtype %d", dtype);
     int rc;
     if (ev) cudaEventRecord(ev[0], st);
-    if ((rc = run_conv1(c, frames, dtype, B, st))) return rc;
-    if (ev) cudaEventRecord(ev[1], st);
+    if (first == 1) {
+        if ((rc = run_conv1(c, frames, dtype, B, st))) return rc;
+        if (ev) cudaEventRecord(ev[1], st);
+    }
     float *logits = reinterpret_cast<float *>(c->d_ws + c->off_logits);
-    for (int i = 2; i <= 23; ++i) {
+    for (int i = first < 2 ? 2 : first; i <= last; ++i) {
         if ((rc = run_conv(c, c->conv[i], B, i == 23 ? logits : nullptr, st))) return rc;
         if (ev) cudaEventRecord(ev[i], st);
     }
-    if (logits_user && logits_user != logits)
+    if (last == 23 && logits_user && logits_user != logits)
         CK(cudaMemcpyAsync(logits_user, logits, (size_t)B * c->G * c->G * c->A * c->D * 4, cudaMemcpyDeviceToDevice, st));
     return 0;
 }
 
 extern "C" int b2t_yolo_forward(b2t_ctx *c, const void *frames, int dtype, int B, float *logits_dev, void *stream) {
     return forward_impl(c, frames, dtype, B, logits_dev, (cudaStream_t)stream, nullptr);
+}
+
+// conv_first .. conv_last of the same forward pass (1 <= first <= last <= 23): lets a host pipeline put the layers
+// whose outputs the tracker tail reads (conv_9 and later) behind an event while conv_1..8 of the next step already run.
+extern "C" int b2t_yolo_forward_range(b2t_ctx *c, const void *frames, int dtype, int B, int first, int last,
+                                      float *logits_dev, void *stream) {
+    return forward_impl(c, frames, dtype, B, logits_dev, (cudaStream_t)stream, nullptr, first, last);
 }
 
 extern "C" const float *b2t_logits(const b2t_ctx *c) {

@@ -131,6 +131,15 @@ class DetectorEngine:
             ev.append((a, b))
         return self.logits(B)
 
+    def forward_range(self, frames: torch.Tensor, first: int, last: int) -> None:
+        """conv_first .. conv_last of the forward pass over `frames` (same checks as forward())."""
+        if frames.device != self.device or not frames.is_contiguous():
+            raise ValueError("frames must be a contiguous tensor on the engine's device")
+        dt = {torch.uint8: N.FRAME_U8, torch.float32: N.FRAME_F32}.get(frames.dtype)
+        if dt is None:
+            raise ValueError("frames must be uint8 or float32")
+        N.check(self.lib.b2t_yolo_forward_range(self.h, frames.data_ptr(), dt, frames.shape[0], first, last, None, _stream()))
+
     def logits(self, B: int) -> torch.Tensor:
         """Zero-copy view of the context's logits buffer (it lives inside the torch-owned workspace)."""
         if self._logits_view is None:

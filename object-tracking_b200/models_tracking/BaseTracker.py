@@ -88,12 +88,18 @@ class BaseTracker(object):
         fv, xin = self._tracker_inputs_from_state(S * T, W, H)
         return self.head.sequence(fv.view(S, T, -1), xin.view(S, T, -1), reset=reset)
 
-    def track_windows(self, frames: torch.Tensor, reset: bool = True, graph: bool = True) -> torch.Tensor:
+    def track_windows(self, frames: torch.Tensor, reset: bool = True, graph: bool = True,
+                      pipeline: bool = False) -> torch.Tensor:
         """frames (S,T,H,W,3) uint8 on the GPU: S independent streams (or windows), T consecutive frames each.
         One batched detector pass over S*T frames, then T recurrent steps over the S streams in parallel
         (input projection hoisted out of the recurrence).  reset=True reproduces Keras' stateless windows.
         graph=True replays the step from two CUDA graphs captured on first use (conv stack | decode + tracker):
-        the ~45 launches of a step are launch-latency bound otherwise.  The result tensor is reused."""
+        the ~45 launches of a step are launch-latency bound otherwise.  The result tensor is reused.
+        pipeline=True (with graph=True) additionally overlaps the tracker tail of this call with the first conv
+        layers of the NEXT call: the tail (decode, selection, pooling, LSTM) runs on ``self.tail_stream`` and only
+        reads outputs of conv_9 and later, so the next call's conv_1..8 start at once and its conv_9..23 wait for
+        ``self.tail_done``.  The returned tensor is then valid after ``self.tail_done`` (an event on the tail stream):
+        consume it on ``self.tail_stream`` or wait for the event."""
         S, T, H, W = frames.shape[0], frames.shape[1], frames.shape[2], frames.shape[3]
         if S > self.max_streams:
             raise ValueError(f"{S} streams > max_streams {self.max_streams}")
@@ -101,6 +107,11 @@ class BaseTracker(object):
         if not graph:
             eng.forward(frames.reshape(S * T, H, W, 3))
             return self._tail(S, T, W, H, reset)
+        if pipeline:
+            return self._track_windows_pipelined(frames, reset)
+        if getattr(self, "tail_done", None) is not None:       # a pipelined call may still be in its tail
+            torch.cuda.current_stream().wait_event(self.tail_done)
+            self.tail_done = None
         key = (S, T, H, W, frames.dtype, bool(reset))
         g = self._graphs.get(key)
         if g is None:
@@ -131,6 +142,59 @@ class BaseTracker(object):
             e1.record()
             ev.append((e0, e1))
         g_tail.replay()
+        eng.add_graph_launches(n_kernels)
+        return static_out
+
+    _SPLIT = 8          # conv_1 .. conv_8 do not write anything the tracker tail reads
+
+    def _track_windows_pipelined(self, frames: torch.Tensor, reset: bool) -> torch.Tensor:
+        S, T, H, W = frames.shape[0], frames.shape[1], frames.shape[2], frames.shape[3]
+        eng = self.model_detector.engine
+        key = ("pipe", S, T, H, W, frames.dtype, bool(reset))
+        g = self._graphs.get(key)
+        if g is None:
+            static_in = torch.empty((S * T, H, W, 3), dtype=frames.dtype, device=frames.device)
+            static_in.view(S, T, H, W, 3).copy_(frames)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                      # warm-up outside capture (allocations, lazy init)
+                eng.forward(static_in)
+                self._tail(S, T, W, H, reset)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            n0 = eng.lib.b2t_launch_count(eng.h)
+            g_a, g_b, g_tail = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_a):
+                eng.forward_range(static_in, 1, self._SPLIT)
+            with torch.cuda.graph(g_b):
+                eng.forward_range(static_in, self._SPLIT + 1, 23)
+            with torch.cuda.graph(g_tail):
+                static_out = self._tail(S, T, W, H, reset)
+            g = self._graphs[key] = (g_a, g_b, g_tail, static_in, static_out, eng.lib.b2t_launch_count(eng.h) - n0)
+            if getattr(self, "tail_stream", None) is None:
+                self.tail_stream = torch.cuda.Stream()
+                self.tail_done = None
+        g_a, g_b, g_tail, static_in, static_out, n_kernels = g
+        cur = torch.cuda.current_stream()
+        static_in.view(S, T, H, W, 3).copy_(frames, non_blocking=True)
+        ev = eng.forward_events
+        if ev is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        g_a.replay()                                           # conv_1 .. conv_8: overlaps the previous call's tail
+        if self.tail_done is not None:
+            cur.wait_event(self.tail_done)                     # conv_9 .. 23 overwrite what that tail reads
+        g_b.replay()
+        if ev is not None:
+            e1.record()
+            ev.append((e0, e1))
+        conv_done = torch.cuda.Event()
+        conv_done.record(cur)
+        with torch.cuda.stream(self.tail_stream):
+            self.tail_stream.wait_event(conv_done)
+            g_tail.replay()
+            self.tail_done = torch.cuda.Event()
+            self.tail_done.record(self.tail_stream)
         eng.add_graph_launches(n_kernels)
         return static_out
 

@@ -518,3 +518,31 @@ def test_device_resize_is_bit_identical_to_cv2():
         got = eng.resize_frames(torch.from_numpy(imgs).cuda(), dst).cpu().numpy()
         for b in range(3):
             assert np.array_equal(got[b], ingest_oracle.resize_linear_u8(imgs[b], dst, dst)), (h, w, dst, b)
+
+
+@pytest.mark.gpu
+def test_pipelined_track_windows_equals_serial():
+    """track_windows(pipeline=True): the tail of call i overlaps conv_1..8 of call i+1 (two streams, three graphs,
+    conv_9..23 behind the previous tail's event).  Same kernels, same numbers: bit-identical to the serial mode for
+    a sequence of different windows, whatever the interleaving."""
+    from object_tracking_b200.models_tracking.TinyTracker import TinyTracker
+    cfg = {"model_detector": {"name": "YOLO", "config_file": "cfg/yolov2.cfg", "meta_file": "cfg/coco.data",
+                              "weights_file": "none.weights", "fv_layer": 25, "nms": 0.45, "thresh": 0.5, "hier_thresh": 0.5},
+           "model_tracker": {"name": "TinyTracker", "lstm_units": 512, "sequence_length": 4, "heatmap_size": 32},
+           "train": {"cpu_only": 0, "dgpu_id": 0, "tgpu_id": 0, "pool": "Global", "batch_size": 4, "max_epochs": 0,
+                     "tensorboard_dir": "logs/", "saved_model_dir": "models/", "classes": ["Person", "Car"]}}
+    trk = TinyTracker(cfg, max_streams=2)
+    rng = np.random.default_rng(8)
+    wins = [torch.from_numpy(rng.integers(0, 256, (2, 4, 416, 416, 3), dtype=np.uint8)).cuda() for _ in range(4)]
+    serial = [trk.track_windows(w).clone() for w in wins]
+    outs = []
+    for w in wins:                                     # back to back: no host sync between the calls
+        y = trk.track_windows(w, pipeline=True)
+        with torch.cuda.stream(trk.tail_stream):
+            outs.append(y.clone())
+    torch.cuda.synchronize()
+    for a, b in zip(serial, outs):
+        assert torch.equal(a, b)
+    again = trk.track_windows(wins[0])                 # serial call right after a pipelined one waits for its tail
+    torch.cuda.synchronize()
+    assert torch.equal(again, serial[0])
