@@ -107,6 +107,13 @@ def reference_runner():
     compiled from /root/reference/darknet/src by oracle/Makefile) driven through the ctypes call sequence of
     models_detection/YOLO.py:140-170, + the numpy LSTM step (Keras is not installable here).  Falls back to
     the oracle port (torch-CPU forward) when the .so did not travel."""
+    # all host threads, also under torchrun (it exports OMP_NUM_THREADS=1 for every rank)
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())
+    try:
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(os.cpu_count())
+    except OSError:
+        pass
     from object_tracking_b200 import weights as W
     from oracle import darknet_ref, tracker_oracle, yolo_oracle
     w = W.synthetic_yolo_weights(N_CLASS, seed=0)
@@ -195,7 +202,7 @@ def main_reference(args):
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": kind,
                              "sample": f"{args.steps} single frames after {args.warmup} warm-up; {what}"},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    print(json.dumps(line), file=JSON_OUT, flush=True)
     return 0
 
 
@@ -359,7 +366,7 @@ def main_b200(args):
             fps, dt, kind, what = time_reference(4, 1)
             line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": os.cpu_count(), "kind": kind,
                                     "sample": f"4 frames (one window) after 1 warm-up frame, {dt:.1f} s; {what}"}
-        print(json.dumps(line))
+        print(json.dumps(line), file=JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -378,4 +385,9 @@ if __name__ == "__main__":
     ap.add_argument("--no-pipeline", action="store_true", help="run the tracker tail of a step before the next step starts")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
+    # stdout carries exactly ONE JSON line: whatever libraries print there (NCCL's version banner, darknet's layer
+    # table) is sent to stderr instead -- file descriptor 1 is pointed at stderr and the line is written to a duplicate
+    sys.stdout.flush()
+    JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     sys.exit(main_reference(a) if a.impl == "reference" else main_b200(a))
