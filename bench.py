@@ -341,7 +341,9 @@ def main_b200(args):
         line = {"metric": METRIC, "value": total_frames / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f16x2-split operands, f32 accumulate", "data": "synthetic",
-                "config": workload_config(S, world),
+                "config": dict(workload_config(S, world),
+                               pipeline="tracker tail of step i on a second stream under conv_1..8 of step i+1"
+                               if PIPE else "serial"),
                 "e2e": {"value": total_frames / (e2e_ms * 1e-3), "unit": UNIT,
                         "h2d_bytes_per_step": frames_per_step * IMAGE * IMAGE * 3,
                         "d2h_bytes_per_step": frames_per_step * 4 * 4},
@@ -363,9 +365,9 @@ def main_b200(args):
                              "hbm": {"achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
                                      "algorithmic_bytes_per_launch": bytes_per_fwd}}}
         if world == 1 and not args.no_cpu_baseline:
-            fps, dt, kind, what = time_reference(4, 1)
+            fps, dt, kind, what = time_reference(40, 2)
             line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": os.cpu_count(), "kind": kind,
-                                    "sample": f"4 frames (one window) after 1 warm-up frame, {dt:.1f} s; {what}"}
+                                    "sample": f"40 frames (10 windows) after 2 warm-up frames, {dt:.1f} s; {what}"}
         print(json.dumps(line), file=JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
