@@ -9,7 +9,9 @@ the detector is stateless per frame).  9 windows are chosen for the machine: 36 
 = 288 work items on the 13x13 layers ~ 2 x 148 SMs; --windows 4 is the reference's config.json train.batch_size.
 Per step: one batched detector pass, region decode + NMS, detection choice, feature pooling, the LSTM input
 projection for all frames, 4 sequential recurrent steps over the windows, one batched Dense head.
---windows 1 gives the single-window latency case.  N>1: every rank runs its own
+--windows 1 gives the single-window latency case.  Steps are pipelined (TinyTracker.track_windows(pipeline=True): the
+tracker tail of step i runs on a second stream under conv_1..8 of step i+1; --no-pipeline serialises them).
+stdout carries exactly one JSON line (library chatter is redirected to stderr).  N>1: every rank runs its own
 stream(s) -- independent units, no data-path collective; one NCCL broadcast of the packed weights at init.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--windows S] [--impl reference]
