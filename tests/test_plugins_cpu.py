@@ -123,3 +123,21 @@ def test_overlap_metrics_match_reference_source():
             t = np.sort(rng.uniform(0, 100, 4)); p = np.sort(rng.uniform(0, 100, 4))
             t = (t[0], t[1], t[2], t[3]); p = (p[0], p[1], p[2], p[3])
             assert U.overlap_score(t, p) == ns["overlap_score"](t, p)
+
+
+def test_item_decode_magic_multiplier_is_exact():
+    """conv_pm_kernel decodes its work items with host-made magic multipliers (api.cu magic_for, conv_pm.cu
+    decode_item): q = umulhi(n, ceil(2^32 / d)) must equal n // d for every item index the kernels can see
+    (n < 2^32 / d).  The arithmetic is restated here and checked exhaustively on the divisors in use and on
+    random ones."""
+    rng = np.random.default_rng(0)
+    divisors = [2, 3, 4, 5, 7, 13, 14, 52, 104, 152, 208, 304, 1456] + [int(x) for x in rng.integers(2, 5000, 40)]
+    for d in divisors:
+        m = ((1 << 32) + d - 1) // d
+        assert m < (1 << 32)
+        hi = min((1 << 32) // d, 1 << 22)
+        n = np.concatenate([np.arange(0, min(hi, 200000), dtype=np.uint64),
+                            rng.integers(0, hi, 100000).astype(np.uint64),
+                            np.array([hi - 1], dtype=np.uint64)])
+        q = (n * np.uint64(m)) >> np.uint64(32)
+        assert np.array_equal(q, n // np.uint64(d)), d
