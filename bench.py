@@ -118,7 +118,7 @@ def reference_runner():
         pass
     from object_tracking_b200 import weights as W
     from oracle import darknet_ref, tracker_oracle, yolo_oracle
-    w = W.synthetic_yolo_weights(N_CLASS, seed=0)
+    w = W.synthetic_detector_weights(N_CLASS, seed=0)
     wl = {k: v.astype(np.float32) for k, v in W.synthetic_lstm_weights(1024 + 4, 512, 4, seed=1).items()}
     state = {"h": np.zeros((1, 512), np.float32), "c": np.zeros((1, 512), np.float32), "t": 0}
 

@@ -137,6 +137,12 @@ int  b2t_lstm_sequence(b2t_lstm *l, const float *fv_dev, const float *det_dev, i
  * Not capturable in a CUDA graph the first time a (src, dst) geometry is seen (coefficient tables are uploaded). */
 int  b2t_resize_frames(b2t_ctx *ctx, const unsigned char *src_dev, int src_h, int src_w, int batch,
                        unsigned char *dst_dev, int dst_h, int dst_w, void *stream);
+/* darknet's ingest for YOLO.detect (YOLO.py:141-145): load_image_color's float(u8)/255 RGB conversion + letterbox_image
+ * (image.c:960-979; network_predict_image, network.c:609-616) for `batch` (src_h, src_w, 3) uint8 frames on the
+ * device -> dst_dev (batch, image_h, image_w, 3) float32, ready for b2t_yolo_forward(B2T_FRAME_F32).
+ * swap_rb != 0: the source is BGR (cv2.imread). */
+int  b2t_letterbox_frames(b2t_ctx *ctx, const unsigned char *src_dev, int src_h, int src_w, int batch, int swap_rb,
+                          float *dst_dev, void *stream);
 /* pooled feature of the last forward's conv layer `name` for frames [0,batch): Global -> (B,C);
  * Max -> (B,(H/4)*(W/4)*C).  chw_view=1 reproduces preprocessing.py:419 (CHW buffer viewed as HWC). */
 int  b2t_pool_features(b2t_ctx *ctx, const char *name, int batch, int pool_mode, int chw_view,

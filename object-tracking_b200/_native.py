@@ -55,6 +55,7 @@ SIGNATURES = {
     "b2t_lstm_sequence": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, C.c_int, C.c_int, _vp]),
     "b2t_pool_features": (C.c_int, [_vp, C.c_char_p, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "b2t_resize_frames": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, _vp]),
+    "b2t_letterbox_frames": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "b2t_heatmap_from_box": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp]),
     "b2t_select_detection": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp,
                                        _vp, _vp]),

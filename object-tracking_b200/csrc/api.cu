@@ -1333,6 +1333,23 @@ extern "C" int b2t_resize_frames(b2t_ctx *c, const unsigned char *src_dev, int s
     return 0;
 }
 
+// load_image_color + letterbox_image (image.c:1442-1482, :960-979) for a batch of uint8 frames already on the device.
+extern "C" int b2t_letterbox_frames(b2t_ctx *c, const unsigned char *src_dev, int src_h, int src_w, int B, int swap_rb,
+                                    float *dst_dev, void *stream) {
+    if (!c || !src_dev || !dst_dev) return fail(-1, "b2t_letterbox_frames: null argument");
+    if (src_h < 1 || src_w < 1 || B < 1) return fail(-1, "b2t_letterbox_frames: bad geometry");
+    LetterboxParams p;
+    p.src = src_dev; p.dst = dst_dev; p.B = B; p.src_h = src_h; p.src_w = src_w;
+    p.net_h = c->cfg.image_h; p.net_w = c->cfg.image_w; p.swap_rb = swap_rb ? 1 : 0;
+    if (((float)p.net_w / src_w) < ((float)p.net_h / src_h)) { p.new_w = p.net_w; p.new_h = (src_h * p.net_w) / src_w; }
+    else { p.new_h = p.net_h; p.new_w = (src_w * p.net_h) / src_h; }
+    if (p.new_w < 2 || p.new_h < 2) return fail(-1, "b2t_letterbox_frames: frame aspect ratio too extreme");
+    const int rc = launch_letterbox_u8(p, (cudaStream_t)stream);
+    if (rc) return fail(-2, "letterbox launch: %s", cudaGetErrorString((cudaError_t)rc));
+    c->launches += 1;
+    return 0;
+}
+
 extern "C" int b2t_pool_features(b2t_ctx *c, const char *name, int B, int mode, int chw_view, float *fv, void *stream) {
     if (!c || !c->finalized || !fv) return fail(-1, "b2t_pool_features: bad arguments");
     if (B < 1 || B > c->cfg.max_batch) return fail(-1, "bad batch");

@@ -440,11 +440,16 @@ __global__ void __launch_bounds__(kDecThreads) decode_nms_kernel(const DecodePar
 }
 
 int launch_decode(bool darknet, const DecodeParams &p, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(decode_nms_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecodeSmem));
-        cudaFuncSetAttribute(decode_nms_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecodeSmem));
-        attr_set = true;
+    // the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(decode_nms_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecodeSmem));
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(decode_nms_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecodeSmem));
+        if (e != cudaSuccess) return (int)e;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     if (darknet)
         decode_nms_kernel<true><<<p.B, kDecThreads, sizeof(DecodeSmem), st>>>(p);

@@ -79,6 +79,14 @@ struct ResizeParams {
     const int4 *ytab;           // per destination row:    source row,    next source row,    b0, b1
 };
 
+struct LetterboxParams {
+    const unsigned char *src;   // (B, src_h, src_w, 3) uint8
+    float *dst;                 // (B, net_h, net_w, 3) float32
+    int B, src_h, src_w, net_h, net_w;
+    int new_w, new_h;           // size of the embedded resized image (darknet's integer arithmetic, host-computed)
+    int swap_rb;                // 1 = source is BGR (cv2.imread), emit RGB like load_image_color
+};
+
 struct ConvLstmGateParams {
     const float *g;       // (M, 4u) pre-activations (input conv + bias + recurrent conv)
     float *c;             // (M, u) cell state, in place
@@ -132,6 +140,7 @@ int launch_heatmap_from_box(const float *xywh, int n, int size, float *heat, cud
 int launch_select_detection(const SelectParams &p, cudaStream_t st);
 int launch_box_from_heatmap(const float *heat, int n, int size, float thresh, int *rect, cudaStream_t st);
 int launch_resize_bilinear_u8(const ResizeParams &p, cudaStream_t st);
+int launch_letterbox_u8(const LetterboxParams &p, cudaStream_t st);
 int launch_convlstm_gates(const ConvLstmGateParams &p, cudaStream_t st);
 
 }  // namespace b2t

@@ -304,8 +304,8 @@ __global__ void __launch_bounds__(kLstmThreads) lstm_seq_kernel(const LstmParams
                 const long long t_start = clock64();
                 do {
                     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
-                    // all CTAs are co-resident by construction (grid <= SM count, launched alone on the stream); if
-                    // that ever fails, fail loudly instead of hanging the device
+                    // all CTAs are co-resident: launch_lstm_seq launches cooperatively (a runtime guarantee); should
+                    // the barrier still not complete, fail loudly instead of hanging the device
                     if (seen < target && clock64() - t_start > (1ll << 31)) __trap();
                 } while (seen < target);
             }
@@ -496,8 +496,21 @@ int launch_lstm_seq(const LstmParams &p, int T, float *h_a, float *h_b, unsigned
     if (p.S > kSeqMaxStreams || p.units > 64 * kSeqMaxK || p.units / kUnitsPerBlock > n_sm) return -1;   // fall back
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), st);
     if (e != cudaSuccess) return (int)e;
-    lstm_seq_kernel<<<p.units / kUnitsPerBlock, kLstmThreads, 0, st>>>(p, T, h_a, h_b, counter);
-    return (int)cudaGetLastError();
+    // The kernel synchronises its CTAs between time steps with a counter barrier, so every CTA must be resident at
+    // once.  A cooperative launch makes that a guarantee of the runtime (it is refused when the grid cannot be
+    // co-resident, and scheduled as a whole when other streams -- e.g. the next step's persistent conv kernels in
+    // BaseTracker's pipelined mode -- occupy SMs), instead of an assumption about what else is running.
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lstm_seq_kernel, kLstmThreads, 0);
+    if (e != cudaSuccess) return (int)e;
+    if (per_sm * n_sm < p.units / kUnitsPerBlock) return -1;     // fall back to one launch per step
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(p.units / kUnitsPerBlock); cfg.blockDim = dim3(kLstmThreads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, lstm_seq_kernel, p, T, h_a, h_b, counter);
 }
 int launch_dense_sigmoid(const float *h, const float *wd, const float *bd, int units, int n_out, int S, float *y,
                          int y_stride, cudaStream_t st) {

@@ -34,6 +34,18 @@ def _np_ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+def rows_to_host(rows: torch.Tensor, counts: torch.Tensor):
+    """(B,max,8) decode rows + (B,) counts on the device -> list of per-frame (n,8) numpy arrays.  The decode kernels
+    report a candidate / entry overflow of their shared-memory tables as count = -1 (only reachable with thresholds
+    below 0.5, where several classes per anchor can pass): that is an error, never a slice."""
+    n = counts.cpu().numpy()
+    if (n < 0).any():
+        raise N.B2TError("decode: more (anchor, class) candidates than the kernel's capacity in frame(s) "
+                         f"{np.nonzero(n < 0)[0].tolist()} (threshold too low)")
+    r = rows.cpu().numpy()
+    return [r[i, :int(n[i])] for i in range(len(n))]
+
+
 class DetectorEngine:
     def __init__(self, n_class: int = 80, image_size: int = 416, max_batch: int = 4, semantics: str = "keras",
                  bn_eps: float = 1e-3, engine: str = "tcgen05", device: int = 0, convlstm_units: int = 0,
@@ -211,6 +223,17 @@ class DetectorEngine:
         B, H, W = frames.shape[0], frames.shape[1], frames.shape[2]
         out = torch.empty((B, size, size, 3), dtype=torch.uint8, device=frames.device)
         N.check(self.lib.b2t_resize_frames(self.h, frames.data_ptr(), H, W, B, out.data_ptr(), size, size, _stream()))
+        return out
+
+    def letterbox_frames(self, frames: torch.Tensor, bgr: bool = False) -> torch.Tensor:
+        """darknet ingest (load_image_color + letterbox_image, image.c:960-979,1442-1482) on the device:
+        (B,H,W,3) uint8 frames of any size -> (B,S,S,3) float32 RGB in [0,1], what network_predict_image feeds."""
+        if frames.dim() != 4 or frames.shape[3] != 3 or frames.dtype != torch.uint8 or not frames.is_cuda:
+            raise ValueError("letterbox_frames expects a (B,H,W,3) uint8 CUDA tensor")
+        frames = frames.contiguous()
+        B, H, W = frames.shape[0], frames.shape[1], frames.shape[2]
+        out = torch.empty((B, self.image_size, self.image_size, 3), dtype=torch.float32, device=frames.device)
+        N.check(self.lib.b2t_letterbox_frames(self.h, frames.data_ptr(), H, W, B, 1 if bgr else 0, out.data_ptr(), _stream()))
         return out
 
     # ---------------------------------------------------------------- tracker helpers

@@ -15,7 +15,7 @@ from typing import List, Optional
 import numpy as np
 import torch
 
-from ..engine import DetectorEngine
+from ..engine import DetectorEngine, rows_to_host
 from ..utility.utils import BoundBox, boxes_from_rows, draw_boxes, normalize
 from ..weights import ANCHORS, read_darknet_weights, synthetic_yolo_weights
 from ._common import load_frame
@@ -93,9 +93,7 @@ class KerasYOLO:
         t = t.to(self.model.device).contiguous()
         logits = self.model.forward(t)
         boxes, counts = self.model.decode(logits, self.OBJ_THRESHOLD, self.NMS_THRESHOLD, self.ANCHORS)
-        counts = counts.cpu().numpy()
-        rows = boxes.cpu().numpy()
-        return [boxes_from_rows(rows[i, :int(counts[i])], self.CLASS) for i in range(t.shape[0])]
+        return [boxes_from_rows(r, self.CLASS) for r in rows_to_host(boxes, counts)]
 
     # ------------------------------------------------------------------ reference API
     def _load(self, input_path):

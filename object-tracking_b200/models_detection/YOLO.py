@@ -7,7 +7,7 @@ META, CONFIG, WEIGHTS, gpu_id, cpu_mode``, ``get_layer_dims(n) -> (h,w,c)``, ``d
 ``extract_spatio_info(frame, layer) -> (detections of config classes, feature)``.
 Darknet semantics (BN 1/(sqrt(var)+1e-6), reorg ordering, per-anchor softmax, objectness NMS) are selected
 with ``semantics="darknet"`` in the engine.  ``image`` may be a path or an HWC uint8 RGB array; frames that
-are not net-sized are resized on the host (darknet's own letterbox ingest is listed as next in SURVEY 8f).
+are not net-sized go through darknet's letterbox ingest on the device (engine.letterbox_frames).
 """
 from __future__ import annotations
 
@@ -17,8 +17,8 @@ from typing import List, Optional, Tuple
 import numpy as np
 import torch
 
-from ..engine import DetectorEngine
-from ..weights import ANCHORS, synthetic_yolo_weights
+from ..engine import DetectorEngine, rows_to_host
+from ..weights import ANCHORS, synthetic_detector_weights
 from ._common import COCO_NAMES, load_config, load_frame
 
 # darknet cfg/yolov2.cfg layer index -> tensor name kept by the engine
@@ -71,7 +71,7 @@ class YOLO:
             self.engine.load_darknet_weights(wpath)
             self.synthetic_weights = False
         else:                                   # the reference ships no weights: random init
-            self.engine.set_weights(synthetic_yolo_weights(self.n_class, seed=0))
+            self.engine.set_weights(synthetic_detector_weights(self.n_class, seed=0))
             self.synthetic_weights = True
         if not (self._broadcast and self._rank != 0):
             self.engine.finalize()
@@ -105,13 +105,21 @@ class YOLO:
 
     # ------------------------------------------------------------------ reference API
     def detect(self, image):
+        """YOLO.py:140-162.  ``image``: a path (decoded on the host; load_image_color gives RGB, so cv2's BGR is
+        swapped) or an HWC uint8 RGB array.  Ingest follows the reference: network_predict_image letterboxes the
+        frame to the net size (image.c:960-979, device kernel) and get_network_boxes(w, h) un-maps the boxes to
+        pixels of the original frame (correct_region_boxes, region_layer.c:336-362)."""
+        is_path = isinstance(image, str)
         frame = load_frame(image)
         h, w = frame.shape[:2]
-        net_in = load_frame(frame, self.image_size)
-        t = torch.from_numpy(np.ascontiguousarray(net_in[None])).to(self.engine.device)
+        t = torch.from_numpy(np.ascontiguousarray(frame[None])).to(self.engine.device)
+        if (h, w) == (self.image_size, self.image_size):
+            if is_path:
+                t = t.flip(-1).contiguous()                      # BGR -> RGB; letterbox of a net-sized frame is the identity
+        else:
+            t = self.engine.letterbox_frames(t, bgr=is_path)
         dets, counts = self.detect_batch(t, w, h)
-        n = int(counts.cpu()[0])
-        rows = dets[0, :n].cpu().numpy()
+        rows = rows_to_host(dets, counts)[0]
         return [(self.names[int(r[6])], float(r[5]), (float(r[0]), float(r[1]), float(r[2]), float(r[3]))) for r in rows]
 
     def extract(self, n):

@@ -9,6 +9,7 @@ from typing import List, Optional
 import numpy as np
 import torch
 
+from ..engine import rows_to_host
 from ..models_detection.KerasYOLO import KerasYOLO
 from ..models_detection._common import load_frame
 from ..utility.utils import BoundBox, boxes_from_rows, draw_boxes
@@ -75,9 +76,7 @@ class MultiObjDetTracker:
         out = []
         for lg in (trk_logits, det_logits):
             boxes, counts = eng.decode(lg, self.OBJ_THRESHOLD, self.NMS_THRESHOLD, self.ANCHORS)
-            counts = counts.cpu().numpy()
-            rows = boxes.cpu().numpy()
-            out.append([boxes_from_rows(rows[i, :int(counts[i])], self.CLASS) for i in range(T)])
+            out.append([boxes_from_rows(r, self.CLASS) for r in rows_to_host(boxes, counts)])
         return out[0], out[1]
 
     def predict(self, input_paths, output_paths):

@@ -121,10 +121,8 @@ def decode_netout(netout, obj_threshold, nms_threshold, anchors, nb_class, engin
     if t.shape[-1] != 5 + nb_class:
         raise ValueError(f"netout last dim {t.shape[-1]} != 5 + nb_class ({5 + nb_class})")
     boxes, counts = eng.decode(t[None], float(obj_threshold), float(nms_threshold), list(anchors))
-    n = int(counts.cpu()[0])
-    if n < 0:
-        raise RuntimeError("decode_netout: more candidates than the device kernel's capacity (threshold too low)")
-    return boxes_from_rows(boxes[0, :n].cpu().numpy(), nb_class)
+    from ..engine import rows_to_host
+    return boxes_from_rows(rows_to_host(boxes, counts)[0], nb_class)
 
 
 def generate_heatmap_feat(det_x, det_y, det_w, det_h, hmap_size=32):

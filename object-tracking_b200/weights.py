@@ -99,7 +99,8 @@ def forward_bytes(n_class: int = 80, image_size: int = 416, batch: int = 1, elem
 # --------------------------------------------------------------------------------------
 
 def synthetic_yolo_weights(n_class: int = 80, seed: int = 0, head_obj_bias: float = -2.0,
-                           head_gains=(0.13, 0.05, 0.40, 0.80)) -> Dict[str, np.ndarray]:
+                           head_gains=(0.13, 0.05, 0.40, 0.80),
+                           class_bias: Optional[Dict[int, float]] = None) -> Dict[str, np.ndarray]:
     """Random-init weights of the KerasYOLO architecture, Keras layouts.
 
     kernel_k : (kh, kw, Cin, Cout) float32   gamma_k/beta_k/mean_k/var_k : (Cout,)   bias_23 : (Cout,)
@@ -107,6 +108,9 @@ def synthetic_yolo_weights(n_class: int = 80, seed: int = 0, head_obj_bias: floa
     scaled per entry type (``head_gains`` = xy, wh, objectness, class; conv_feat has rms ~7 on
     random frames) and the objectness bias shifted so that t_xy ~ N(0,1), t_wh ~ N(0,0.4) and a few
     dozen anchors pass the 0.5 threshold on random frames.
+    ``class_bias`` {class index: offset} is added to those classes' conv_23 bias for every anchor ("planted"
+    classes: a random head emits the same few classes on every random frame, none of them the tracker's
+    allowed ones -- see ``synthetic_detector_weights``).
     """
     rng = np.random.default_rng(seed)
     w: Dict[str, np.ndarray] = {}
@@ -130,8 +134,23 @@ def synthetic_yolo_weights(n_class: int = 80, seed: int = 0, head_obj_bias: floa
             b = (0.1 * rng.standard_normal(s.cout)).astype(np.float32)
             d = 5 + n_class
             b.reshape(N_BOX, d)[:, 4] += np.float32(head_obj_bias)
+            for c, off in (class_bias or {}).items():
+                b.reshape(N_BOX, d)[:, 5 + int(c)] += np.float32(off)
             w[f"bias_{s.index}"] = b
     return w
+
+
+PLANTED_CLASS_BIAS = {0: 10.0, 2: 9.0}     # COCO "person", "car" = config.json train.classes (config.json:39)
+
+
+def synthetic_detector_weights(n_class: int = 80, seed: int = 0) -> Dict[str, np.ndarray]:
+    """The random-init detector the YOLO plugin, bench.py and the tracker tests share when no
+    ``darknet/yolov2.weights`` exists: ``synthetic_yolo_weights`` with the tracker's allowed classes planted, so
+    that on random frames most (not all) frames carry person / car detections, several per frame -- the
+    detection choice of utility/preprocessing.py:434-449 (class filter, top probability, zeros if none) is then
+    exercised on both branches."""
+    bias = {c: v for c, v in PLANTED_CLASS_BIAS.items() if c < n_class} if n_class >= 80 else None
+    return synthetic_yolo_weights(n_class, seed=seed, class_bias=bias)
 
 
 # --------------------------------------------------------------------------------------

@@ -31,3 +31,20 @@ def decode_case(seed, g, c, kind):
     return net
 
 
+def heatmap_case_inputs(n: int, seed: int):
+    """Seeded (x, y, w, h) rows as preprocessing.py:452-456 forms them (top-left corner, may be negative or past
+    the frame) and thresholded-noise heat-maps for the read-back."""
+    rng = np.random.default_rng(seed)
+    xywh = rng.uniform(-0.3, 1.2, (n, 4))
+    xywh[:, 2:] = np.abs(rng.uniform(0, 0.9, (n, 2)))
+    xywh[0] = 0.0                                       # the "no detection" row (preprocessing.py:445-449)
+    xywh[1] = (0.5, 0.5, 0.0, 0.0)
+    xywh[2] = (0.999, 0.999, 0.5, 0.5)
+    xywh[3] = (-0.01, -0.01, 0.1, 0.1)                  # int() truncates toward zero: -0.32 -> 0
+    xywh[4] = (-0.5, 0.2, 0.3, 0.3)                     # negative slice start wraps once in numpy
+    heat = rng.uniform(0, 1, (n, 32, 32)) * (rng.uniform(0, 1, (n, 1, 1)) ** 2 + 0.6)
+    heat[0] = 0.0                                       # nothing >= thresh -> (32, 32, -1, -1)
+    heat[1] = 1.0
+    # float32-representable values: the device entry points take float32 rows and the python int() truncation must
+    # see the same numbers
+    return xywh.astype(np.float32).astype(np.float64), heat.astype(np.float32).astype(np.float64)

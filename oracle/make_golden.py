@@ -13,6 +13,8 @@ What is produced (all small, committed):
                        fv_layer 25 feature (max-pooled), post-NMS detections
   keras_416_c2.npz     fp64 oracle outputs for the Keras-semantics graph (C=2; regression vector)
   tracker_cases.npz    fp64 oracle outputs of the LSTM / heat-map / ConvLSTM steps
+  heatmap_cases.npz    outputs of the reference's OWN generate_heatmap_feat / generate_rectangle_from_heatmap
+                       (utility/utils.py:53-79 exec'd from /root/reference) on seeded boxes / heat-maps
 """
 from __future__ import annotations
 
@@ -29,7 +31,7 @@ REF = "/root/reference"
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 from oracle import decode_oracle, yolo_oracle, tracker_oracle, darknet_ref  # noqa: E402
-from oracle.cases import decode_case, DECODE_KINDS, DECODE_SPECS  # noqa: E402
+from oracle.cases import decode_case, heatmap_case_inputs, DECODE_KINDS, DECODE_SPECS  # noqa: E402
 
 pkg = importlib.import_module("object-tracking_b200")
 W = importlib.import_module("object-tracking_b200.weights")
@@ -164,6 +166,37 @@ def make_tracker_golden():
     print(f"[tracker] {len(out)} arrays written")
 
 
+def load_reference_heatmap():
+    """exec utility/utils.py:53-79 (generate_heatmap_feat, generate_rectangle_from_heatmap): plain numpy, no
+    py2-only syntax on those lines."""
+    src = open(os.path.join(REF, "utility", "utils.py")).read().split("\n")
+    ns = {"np": np}
+    exec(compile("\n".join(src[52:79]), "reference:utility/utils.py", "exec"), ns)
+    return ns["generate_heatmap_feat"], ns["generate_rectangle_from_heatmap"]
+
+
+def make_heatmap_golden():
+    ref_feat, ref_rect = load_reference_heatmap()
+    bad = 0
+    xywh, heat = heatmap_case_inputs(3000, 20250)
+    for i in range(3000):
+        a = ref_feat(*xywh[i], hmap_size=32)
+        b = tracker_oracle.generate_heatmap_feat(*xywh[i], hmap_size=32)
+        bad += int(not np.array_equal(a, b))
+        ra = tuple(int(v) for v in ref_rect(heat[i], 0.75, 32))
+        rb = tuple(int(v) for v in tracker_oracle.generate_rectangle_from_heatmap(heat[i], 0.75, 32))
+        bad += int(ra != rb)
+    assert bad == 0, f"heat-map oracle differs from the reference in {bad} cases"
+    n = 96
+    xywh, heat = heatmap_case_inputs(n, 777)
+    feats = np.stack([ref_feat(*xywh[i], hmap_size=32) for i in range(n)])
+    rects = np.array([ref_rect(heat[i], 0.75, 32) for i in range(n)], dtype=np.int32)
+    rects_of_feats = np.array([ref_rect(feats[i].reshape(32, 32), 0.75, 32) for i in range(n)], dtype=np.int32)
+    np.savez_compressed(os.path.join(GOLD, "heatmap_cases.npz"), seed=np.array(777), n=np.array(n),
+                        feat_bits=np.packbits(feats.astype(np.uint8), axis=1), rect=rects, rect_of_feat=rects_of_feats)
+    print(f"[heatmap] oracle == reference utils.py:53-79 on 3000 cases; {n} reference outputs written")
+
+
 def make_resize_golden():
     """Outputs of the installed OpenCV's cv2.resize (the reference's ingest step, KerasYOLO.py:526) on seeded images."""
     import cv2
@@ -187,7 +220,7 @@ def make_resize_golden():
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    what = sys.argv[1:] or ["decode", "darknet", "keras", "tracker", "resize"]
+    what = sys.argv[1:] or ["decode", "darknet", "keras", "tracker", "resize", "heatmap"]
     if "decode" in what:
         make_decode_goldens()
     if "darknet" in what:
@@ -198,3 +231,5 @@ if __name__ == "__main__":
         make_tracker_golden()
     if "resize" in what:
         make_resize_golden()
+    if "heatmap" in what:
+        make_heatmap_golden()

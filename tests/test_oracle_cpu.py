@@ -138,3 +138,97 @@ def test_ingest_oracle_matches_cv2_resize_goldens():
     img = np.random.default_rng(3).integers(0, 256, (211, 333, 3), dtype=np.uint8)
     for dst in (416, 608):
         assert np.array_equal(ingest_oracle.resize_linear_u8(img, dst, dst), cv2.resize(img, (dst, dst)))
+
+
+def test_heatmap_oracle_matches_reference_outputs():
+    """Committed outputs of the REFERENCE's generate_heatmap_feat / generate_rectangle_from_heatmap
+    (utility/utils.py:53-79 exec'd from /root/reference by oracle/make_golden.py), not of our restatement."""
+    from oracle.cases import heatmap_case_inputs
+    z = np.load(os.path.join(GOLD, "heatmap_cases.npz"))
+    n = int(z["n"])
+    xywh, heat = heatmap_case_inputs(n, int(z["seed"]))
+    feats = np.unpackbits(z["feat_bits"], axis=1)[:, :1024]
+    for i in range(n):
+        got = tracker_oracle.generate_heatmap_feat(*xywh[i], hmap_size=32)
+        assert np.array_equal(got, feats[i].astype(np.float64)), i
+        assert tracker_oracle.generate_rectangle_from_heatmap(heat[i], 0.75, 32) == tuple(int(v) for v in z["rect"][i]), i
+        assert tracker_oracle.generate_rectangle_from_heatmap(feats[i], 0.75, 32) == tuple(int(v) for v in z["rect_of_feat"][i]), i
+    assert feats.sum() > 1000 and (z["rect"][:, 2] >= 0).sum() > n // 2
+
+
+def test_lstm_oracle_matches_torch_lstmcell():
+    """Independent pin of the LSTM restatement's gate order (i, f, c, o), weight layout (kernel (n_in,4u) =
+    weight_ih^T, recurrent_kernel (u,4u) = weight_hh^T) and state update: torch.nn.LSTMCell computes the same
+    cell with sigmoid gates (Keras >= 2.3's recurrent_activation); the hard_sigmoid of Keras 2.0-2.2 differs only
+    in the gate non-linearity, checked separately against its definition."""
+    import torch
+    n_in, u, S = 37, 16, 5
+    w = W.synthetic_lstm_weights(n_in, u, 4, seed=9)
+    cell = torch.nn.LSTMCell(n_in, u).double()
+    with torch.no_grad():
+        cell.weight_ih.copy_(torch.from_numpy(w["kernel"].T.astype(np.float64)))
+        cell.weight_hh.copy_(torch.from_numpy(w["recurrent_kernel"].T.astype(np.float64)))
+        cell.bias_ih.copy_(torch.from_numpy(w["bias"].astype(np.float64)))
+        cell.bias_hh.zero_()
+    rng = np.random.default_rng(4)
+    h = np.zeros((S, u)); c = np.zeros((S, u))
+    ht, ct = torch.zeros(S, u, dtype=torch.float64), torch.zeros(S, u, dtype=torch.float64)
+    w64 = {k: v.astype(np.float64) for k, v in w.items()}
+    for _ in range(6):
+        x = rng.standard_normal((S, n_in))
+        h, c = tracker_oracle.lstm_step(x, h, c, w64, recurrent_activation=tracker_oracle.sigmoid)
+        with torch.no_grad():
+            ht, ct = cell(torch.from_numpy(x), (ht, ct))
+        assert np.abs(h - ht.numpy()).max() < 1e-12 and np.abs(c - ct.numpy()).max() < 1e-12
+    x = np.linspace(-4, 4, 33)
+    assert np.array_equal(tracker_oracle.hard_sigmoid(x), np.clip(0.2 * x + 0.5, 0, 1))
+    assert tracker_oracle.hard_sigmoid(np.array([-2.5, 0.0, 2.5])).tolist() == [0.0, 0.5, 1.0]
+
+
+def test_convlstm_oracle_matches_torch_reference():
+    """ConvLSTM2D restatement against an independent torch composition (conv2d with 'same' padding on NCHW
+    tensors, gate slices i,f,c,o) -- checks the HWIO->OIHW kernel handling and the state update."""
+    import torch
+    import torch.nn.functional as F
+    G, cin, u = 5, 7, 4
+    w = W.synthetic_convlstm_weights(cin, u, 6, seed=5)
+    rng = np.random.default_rng(1)
+    h = np.zeros((G, G, u)); c = np.zeros((G, G, u))
+    ht = torch.zeros(1, u, G, G, dtype=torch.float64); ct = torch.zeros(1, u, G, G, dtype=torch.float64)
+    k = torch.from_numpy(w["kernel"].astype(np.float64)).permute(3, 2, 0, 1)
+    r = torch.from_numpy(w["recurrent_kernel"].astype(np.float64)).permute(3, 2, 0, 1)
+    b = torch.from_numpy(w["bias"].astype(np.float64))
+    w64 = {kk: v.astype(np.float64) for kk, v in w.items()}
+    for _ in range(3):
+        z = rng.standard_normal((G, G, cin))
+        h, c = tracker_oracle.convlstm_step(z, h, c, w64)
+        zt = torch.from_numpy(z).permute(2, 0, 1)[None]
+        g = F.conv2d(zt, k, b, padding=1) + F.conv2d(ht, r, padding=1)
+        hs = lambda t: torch.clamp(0.2 * t + 0.5, 0, 1)
+        i, f, o = hs(g[:, :u]), hs(g[:, u:2 * u]), hs(g[:, 3 * u:])
+        ct = f * ct + i * torch.tanh(g[:, 2 * u:3 * u])
+        ht = o * torch.tanh(ct)
+        assert np.abs(h - ht[0].permute(1, 2, 0).numpy()).max() < 1e-12
+
+
+def test_detection_to_tracker_input_spec():
+    """preprocessing.py:434-456: the first (highest-probability) detection of the class-filtered list, normalised by
+    the frame size; zeros when the list is empty; heat-map variant takes the top-left corner."""
+    lst = [("car", 0.9, (208.0, 104.0, 41.6, 83.2)), ("person", 0.8, (10.0, 10.0, 5.0, 5.0))]
+    v = tracker_oracle.detection_to_tracker_input(lst, 416, 208)
+    assert np.allclose(v, [0.5, 0.5, 0.1, 0.4]) and v.dtype == np.float32
+    assert np.array_equal(tracker_oracle.detection_to_tracker_input([], 416, 208), np.zeros(4, np.float32))
+    hm = tracker_oracle.detection_to_tracker_input(lst, 416, 208, heatmap_size=32).reshape(32, 32)
+    assert hm.sum() == (int(0.1 * 32) + 1) * (int(0.4 * 32) + 1) and hm[int(0.3 * 32), int(0.45 * 32)] == 1
+    assert tracker_oracle.detection_to_tracker_input([], 416, 208, heatmap_size=32).sum() == 1    # the (0,0) cell
+
+
+def test_planted_synthetic_detector_emits_allowed_classes():
+    """weights.synthetic_detector_weights: the tracker's allowed classes (person, car) are planted in the random head
+    so that the positive branch of the detection choice is exercised (it never was)."""
+    a, b = W.synthetic_yolo_weights(80, seed=0), W.synthetic_detector_weights(80, seed=0)
+    for k in a:
+        if k != "bias_23":
+            assert np.array_equal(a[k], b[k]), k
+    d = (b["bias_23"] - a["bias_23"]).reshape(5, 85)
+    assert np.allclose(d[:, 5], 10.0) and np.allclose(d[:, 7], 9.0) and np.count_nonzero(d) == 10
