@@ -41,11 +41,14 @@ N_CLASS, IMAGE, SEQ, CLIP = 80, 416, 4, 300
 
 
 def measured_peaks():
+    """MEASURED_PEAKS.json (driver-written) or the fallback figures of B200_PROFILING.md."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
-    return 6650.0, 1590.0, "fallback"
+        burst = d.get("bf16_tflops", 1590.0)
+        return {"hbm": d.get("hbm_gbs", 6650.0), "tflops_burst": burst,
+                "tflops_sustained": d.get("bf16_tflops_sustained", burst), "source": "measured"}
+    return {"hbm": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1590.0, "source": "fallback"}
 
 
 class ClockSampler:
@@ -103,12 +106,54 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
+TRACKER_CFG = {"model_detector": {"name": "YOLO", "config_file": "cfg/yolov2.cfg", "meta_file": "cfg/coco.data",
+                                  "weights_file": "yolov2.weights", "fv_layer": 25, "nms": 0.45, "thresh": 0.5,
+                                  "hier_thresh": 0.5},
+               "model_tracker": {"name": "TinyTracker", "lstm_units": 512, "sequence_length": SEQ, "heatmap_size": 32},
+               "train": {"cpu_only": 0, "dgpu_id": 0, "tgpu_id": 0, "pool": "Global", "batch_size": 4, "max_epochs": 0,
+                         "tensorboard_dir": "logs/", "saved_model_dir": "models/", "classes": ["Person", "Car"]}}
+
+# BASELINE.json configs -> (plugin class, classes, image size, streams/windows per step, frames per window)
+WORKLOADS = {
+    # configs[1]: the headline.  9 independent 4-frame windows of the stream's clip per step (see module docstring)
+    "tiny": dict(cls="TinyTracker", n_class=80, image=416, S=9, T=4,
+                 what="TinyTracker YOLOv2-416 C=80 (darknet semantics) + LSTM(512), 1 stream/window per GPU x %d, "
+                      "synthetic 300-frame clip"),
+    # configs[1] literally: one stream, frame by frame (batch 1 per step, LSTM state carried, reset every 4 frames)
+    "c2": dict(cls="TinyTracker", n_class=80, image=416, S=1, T=1,
+               what="TinyTracker YOLOv2-416 C=80 + LSTM(512), %d stream, ONE frame per step (online latency regime)"),
+    # configs[3]: 32 streams over 8 GPUs = 4 streams per GPU advancing frame by frame (batch 4 per step)
+    "c4": dict(cls="TinyTracker", n_class=80, image=416, S=4, T=1,
+               what="TinyTracker YOLOv2-416 C=80 + LSTM(512), %d streams per GPU, one frame of each per step"),
+    # configs[2]: MultiObjDetTracker, 20 classes, ConvLSTM2D(512) + 1x1 head + decode_netout of the tracker output
+    "multiobj": dict(cls="MultiObjDetTracker", n_class=20, image=416, S=9, T=4,
+                     what="MultiObjDetTracker YOLOv2-416 C=20 (Keras semantics) + ConvLSTM2D(512) + 1x1 head + "
+                          "decode/NMS, %d windows of 4 frames per step, synthetic MOT17-shaped clip"),
+    # configs[4]: YOLOv2-608 80 classes + TinyHeatmapTracker, 8 streams per GPU advancing frame by frame
+    "c5": dict(cls="TinyHeatmapTracker", n_class=80, image=608, S=8, T=1,
+               what="TinyHeatmapTracker YOLOv2-608 C=80 + LSTM(512) heat-map head, %d streams per GPU, one frame of "
+                    "each per step"),
+}
+
+
+
 # ------------------------------------------------------------------------------------------------ reference arm
-def reference_runner():
+def workload_config(name: str, S: int, world: int) -> dict:
+    """`config` of the JSON line -- the same object for the B200 arm and the reference arm."""
+    spec = WORKLOADS[name]
+    T = spec["T"]
+    return {"workload": spec["what"] % S, "frames_per_step": S * T, "window": T, "windows_per_step": S,
+            "l2": "the packed weights (>= 204 MB) are streamed every step and the inputs cycle through a clip; both "
+                  "exceed the 126 MB L2; no explicit flush",
+            "weights": "random-init (reference ships none), seed 0", "parallelism": f"streams x{world}"}
+
+
+def reference_runner(name: str = "tiny"):
     """The reference's own CPU implementation of the path: its darknet C library (oracle/_ref/libdarknet.so,
     compiled from /root/reference/darknet/src by oracle/Makefile) driven through the ctypes call sequence of
     models_detection/YOLO.py:140-170, + the numpy LSTM step (Keras is not installable here).  Falls back to
-    the oracle port (torch-CPU forward) when the .so did not travel."""
+    the oracle port (torch-CPU forward) when the .so did not travel; MultiObjDetTracker (a Keras-only model) always
+    runs as the oracle port: torch-CPU fp32 forward + numpy ConvLSTM2D + the decode restatement."""
     # all host threads, also under torchrun (it exports OMP_NUM_THREADS=1 for every rank)
     os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())
     try:
@@ -116,70 +161,80 @@ def reference_runner():
         ctypes.CDLL("libgomp.so.1").omp_set_num_threads(os.cpu_count())
     except OSError:
         pass
+    import torch
+    torch.set_num_threads(os.cpu_count())
     from object_tracking_b200 import weights as W
-    from oracle import darknet_ref, tracker_oracle, yolo_oracle
-    w = W.synthetic_detector_weights(N_CLASS, seed=0)
-    wl = {k: v.astype(np.float32) for k, v in W.synthetic_lstm_weights(1024 + 4, 512, 4, seed=1).items()}
-    state = {"h": np.zeros((1, 512), np.float32), "c": np.zeros((1, 512), np.float32), "t": 0}
+    from oracle import darknet_ref, decode_oracle, tracker_oracle, yolo_oracle
+    spec = WORKLOADS[name]
+    C, IM = spec["n_class"], spec["image"]
+    G = IM // 32
 
-    def lstm(fv, det):
+    if spec["cls"] == "MultiObjDetTracker":
+        w = W.synthetic_yolo_weights(C, seed=0)
+        wl = W.synthetic_multiobj_weights(C, 512, seed=2)
+        st = {"h": np.zeros((G, G, 512), np.float32), "c": np.zeros((G, G, 512), np.float32), "t": 0}
+
+        def run(frame_u8):
+            x = (frame_u8[None].astype(np.float32) / np.float32(255.))
+            o = yolo_oracle.yolo_forward(x, w, C, dtype=np.float32)
+            if st["t"] % SEQ == 0:
+                st["h"][:] = 0; st["c"][:] = 0
+            st["t"] += 1
+            out, st["h"], st["c"] = tracker_oracle.multiobj_step(o["logits"][0].reshape(G, G, -1), o["feat"][0],
+                                                                 st["h"], st["c"], wl)
+            return decode_oracle.decode_netout(out.reshape(G, G, 5, 5 + C).astype(np.float32), 0.5, 0.45, W.ANCHORS, C)
+        return run, "port", "oracle port: torch-CPU fp32 forward + numpy ConvLSTM2D(512) + decode restatement"
+
+    heat = spec["cls"] == "TinyHeatmapTracker"
+    n_det, n_out = (1024, 1024) if heat else (4, 4)
+    w = W.synthetic_detector_weights(C, seed=0)
+    wl = {k: v.astype(np.float32) for k, v in W.synthetic_lstm_weights(1024 + n_det, 512, n_out, seed=1).items()}
+    state = {"h": np.zeros((1, 512), np.float32), "c": np.zeros((1, 512), np.float32), "t": 0}
+    allowed = [0, 2]                                            # person, car = config.json train.classes
+
+    def lstm(fv, boxes, prob):
+        """YOLO.py:177-180 + preprocessing.py:434-456: top-probability detection of an allowed class -> LSTM input"""
         if state["t"] % SEQ == 0:
             state["h"][:] = 0; state["c"][:] = 0
         state["t"] += 1
+        p = prob[:, allowed].max(1)
+        lst = [("x", float(p[j]), tuple(float(v) for v in boxes[j])) for j in np.argsort(-p, kind="stable") if p[j] > 0]
+        det = tracker_oracle.detection_to_tracker_input(lst, IM, IM, heatmap_size=32 if heat else None).astype(np.float32)
         y, state["h"], state["c"] = tracker_oracle.tracker_step(fv[None], det[None], state["h"], state["c"], wl)
         return y
 
     if darknet_ref.available():
         tmp = tempfile.mkdtemp()
         cfg, wpath = os.path.join(tmp, "yolov2.cfg"), os.path.join(tmp, "synthetic.weights")
-        darknet_ref.write_yolov2_cfg(cfg, N_CLASS, IMAGE)
-        W.write_darknet_weights(wpath, w, N_CLASS)
+        darknet_ref.write_yolov2_cfg(cfg, C, IM)
+        W.write_darknet_weights(wpath, w, C)
         net = darknet_ref.DarknetRef(cfg, wpath)
 
         def run(frame_u8):
             chw = np.ascontiguousarray(np.transpose(frame_u8.astype(np.float32) / np.float32(255.), (2, 0, 1)))
             net.predict(chw)
-            boxes, obj, prob = net.detect(IMAGE, IMAGE, 0.5, 0.5, 0.45, N_CLASS)
+            boxes, obj, prob = net.detect(IM, IM, 0.5, 0.5, 0.45, C)
             feat = net.extract(25).reshape(1024, -1).max(1)
-            live = np.nonzero(prob.max(1) > 0)[0]
-            det = np.zeros(4, np.float32)
-            if live.size:
-                j = live[np.argmax(prob[live].max(1))]
-                det = (boxes[j] / np.float32(IMAGE)).astype(np.float32)
-            return lstm(feat.astype(np.float32), det)
+            return lstm(feat.astype(np.float32), boxes, prob)
         return run, "reference", "libdarknet.so (reference C sources, -Ofast -fopenmp) + numpy LSTM step"
 
     from oracle import darknet_oracle
 
     def run(frame_u8):
         x = (frame_u8[None].astype(np.float32) / np.float32(255.))
-        o = yolo_oracle.yolo_forward(x, w, N_CLASS, dtype=np.float32, mode="darknet", want=["norm_20"])
-        logits = np.transpose(o["logits"].reshape(13, 13, -1), (2, 0, 1))
-        region = darknet_oracle.region_forward(logits, N_CLASS)
-        boxes, obj, prob = darknet_oracle.detect(region, IMAGE, IMAGE, IMAGE, IMAGE, 0.5, 0.45, N_CLASS)
-        live = np.nonzero(prob.max(1) > 0)[0]
-        det = np.zeros(4, np.float32)
-        if live.size:
-            j = live[np.argmax(prob[live].max(1))]
-            det = (boxes[j] / np.float32(IMAGE)).astype(np.float32)
-        return lstm(o["norm_20"][0].max(axis=(0, 1)).astype(np.float32), det)
+        o = yolo_oracle.yolo_forward(x, w, C, dtype=np.float32, mode="darknet", want=["norm_20"])
+        logits = np.transpose(o["logits"].reshape(G, G, -1), (2, 0, 1))
+        region = darknet_oracle.region_forward(logits, C)
+        boxes, obj, prob = darknet_oracle.detect(region, IM, IM, IM, IM, 0.5, 0.45, C)
+        return lstm(o["norm_20"][0].max(axis=(0, 1)).astype(np.float32), boxes, prob)
     return run, "port", "oracle port: torch-CPU fp32 forward + numpy region decode/NMS + numpy LSTM step"
 
 
-def workload_config(S: int, world: int) -> dict:
-    """`config` of the JSON line -- the same object for the B200 arm and the reference arm."""
-    return {"workload": "TinyTracker YOLOv2-416 C=80 (darknet semantics) + LSTM(512), 1 stream/window "
-                        "per GPU x %d, synthetic 300-frame clip" % S,
-            "frames_per_step": S * SEQ, "window": SEQ, "windows_per_step": S,
-            "l2": "inputs cycle through a 156 MB clip per stream and the 204 MB weight blob is streamed "
-                  "every step (both > 126 MB L2); no explicit flush",
-            "weights": "random-init (reference ships none), seed 0", "parallelism": f"streams x{world}"}
-
-
-def time_reference(steps: int, warmup: int):
-    run, kind, what = reference_runner()
+def time_reference(steps: int, warmup: int, name: str = "tiny"):
+    run, kind, what = reference_runner(name)
     rng = np.random.default_rng(1234)
-    frames = rng.integers(0, 256, (max(1, min(8, steps + warmup)), IMAGE, IMAGE, 3), dtype=np.uint8)
+    IM = WORKLOADS[name]["image"]
+    frames = rng.integers(0, 256, (max(1, min(8, steps + warmup)), IM, IM, 3), dtype=np.uint8)
     for i in range(warmup):
         run(frames[i % len(frames)])
     t0 = time.perf_counter()
@@ -193,14 +248,15 @@ def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    fps, dt, kind, what = time_reference(args.steps, args.warmup)
+    fps, dt, kind, what = time_reference(args.steps, args.warmup, args.workload)
     cores = os.cpu_count()
+    S = args.windows if args.windows > 0 else WORKLOADS[args.workload]["S"]
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(args.windows, max(1, args.gpus)),
+            "config": dict(workload_config(args.workload, S, max(1, args.gpus)),
                            reference_step="1 frame per step: a bounded sample of the %d-frame step, same frames/s metric"
-                                          % (args.windows * SEQ)),
+                                          % (S * WORKLOADS[args.workload]["T"])),
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": kind,
                              "sample": f"{args.steps} single frames after {args.warmup} warm-up; {what}"},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -209,11 +265,205 @@ def main_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
+def convlstm_traffic(n_class: int, units: int = 512, grid: int = 13):
+    """Algorithmic adders of MultiObjDetTracker's head per frame: ConvLSTM2D(units, 3x3) over
+    concat[logits, conv_feat] + the 1x1 head.  Returns (flops, weight elements, activation elements)."""
+    ad = 5 * (5 + n_class)
+    cz = ad + 1024
+    w_el = 9 * cz * 4 * units + 9 * units * 4 * units + 4 * units + units * ad + ad
+    px = grid * grid
+    flops = 2.0 * px * (9 * cz * 4 * units + 9 * units * 4 * units + units * ad)
+    act_el = px * (cz + units + 4 * units + units + ad)       # z and h read, gates written, h written, logits written
+    return flops, w_el, act_el
+
+
+class Runner:
+    """One BASELINE config on this rank: builds the plugin object, owns a device-resident synthetic clip and runs one
+    step (= S windows/streams x T frames through the plugin's batched call)."""
+
+    def __init__(self, name, S, rank, world, local, pipeline, clip_windows):
+        import torch
+        from object_tracking_b200 import weights as W
+        from object_tracking_b200.sharding import shard_streams
+        spec = WORKLOADS[name]
+        self.name, self.spec, self.S, self.T = name, spec, S, spec["T"]
+        self.image, self.n_class = spec["image"], spec["n_class"]
+        self.pipeline = pipeline and spec["cls"] != "MultiObjDetTracker"
+        cfg = {k: dict(v) for k, v in TRACKER_CFG.items()}
+        cfg["train"]["dgpu_id"] = cfg["train"]["tgpu_id"] = local
+        cfg["model_tracker"]["name"] = spec["cls"]
+        kw = {"broadcast": world > 1, "rank": rank, "image_size": self.image}
+        if spec["cls"] == "MultiObjDetTracker":
+            from object_tracking_b200.models_tracking.MultiObjDetTracker import MultiObjDetTracker
+            labels = [str(i) for i in range(self.n_class)]
+            self.obj = MultiObjDetTracker({"LABELS": labels}, device=local, max_streams=S)
+            self.eng = self.obj.model
+            if world > 1:
+                self.eng.broadcast_weights(src=0)               # same blob everywhere (the one collective)
+        else:
+            import importlib
+            mod = importlib.import_module("object_tracking_b200.models_tracking." + spec["cls"])
+            if self.T == 1:                                     # frame-by-frame streams: batch = S frames per step
+                kw["max_batch"] = S
+            self.obj = getattr(mod, spec["cls"])(cfg, max_streams=S, detector_kwargs=kw)
+            self.eng = self.obj.model_detector.engine
+        # synthetic clip(s): S streams x n_win windows of T frames, seeded per global stream id; pinned host + device copy
+        self.n_win = clip_windows
+        gids = list(shard_streams(world * S, rank, world))
+        L = self.n_win * self.T
+        self.host = torch.empty((S, L, self.image, self.image, 3), dtype=torch.uint8, pin_memory=True)
+        for s_local, gid in enumerate(gids):
+            rng = np.random.default_rng(1234 + gid)
+            self.host[s_local].numpy()[...] = rng.integers(0, 256, (L, self.image, self.image, 3), dtype=np.uint8)
+        self.dev = self.host.cuda(non_blocking=True)
+        torch.cuda.synchronize()
+        t = W.traffic_model(self.n_class, self.image)
+        B = S * self.T
+        self.flops_per_step = t["flops"] * B
+        self.bytes_per_step = 4.0 * (t["W"] + B * (t["R"] + t["Wr"]))
+        if spec["cls"] == "MultiObjDetTracker":
+            f, w_el, a_el = convlstm_traffic(self.n_class, 512, self.image // 32)
+            self.flops_per_step += f * B
+            self.bytes_per_step += 4.0 * (w_el + B * a_el)
+
+    def window(self, t, i):
+        j = (i % self.n_win) * self.T
+        return t[:, j:j + self.T]
+
+    def out_stream(self):
+        import torch
+        return self.obj.tail_stream if self.pipeline else torch.cuda.current_stream()
+
+    def step(self, frames, i):
+        """-> the (small) device tensor a caller reads back: tracker boxes / heat-maps of this step."""
+        if self.spec["cls"] == "MultiObjDetTracker":
+            _, boxes, counts = self.obj.track_windows(frames, reset=True, graph=True)
+            return boxes[:, :self.obj.MAX_BOX_PER_IMAGE], counts
+        reset = True if self.T > 1 else (i % SEQ == 0)          # T = 1: state carried, reset every SEQ frames
+        return (self.obj.track_windows(frames, reset=reset, pipeline=self.pipeline),)
+
+    def finish(self):
+        import torch
+        if self.pipeline and getattr(self.obj, "tail_done", None) is not None:
+            torch.cuda.current_stream().wait_event(self.obj.tail_done)
+
+    def config(self, world):
+        return workload_config(self.name, self.S, world)
+
+
+def timed_loop(r, steps, warmup, barrier):
+    """value leg: inputs resident in HBM, CUDA events on the launching stream.  -> (ms total, conv-stack ms / step, launches)"""
+    import torch
+    for i in range(warmup):
+        r.step(r.window(r.dev, i), i)
+    r.finish()
+    r.eng.forward_events = []
+    barrier()
+    l0 = r.eng.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        r.step(r.window(r.dev, warmup + i), warmup + i)
+    r.finish()                                                  # the last step's tail is inside the timed region
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    ev = r.eng.forward_events
+    fwd_ms = sum(a.elapsed_time(b) for a, b in ev) / max(1, len(ev))
+    r.eng.forward_events = None
+    return ms, fwd_ms, r.eng.launches - l0
+
+
+def e2e_loop(r, steps, warmup, barrier):
+    """e2e leg: through the plugin call with HOST buffers.  Every step's frames travel pinned host -> device inside the
+    timed region and every step's result is read back to the host.  The copy of step i+1 is issued on a second
+    stream while step i computes (double-buffered device staging); the host reads step i-1's result (async D2H
+    into pinned memory + event) while step i runs, and the last step's before the clock stops."""
+    import torch
+    S, T, IM = r.S, r.T, r.image
+    copy_stream = torch.cuda.Stream()
+    stage = [torch.empty((S, T, IM, IM, 3), dtype=torch.uint8, device="cuda") for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def upload(i, slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])              # the step that last used this slot is done
+            w = r.window(r.host, i)
+            for s in range(S):                                  # S contiguous pinned segments -> async DMA
+                stage[slot][s].copy_(w[s], non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    proto = r.step(r.window(r.dev, 0), 0)
+    r.finish()
+    torch.cuda.synchronize()
+    y_host = [[torch.empty(tuple(t.shape), dtype=t.dtype).pin_memory() for t in proto] for _ in range(2)]
+    d2h = sum(t.numel() * t.element_size() for t in proto)
+    y_done = [torch.cuda.Event(), torch.cuda.Event()]
+    for slot in range(2):
+        consumed[slot].record()
+
+    def run(i, slot):
+        torch.cuda.current_stream().wait_event(ready[slot])
+        ys = r.step(stage[slot], i)
+        consumed[slot].record()
+        with torch.cuda.stream(r.out_stream()):
+            for dst, src in zip(y_host[slot], ys):
+                dst.copy_(src, non_blocking=True)               # D2H of this step's result into pinned memory
+            y_done[slot].record()
+
+    for i in range(2):                                          # warm the path (graphs exist already)
+        upload(i, i & 1)
+        run(i, i & 1)
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    upload(warmup, 0)
+    checksum = 0.0
+    for i in range(steps):
+        slot = i & 1
+        if i + 1 < steps:
+            upload(warmup + i + 1, slot ^ 1)
+        run(warmup + i, slot)
+        if i:                                                   # the host reads step i-1's result while step i runs
+            y_done[slot ^ 1].synchronize()
+            checksum += float(y_host[slot ^ 1][0].flatten()[0])
+    y_done[(steps - 1) & 1].synchronize()
+    checksum += float(y_host[(steps - 1) & 1][0].flatten()[0])
+    r.finish()
+    barrier()
+    return (time.perf_counter() - t0) * 1e3, S * T * IM * IM * 3, d2h
+
+
+def roofline_block(r, fwd_ms, timed_ms, kernel_desc):
+    pk = measured_peaks()
+    # a kernel timed alone / in a short burst runs at boost clocks; inside a long step the chip is power-capped:
+    # the burst peak applies to timed regions under 2 s, the sustained one above (both fractions are printed)
+    peak = pk["tflops_sustained"] if timed_ms >= 2000.0 else pk["tflops_burst"]
+    ach = r.flops_per_step / (fwd_ms * 1e-3) / 1e12
+    gbs = r.bytes_per_step / (fwd_ms * 1e-3) / 1e9
+    return {"bound": "tensor", "kernel": kernel_desc, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+            "frac_burst": ach / pk["tflops_burst"], "frac_sustained": ach / pk["tflops_sustained"],
+            "peak_kind": "sustained (timed region >= 2 s)" if timed_ms >= 2000.0 else "burst (timed region < 2 s)",
+            "peak_source": pk["source"] + " (cuBLAS bf16)", "launch_ms": fwd_ms,
+            # dram__bytes_read+write summed over the conv kernels of one 36-frame launch of the headline workload,
+            # ncu --set full captures in profiles/ (null for the other workloads: not captured)
+            "traffic": TRAFFIC_NCU.get((r.name, r.S * r.T)),
+            "algorithmic_flops_per_launch": r.flops_per_step, "algorithmic_bytes_per_launch": r.bytes_per_step,
+            # parity (bbox within 1e-3) needs 3 fp16 MMAs per product (profiles/r2_precision_budget_cpu.txt: demoting
+            # ANY single layer to 2 terms costs 3e-3..7e-3 of logit error): the algorithmic fraction cannot exceed
+            # 1/3 of the tensor peak; frac_of_ceiling = issued MMA rate / peak
+            "issued_tflops": 3 * ach, "ceiling_frac": 1.0 / 3.0, "frac_of_ceiling": 3 * ach / peak,
+            # the HBM view BASELINE.json's metric names: algorithmic fp32-equivalent bytes / conv-stack time
+            "hbm_gbs": gbs, "hbm_peak_gbs": pk["hbm"], "hbm_frac": gbs / pk["hbm"]}
+
+
+TRAFFIC_NCU = {("tiny", 36): 2.140e9}
+
+
 def main_b200(args):
     import torch
     import torch.distributed as dist
-    from object_tracking_b200 import weights as W
-    from object_tracking_b200.models_tracking.TinyTracker import TinyTracker
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -223,155 +473,75 @@ def main_b200(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    S, T = args.windows, SEQ
-    cfg = {"model_detector": {"name": "YOLO", "config_file": "cfg/yolov2.cfg", "meta_file": "cfg/coco.data",
-                              "weights_file": "yolov2.weights", "fv_layer": 25, "nms": 0.45, "thresh": 0.5, "hier_thresh": 0.5},
-           "model_tracker": {"name": "TinyTracker", "lstm_units": 512, "sequence_length": T, "heatmap_size": 32},
-           "train": {"cpu_only": 0, "dgpu_id": local, "tgpu_id": local, "pool": "Global", "batch_size": 4, "max_epochs": 0,
-                     "tensorboard_dir": "logs/", "saved_model_dir": "models/", "classes": ["Person", "Car"]}}
-    trk = TinyTracker(cfg, max_streams=S, detector_kwargs={"broadcast": world > 1, "rank": rank})
-    eng = trk.model_detector.engine
-
-    # synthetic clip(s): S streams x 300 frames, seeded per global stream id; resident copy + pinned host copy
-    n_win = CLIP // T
-    from object_tracking_b200.sharding import shard_streams
-    gids = list(shard_streams(world * S, rank, world))         # global stream ids owned by this rank
-    host = torch.empty((len(gids), CLIP, IMAGE, IMAGE, 3), dtype=torch.uint8, pin_memory=True)   # (S, 300, H, W, 3)
-    for s_local, gid in enumerate(gids):                       # filled stream by stream: no second host copy
-        rng = np.random.default_rng(1234 + gid)
-        host[s_local].numpy()[...] = rng.integers(0, 256, (CLIP, IMAGE, IMAGE, 3), dtype=np.uint8)
-    dev = host.cuda(non_blocking=True)
-    torch.cuda.synchronize()
-
-    def window(t, i):          # (S, T, H, W, 3) view of window i
-        return t[:, (i % n_win) * T:(i % n_win) * T + T]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- value: inputs resident in HBM
+    spec = WORKLOADS[args.workload]
+    S = args.windows if args.windows > 0 else spec["S"]
+    PIPE = not args.no_pipeline          # tracker tail of step i overlaps conv_1..8 of step i+1 (BaseTracker.track_windows)
+    r = Runner(args.workload, S, rank, world, local, PIPE, clip_windows=(CLIP // spec["T"] if spec["T"] > 1 else 64))
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    PIPE = not args.no_pipeline          # tracker tail of step i overlaps conv_1..8 of step i+1 (BaseTracker.track_windows)
-    for i in range(args.warmup):
-        trk.track_windows(window(dev, i), pipeline=PIPE)
-    eng.forward_events = []
-    barrier()
+    for i in range(2):                                          # graphs are captured before the sampler window opens
+        r.step(r.window(r.dev, i), i)
+    r.finish()
     sampler.mark_start()
-    l0 = eng.launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        out = trk.track_windows(window(dev, args.warmup + i), pipeline=PIPE)
-    if PIPE:
-        torch.cuda.current_stream().wait_event(trk.tail_done)       # the last step's tail is inside the timed region
-    e1.record()
-    barrier()
+    ms, fwd_ms, launches = timed_loop(r, args.steps, args.warmup, barrier)
     sampler.mark_end()
-    launches = eng.launches - l0
-    ms = e0.elapsed_time(e1)
-    fwd_ms = sum(a.elapsed_time(b) for a, b in eng.forward_events) / max(1, len(eng.forward_events))
-    eng.forward_events = None
     clocks = sampler.stop() if rank == 0 else None
+    e2e_ms, h2d, d2h = e2e_loop(r, args.steps, args.warmup, barrier)
 
-    # ---- e2e: through the plugin call (TinyTracker.track_windows) with HOST buffers: every step's frames travel
-    # pinned host -> device inside the timed region and every step's result is read back to the host.  The copy of
-    # step i+1 is issued on a second stream while step i computes (double-buffered device staging); the host reads
-    # step i-1's boxes (async D2H into pinned memory + event) while step i runs, and the last step's before the clock stops.
-    copy_stream = torch.cuda.Stream()
-    stage = [torch.empty((S, T, IMAGE, IMAGE, 3), dtype=torch.uint8, device="cuda") for _ in range(2)]
-    ready = [torch.cuda.Event(), torch.cuda.Event()]
-    consumed = [torch.cuda.Event(), torch.cuda.Event()]
-
-    def upload(i, slot):
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[slot])                  # the step that last used this slot is done
-            w = window(host, i)
-            for s in range(S):                                      # S contiguous 2 MB pinned segments -> async DMA
-                stage[slot][s].copy_(w[s], non_blocking=True)
-            ready[slot].record(copy_stream)
-
-    y_host = [torch.empty((S, T, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
-    y_done = [torch.cuda.Event(), torch.cuda.Event()]
-    for slot in range(2):
-        consumed[slot].record()
-    for i in range(2):                                              # warm the path (graphs exist already)
-        upload(i, i & 1)
-        torch.cuda.current_stream().wait_event(ready[i & 1])
-        y = trk.track_windows(stage[i & 1], pipeline=PIPE)
-        consumed[i & 1].record()
-        with torch.cuda.stream(trk.tail_stream if PIPE else torch.cuda.current_stream()):
-            y_host[i & 1].copy_(y)
-    barrier()
-    t0 = time.perf_counter()
-    upload(args.warmup, 0)
-    checksum = 0.0
-    for i in range(args.steps):
-        slot = i & 1
-        if i + 1 < args.steps:
-            upload(args.warmup + i + 1, slot ^ 1)
-        torch.cuda.current_stream().wait_event(ready[slot])
-        y = trk.track_windows(stage[slot], pipeline=PIPE)
-        consumed[slot].record()
-        with torch.cuda.stream(trk.tail_stream if PIPE else torch.cuda.current_stream()):
-            y_host[slot].copy_(y, non_blocking=True)                # D2H of this step's boxes into pinned memory
-            y_done[slot].record()
-        if i:                                                       # the host reads step i-1's boxes while step i runs
-            y_done[slot ^ 1].synchronize()
-            checksum += float(y_host[slot ^ 1][0, 0, 0])
-    y_done[(args.steps - 1) & 1].synchronize()
-    checksum += float(y_host[(args.steps - 1) & 1][0, 0, 0])
-    barrier()
-    e2e_s = time.perf_counter() - t0
-
-    t_ms = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    t_ms = torch.tensor([ms, e2e_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms, e2e_ms = float(t_ms[0]), float(t_ms[1])
-    frames_per_step = S * T
+    frames_per_step = S * r.T
     total_frames = world * args.steps * frames_per_step
 
     if rank == 0:
-        hbm, tflops, src = measured_peaks()
-        B = frames_per_step
-        bytes_per_fwd = W.forward_bytes(N_CLASS, IMAGE, batch=B) * B       # algorithmic, fp32-equivalent 4 B/elem
-        flops_per_fwd = W.traffic_model(N_CLASS, IMAGE)["flops"] * B
-        ach = bytes_per_fwd / (fwd_ms * 1e-3) / 1e9
         line = {"metric": METRIC, "value": total_frames / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f16x2-split operands, f32 accumulate", "data": "synthetic",
-                "config": dict(workload_config(S, world),
+                "config": dict(r.config(world),
                                pipeline="tracker tail of step i on a second stream under conv_1..8 of step i+1"
-                               if PIPE else "serial"),
-                "e2e": {"value": total_frames / (e2e_ms * 1e-3), "unit": UNIT,
-                        "h2d_bytes_per_step": frames_per_step * IMAGE * IMAGE * 3,
-                        "d2h_bytes_per_step": frames_per_step * 4 * 4},
-                "gpu_launches": int(launches),
-                "clocks": clocks,
+                               if r.pipeline else "serial"),
+                "e2e": {"value": total_frames / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h,
+                        "note": "value is not an upper bound on e2e: the host syncs of the e2e loop give the power-capped "
+                                "chip short idle gaps, so its kernels run at slightly higher clocks"},
+                "gpu_launches": int(launches), "clocks": clocks,
                 # The conv stack is tensor-bound, not HBM-bound: parity needs 3 fp16 MMAs per product (DESIGN.md
                 # section 4), so its tensor floor (3*flops / peak) is above its HBM floor at every batch size.
-                # `achieved` = ALGORITHMIC flops (1x) / measured time; the HBM view is kept beside it.
-                "roofline": {"bound": "tensor", "kernel": "YOLOv2 conv stack = frames_to_c8 + 3x conv_pm_kernel + 20x conv_halo_*"
-                                                          "kernel (+ split-K epilogues), one CUDA-graph launch per step",
-                             "achieved": flops_per_fwd / (fwd_ms * 1e-3) / 1e12, "peak": tflops, "unit": "TFLOP/s",
-                             "frac": flops_per_fwd / (fwd_ms * 1e-3) / 1e12 / tflops,
-                             # dram__bytes_read+write summed over the stack's 23 conv kernels of one 36-frame launch,
-                             # ncu --set full capture in profiles/ (split-K epilogues and the u8->fp16 copy not included)
-                             "traffic": 2.140e9 if B == 36 else None,
-                             "peak_source": src + " (cuBLAS bf16, sustained)", "launch_ms": fwd_ms,
-                             "algorithmic_flops_per_launch": flops_per_fwd,
-                             "issued_tflops": 3 * flops_per_fwd / (fwd_ms * 1e-3) / 1e12,
-                             # parity (bbox within 1e-3) needs 3 fp16 MMAs per product: the algorithmic fraction cannot
-                             # exceed 1/3 of the tensor peak; frac_of_ceiling = issued MMA rate / peak
-                             "ceiling_frac": 1.0 / 3.0,
-                             "frac_of_ceiling": 3 * flops_per_fwd / (fwd_ms * 1e-3) / 1e12 / tflops,
-                             "hbm": {"achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                                     "algorithmic_bytes_per_launch": bytes_per_fwd}}}
+                # `achieved` = ALGORITHMIC flops (1x) / measured time; the HBM view is kept beside it as scalars.
+                "roofline": roofline_block(r, fwd_ms, ms, "conv stack of one step (frames_to_c8 + conv_pm + conv_halo* "
+                                           "[+ split-K epilogues, ConvLSTM convs]), one CUDA-graph launch per step")}
+        del r
+        torch.cuda.empty_cache()
+        if world == 1 and not args.no_extra and args.workload == "tiny":
+            # the other BASELINE configs that fit one GPU, short runs, reported as scalar keys beside the headline
+            for name, key in (("c2", "c2_b1"), ("c4", "c4_b4"), ("multiobj", "c3_multiobj_b36"), ("c5", "c5_608_b8")):
+                try:
+                    rr = Runner(name, WORKLOADS[name]["S"], 0, 1, local, PIPE, clip_windows=32)
+                    k = 100 if name in ("c2", "c4", "c5") else 40
+                    m, f, _ = timed_loop(rr, k, 5, barrier)
+                    B = rr.S * rr.T
+                    pk = measured_peaks()
+                    fps = k * B / (m * 1e-3)
+                    line[key + "_fps"] = fps
+                    line[key + "_us_per_frame"] = 1e6 / fps
+                    line[key + "_conv_ms"] = f
+                    line[key + "_hbm_frac"] = rr.bytes_per_step / (f * 1e-3) / 1e9 / pk["hbm"]
+                    line[key + "_tensor_frac"] = rr.flops_per_step / (f * 1e-3) / 1e12 / pk["tflops_burst"]
+                    del rr
+                    torch.cuda.empty_cache()
+                except Exception as e:                          # a secondary config must not lose the headline
+                    line[key + "_error"] = repr(e)[:200]
         if world == 1 and not args.no_cpu_baseline:
-            fps, dt, kind, what = time_reference(40, 2)
+            fps, dt, kind, what = time_reference(40, 2, args.workload)
             line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": os.cpu_count(), "kind": kind,
                                     "sample": f"40 frames (10 windows) after 2 warm-up frames, {dt:.1f} s; {what}"}
         print(json.dumps(line), file=JSON_OUT, flush=True)
@@ -385,9 +555,13 @@ if __name__ == "__main__":
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--windows", type=int, default=9,
-                    help="independent 4-frame windows per GPU per step (9 x 4 = 36 frames: 36 images x 8 cout tiles = 288 "
-                         "work items ~ 2 x 148 SMs for the 13x13 layers)")
+    ap.add_argument("--workload", default="tiny", choices=sorted(WORKLOADS),
+                    help="BASELINE.json config: tiny = configs[1] batched over 9 windows (headline), c2 = configs[1] "
+                         "frame by frame, multiobj = configs[2], c4 = configs[3] per GPU, c5 = configs[4] per GPU")
+    ap.add_argument("--windows", type=int, default=0,
+                    help="windows / streams per GPU per step (default: the workload's; tiny: 9 x 4 = 36 frames: 36 "
+                         "images x 8 cout tiles = 288 work items ~ 2 x 148 SMs for the 13x13 layers)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short runs of the other BASELINE configs")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="run the tracker tail of a step before the next step starts")

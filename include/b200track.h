@@ -27,11 +27,13 @@ typedef struct b2t_ctx b2t_ctx;
 enum { B2T_SEM_KERAS = 0,     /* gamma*(x-mean)/sqrt(var+eps)+beta, tf.space_to_depth  (KerasYOLO.py:257-262,241) */
        B2T_SEM_DARKNET = 1 }; /* (x-mean)/(sqrt(var)+1e-6)*gamma+beta, reorg_cpu        (blas.c:147-158, :9-30)    */
 
-/* which contraction kernel runs the convolutions */
+/* which contraction kernel runs the convolutions.  The release library has ONE: B2T_ENGINE_TCGEN05.  The other two
+ * values select developer cross-check engines that exist only in `make DEV=1` builds (libb200track_dev.so,
+ * b2t_dev_build() == 1); b2t_create rejects them otherwise. */
 enum { B2T_ENGINE_TCGEN05 = 0,   /* tcgen05.mma, fp16 hi/lo split operands, 3 MMAs per product, fp32 accumulate in TMEM;
-                                    activation patch stationary in shared memory (conv_halo.cu)                        */
-       B2T_ENGINE_SIMT = 1,      /* fp32 FMA on the same operands: on-device cross-check only (slow)                    */
-       B2T_ENGINE_TCGEN05_TILE = 2 }; /* first-generation tcgen05 kernel, one TMA box per tap (conv_umma.cu); cross-check */
+                                    activation patch stationary in shared memory (conv_halo.cu / conv_pm.cu)          */
+       B2T_ENGINE_SIMT = 1,      /* DEV: fp32 FMA on the same operands (slow)                                          */
+       B2T_ENGINE_TCGEN05_TILE = 2 }; /* DEV: first-generation tcgen05 kernel, one TMA box per tap (dev_engines.cu)   */
 
 enum { B2T_FRAME_U8 = 0,      /* HWC uint8, divided by 255 on load (utils.py:150-153 normalize) */
        B2T_FRAME_F32 = 1 };   /* HWC float32, already normalised                                 */
@@ -50,6 +52,7 @@ typedef struct {
 
 const char *b2t_last_error(void);
 int  b2t_version(void);
+int  b2t_dev_build(void);     /* 1 = built with -DB2T_DEV (cross-check engines, B2T_* environment overrides, trace stamps) */
 
 /* ---- lifetime ---------------------------------------------------------------------------- */
 int  b2t_create(const b2t_config *cfg, b2t_ctx **out);
@@ -127,6 +130,10 @@ int  b2t_lstm_reset(b2t_lstm *l, int stream_index /* -1 = all */, void *stream);
  * stored (S,T,F) can be stepped without a gather. */
 int  b2t_lstm_step(b2t_lstm *l, const float *fv_dev, int fv_stride, const float *det_dev, int det_stride,
                    int n_streams, float *y_dev, int y_stride, int hard_sigmoid, void *stream);
+/* the same for streams [slot0, slot0 + n_streams) of the head's max_streams state slots; the other streams keep
+ * their (h, c): BaseTracker.step(frame, stream=k) for interleaved online streams */
+int  b2t_lstm_step_slots(b2t_lstm *l, int slot0, const float *fv_dev, int fv_stride, const float *det_dev,
+                         int det_stride, int n_streams, float *y_dev, int y_stride, int hard_sigmoid, void *stream);
 /* A whole window in one call: fv_dev (S,T,n_feat), det_dev (S,T,n_det) dense -> y_dev (S,T,n_out).  The input
  * projection x*W of all S*T rows is one launch, only h*U + gates is sequential (T launches), the Dense head is one
  * launch.  reset != 0 zeroes (h,c) first = Keras' stateless windows. T <= 16. */
@@ -160,9 +167,16 @@ int  b2t_box_from_heatmap(b2t_ctx *ctx, const float *heat_dev, int n, int size, 
                           int *rect_dev /* (S,4) x1,y1,x2,y2 */, void *stream);
 
 /* MultiObjDetTracker (MultiObjDetTracker.py:160-189): ConvLSTM2D over concat[conv_23 logits, conv_feat]
- * of the last b2t_yolo_forward, frames [0,batch) taken as consecutive time steps of ONE stream
- * (TimeDistributed, :162-171), then the 1x1 head.  trk_logits_dev (batch,G,G,5*(5+C)) fp32. */
-int  b2t_convlstm_reset(b2t_ctx *ctx, void *stream);
+ * of the last b2t_yolo_forward, then the 1x1 head.  The context holds max_batch recurrent-state slots (h, c).
+ * b2t_convlstm_sequence: frames [0, S*T) of the last forward are S streams x T consecutive time steps (frame index
+ * s*T + t; TimeDistributed, :162-171); stream s uses state slot slot0 + s.  reset != 0 zeroes those slots first
+ * (= Keras' stateless windows).  The input conv and the head run once over all S*T frames; the recurrent conv runs
+ * once per time step over the S streams.  trk_logits_dev (S*T,G,G,5*(5+C)) fp32.
+ * b2t_convlstm_window(batch) = sequence(S=1, T=batch, slot0=0, reset=0). */
+int  b2t_convlstm_reset(b2t_ctx *ctx, void *stream);                               /* every slot */
+int  b2t_convlstm_reset_slots(b2t_ctx *ctx, int slot0, int n_slots, void *stream);
+int  b2t_convlstm_sequence(b2t_ctx *ctx, int n_streams, int n_steps, int slot0, int reset, float *trk_logits_dev,
+                           int hard_sigmoid, void *stream);
 int  b2t_convlstm_window(b2t_ctx *ctx, int batch, float *trk_logits_dev, int hard_sigmoid, void *stream);
 
 /* ---- introspection for bench.py ------------------------------------------------------------ */

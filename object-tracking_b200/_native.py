@@ -6,7 +6,10 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
+# B2T_USE_DEV_LIB=1 loads the developer build (make DEV=1: cross-check engines, B2T_* overrides) when it exists
 LIB_PATH = os.path.join(_HERE, "libb200track.so")
+if os.environ.get("B2T_USE_DEV_LIB") == "1" and os.path.exists(os.path.join(_HERE, "libb200track_dev.so")):
+    LIB_PATH = os.path.join(_HERE, "libb200track_dev.so")
 
 SEM_KERAS, SEM_DARKNET = 0, 1
 ENGINE_TCGEN05, ENGINE_SIMT, ENGINE_TCGEN05_TILE = 0, 1, 2
@@ -29,6 +32,7 @@ _vp, _fp, _ip = C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)
 SIGNATURES = {
     "b2t_last_error": (C.c_char_p, []),
     "b2t_version": (C.c_int, []),
+    "b2t_dev_build": (C.c_int, []),
     "b2t_create": (C.c_int, [C.POINTER(Config), C.POINTER(_vp)]),
     "b2t_destroy": (None, [_vp]),
     "b2t_weight_bytes": (C.c_size_t, [_vp]),
@@ -52,6 +56,7 @@ SIGNATURES = {
     "b2t_lstm_set_weights": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b2t_lstm_reset": (C.c_int, [_vp, C.c_int, _vp]),
     "b2t_lstm_step": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, C.c_int, _vp, C.c_int, C.c_int, _vp]),
+    "b2t_lstm_step_slots": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp, C.c_int, C.c_int, _vp, C.c_int, C.c_int, _vp]),
     "b2t_lstm_sequence": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, C.c_int, C.c_int, _vp]),
     "b2t_pool_features": (C.c_int, [_vp, C.c_char_p, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "b2t_resize_frames": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, _vp]),
@@ -62,6 +67,8 @@ SIGNATURES = {
     "b2t_box_from_heatmap": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_float, _vp, _vp]),
     "b2t_convlstm_reset": (C.c_int, [_vp, _vp]),
     "b2t_convlstm_window": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp]),
+    "b2t_convlstm_reset_slots": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "b2t_convlstm_sequence": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp]),
     "b2t_launch_count": (C.c_long, [_vp]),
     "b2t_profile_forward": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _fp, C.POINTER(C.c_double), _vp]),
 }

@@ -41,7 +41,17 @@ int b2t_fail_internal(int code, const char *msg) {
     return code;
 }
 extern "C" const char *b2t_last_error(void) { return g_err; }
-extern "C" int b2t_version(void) { return 100; }
+extern "C" int b2t_version(void) { return 200; }
+
+// Developer switches (tile geometry / split overrides, trace stamps, the SIMT and first-generation tile engines) exist
+// only in `make DEV=1` builds.  The release library reads no environment variable and has one conv path.
+#ifdef B2T_DEV
+extern "C" int b2t_dev_build(void) { return 1; }
+static int dev_env(const char *name, int dflt) { const char *e = getenv(name); return e ? atoi(e) : dflt; }
+#else
+extern "C" int b2t_dev_build(void) { return 0; }
+static inline int dev_env(const char *, int dflt) { return dflt; }
+#endif
 
 // ------------------------------------------------------------------------------------------------ plan
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -138,8 +148,7 @@ static void choose_tile(int H, int W, bool pool, int &TW, int &TH) {
 static void choose_halo_tile(int H, int W, int ksize, bool pool, ConvLayer &l) {
     const int pad = ksize / 2, taps = ksize * ksize;
     // short K and many tiles -> the small shape (two CTAs per SM overlap each other's prologue/epilogue)
-    const char *env = getenv("B2T_SMALL");
-    const int small_mode = env ? atoi(env) : -1;
+    const int small_mode = dev_env("B2T_SMALL", -1);
     const int kbytes = l.kchunk * 2;
     l.h_small = small_mode >= 0 ? (small_mode != 0 && H >= 26) : (l.cin_pad / l.kchunk * taps <= 36 && H >= 52);
     const int max_rows = l.h_small ? 176 : 256, max_n = l.h_small ? 128 : 256;
@@ -196,16 +205,16 @@ static void choose_pm_tile(int H, int W, int ksize, bool pool, int row_bytes, bo
 static unsigned magic_for(int d) { return d <= 1 ? 0u : (unsigned)((0x100000000ull + (unsigned)d - 1) / (unsigned)d); }
 
 static int choose_splits_halo(int ctas, int cin_chunks, int taps, int n_sm) {
-    const char *env = getenv("B2T_SPLITS");
+    const int force = dev_env("B2T_SPLITS", 0);
     int best_s = 1;
     double best_cost = 1e30;
     const int max_s = cin_chunks > 32 ? 32 : cin_chunks;
     for (int s = 1; s <= max_s; ++s) {
         const int per = (cin_chunks + s - 1) / s;
         if ((cin_chunks + per - 1) / per != s) continue;
-        if (env && atoi(env) > 0 && s != atoi(env) && s != max_s) continue;
+        if (force > 0 && s != force && s != max_s) continue;
         // the tensor core truncates addends to the accumulator's exponent: keep one accumulation chain short
-        static const int chain_cap = getenv("B2T_CHAIN") ? atoi(getenv("B2T_CHAIN")) : 320;
+        static const int chain_cap = dev_env("B2T_CHAIN", 320);
         if (per * taps * 4 > chain_cap && s < max_s) continue;
         const long waves = ((long)ctas * s + n_sm - 1) / n_sm;
         const double cost = (double)waves * (per * taps + 10.0) + (s > 1 ? 3.0 * s : 0.0);
@@ -214,6 +223,7 @@ static int choose_splits_halo(int ctas, int cin_chunks, int taps, int n_sm) {
     return best_s;
 }
 
+#ifdef B2T_DEV
 static int choose_splits(int tiles, int chunks, int n_sm) {
     const char *env = getenv("B2T_SPLITS");
     if (env && atoi(env) > 0) {
@@ -235,6 +245,7 @@ static int choose_splits(int tiles, int chunks, int n_sm) {
     }
     return best_s;
 }
+#endif
 
 // ------------------------------------------------------------------------------------------------ create
 static ConvLayer &new_conv(b2t_ctx *c, int index, int k, int cin, int cout, bool act, bool pool, int H, int W) {
@@ -275,6 +286,10 @@ extern "C" int b2t_create(const b2t_config *cfg, b2t_ctx **out) {
         return fail(-1, "b2t_create: image size %dx%d must be a positive multiple of 32", cfg->image_h, cfg->image_w);
     if (cfg->image_h != cfg->image_w) return fail(-1, "b2t_create: square input expected (GRID_H == GRID_W)");
     if (cfg->n_class < 1 || cfg->max_batch < 1) return fail(-1, "b2t_create: bad n_class/max_batch");
+#ifndef B2T_DEV
+    if (cfg->engine != B2T_ENGINE_TCGEN05)
+        return fail(-1, "b2t_create: engine %d is a developer cross-check engine (build with make DEV=1)", cfg->engine);
+#endif
     b2t_ctx *c = new b2t_ctx();
     c->cfg = *cfg;
     c->keep_prepool = cfg->reserved[0];
@@ -361,7 +376,6 @@ extern "C" int b2t_create(const b2t_config *cfg, b2t_ctx **out) {
         if (u % 64) { delete c; return fail(-1, "convlstm_units must be a multiple of 64"); }
         c->buf_hrec = add_buf(c, "", Gs, Gs, u);
         c->buf_hseq = add_buf(c, "", Gs, Gs, u);
-        c->bufs[c->buf_hrec].plane = (long long)Gs * Gs * u;        // one stream only
         c->L_CIN = 24; c->L_CREC = 25; c->L_HEAD = 26;
         ConvLayer &a = new_conv(c, 24, 3, zc, 4 * u, false, false, Gs, Gs);
         a.in_buf = featz; a.f32_out = 2;
@@ -395,13 +409,18 @@ extern "C" int b2t_create(const b2t_config *cfg, b2t_ctx **out) {
         const ConvLayer &l = c->conv[i];
         if (!l.index) continue;
         const size_t ldp = round_up(l.cout, 32);
+#ifdef B2T_DEV
         const int tiles1 = ((l.W + l.TW - 1) / l.TW) * ((l.H + l.TH - 1) / l.TH) * ((l.cout + l.BN - 1) / l.BN);
+#endif
         for (int bsz = 1; bsz <= MB; ++bsz) {
             size_t s = 1;
+#ifdef B2T_DEV
             if (cfg->engine == 2) {
                 s = choose_splits(tiles1 * bsz, l.k * l.k * l.cin_pad / 64, 148);
                 if (s == 1) continue;
-            } else if (cfg->engine == B2T_ENGINE_TCGEN05) {
+            } else
+#endif
+            if (cfg->engine == B2T_ENGINE_TCGEN05) {
                 const int ctas = ((l.W + l.hC - 1) / l.hC) * ((l.H + l.hR - 1) / l.hR) * ((l.cout + 127) / 128) * bsz;
                 s = choose_splits_halo(ctas, l.cin_pad / l.kchunk, l.k * l.k, 148);
                 if (s == 1) continue;
@@ -414,7 +433,7 @@ extern "C" int b2t_create(const b2t_config *cfg, b2t_ctx **out) {
     if (lstm) {
         const int u = cfg->convlstm_units;
         c->off_gates = o;   o += align_up((size_t)MB * Gs * Gs * 4 * u * 4, 1024);
-        c->off_cstate = o;  o += align_up((size_t)Gs * Gs * u * 4, 1024);
+        c->off_cstate = o;  o += align_up((size_t)MB * Gs * Gs * u * 4, 1024);    // one (h, c) state slot per frame of a batch
     }
     c->ws_bytes = o;
     *out = c;
@@ -649,8 +668,10 @@ extern "C" int b2t_finalize(b2t_ctx *c, int upload, void *stream) {
         if (!fn || q != cudaDriverEntryPointSuccess) return fail(-2, "cuTensorMapEncodeTiled not available in this driver");
         c->encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
     }
-    int rc = conv_umma_init();
-    if (!rc) rc = conv_halo_init();
+    int rc = conv_halo_init();
+#ifdef B2T_DEV
+    if (!rc) rc = conv_umma_init();
+#endif
     if (!rc) rc = conv_pm_init();
     if (rc) return fail(-2, "cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString((cudaError_t)rc));
     if (upload) CK(cudaMemcpyAsync(c->d_blob, c->host_blob.data(), c->weight_bytes, cudaMemcpyHostToDevice, st));
@@ -662,7 +683,7 @@ extern "C" int b2t_finalize(b2t_ctx *c, int upload, void *stream) {
         ConvLayer &l = c->conv[i];
         if (!l.index) continue;
         const ActBuf &in = c->bufs[l.in_buf];
-        const int nb = (l.in_buf == c->buf_hrec) ? 1 : MB;
+        const int nb = MB;
         cuuint64_t dims[4] = {(cuuint64_t)l.cin_pad, (cuuint64_t)l.W, (cuuint64_t)l.H, (cuuint64_t)nb};
         cuuint64_t strides[3] = {(cuuint64_t)in.C * 2, (cuuint64_t)in.C * 2 * l.W, (cuuint64_t)in.C * 2 * l.W * l.H};
         cuuint32_t box[4] = {64, (cuuint32_t)l.TW, (cuuint32_t)l.TH, 1};
@@ -690,7 +711,7 @@ extern "C" int b2t_finalize(b2t_ctx *c, int upload, void *stream) {
         if ((rc = make_tmap(c, &l.tmWp_lo, c->d_blob + l.off_wlo, 2, wd, wst, wbox3, sw64))) return rc;
         // 1x1 layers without pooling and with a plain destination: tiles of exactly 128 pixels of the flat pixel list
         // of the whole batch, persistent kernel (TMEM double buffering: the epilogue overlaps the next tile's MMAs)
-        static const int flat_mode = getenv("B2T_FLAT") ? atoi(getenv("B2T_FLAT")) : 1;
+        static const int flat_mode = dev_env("B2T_FLAT", 1);
         // (measured: a win up to K = 512; longer K re-streams too many weight bytes per 128-pixel tile -- the
         // shared-memory port saturates -- and the N = 192 whole-image tiles of conv_halo_kernel stay faster)
         l.flat1x1 = flat_mode && l.k == 1 && !l.pool && l.out_mode == DEST_PLAIN && l.kchunk == 64 && nb == MB &&
@@ -704,7 +725,7 @@ extern "C" int b2t_finalize(b2t_ctx *c, int upload, void *stream) {
             if ((rc = make_tmap(c, &l.tmXf_lo, in.hi + in.plane + l.in_ch_off, 4, fd, fs, fb))) return rc;
         }
         // pixel-major variant: narrow layers whose weights all stay resident in shared memory
-        static const int pm_mode = getenv("B2T_PM") ? atoi(getenv("B2T_PM")) : 1;
+        static const int pm_mode = dev_env("B2T_PM", 1);
         l.pm = false;
         if (pm_mode && l.pmC && c->cfg.engine == B2T_ENGINE_TCGEN05 && l.cout <= 64 && nb == MB) {
             l.pm_flat = l.k == 1 && !l.pool && l.out_mode == DEST_PLAIN;
@@ -732,7 +753,7 @@ extern "C" int b2t_finalize(b2t_ctx *c, int upload, void *stream) {
     }
     {   // conv_1 on the tensor cores: TMA view of the fp16-integer frame copy [MB][H][W][8]
         ConvLayer &l = c->conv[1];
-        static const int pm_mode = getenv("B2T_PM") ? atoi(getenv("B2T_PM")) : 1;
+        static const int pm_mode = dev_env("B2T_PM", 1);
         l.pm = false;
         if (pm_mode && l.pmC && c->cfg.engine == B2T_ENGINE_TCGEN05) {
             cuuint64_t dims[4] = {8, (cuuint64_t)l.W, (cuuint64_t)l.H, (cuuint64_t)MB};
@@ -762,7 +783,10 @@ static Dest dest_planes(const b2t_ctx *c, int buf, int ch_off, int srcH, int src
     return d;
 }
 
-static int run_conv(b2t_ctx *c, ConvLayer &l, int B, float *f32_dst, cudaStream_t st) {
+// f32_img_stride (pixels, 0 = dense) and in_img_off (images) serve the ConvLSTM recurrent conv: stream s of a step reads
+// state slot in_img_off + s and accumulates into frame s*T + t of the gate buffer.
+static int run_conv(b2t_ctx *c, ConvLayer &l, int B, float *f32_dst, cudaStream_t st, long long f32_img_stride = 0,
+                    int in_img_off = 0) {
     ConvParams p;
     memset(&p, 0, sizeof p);
     p.B = B; p.H = l.H; p.W = l.W; p.ksize = l.k; p.cin_chunks = l.cin_pad / l.kchunk; p.Cout = l.cout;
@@ -772,7 +796,7 @@ static int run_conv(b2t_ctx *c, ConvLayer &l, int B, float *f32_dst, cudaStream_
     p.chunks_total = l.k * l.k * p.cin_chunks;
     p.ldp = round_up(l.cout, 32);
     p.act = l.act; p.pool = l.pool;
-    { const char *e = getenv("B2T_NMAIN"); p.n_main = e ? atoi(e) : 3; if (p.n_main < 1) p.n_main = 1; if (p.n_main > 3) p.n_main = 3; }
+    { static const int nm = dev_env("B2T_NMAIN", 3); p.n_main = nm < 1 ? 1 : nm > 3 ? 3 : nm; }
     p.scale = reinterpret_cast<const float *>(c->d_blob + l.off_scale);
     p.bias = reinterpret_cast<const float *>(c->d_blob + l.off_bias);
     p.partial = reinterpret_cast<float *>(c->d_ws + c->off_partial);
@@ -783,13 +807,16 @@ static int run_conv(b2t_ctx *c, ConvLayer &l, int B, float *f32_dst, cudaStream_
         p.out.pix_stride_f = l.cout;
         p.out.ch_off_f = 0;
         p.out.accumulate_f = l.f32_accumulate;
+        p.out.img_stride_f = f32_img_stride;
     }
+    p.b_in_off = in_img_off;
     int rc;
+#ifdef B2T_DEV
     if (c->cfg.engine == B2T_ENGINE_SIMT) {
         p.splits = 1;
         const ActBuf &in = c->bufs[l.in_buf];
         SimtView v;
-        v.a_hi = in.hi + l.in_ch_off; v.a_plane = in.plane; v.a_pix_stride = in.C;
+        v.a_hi = in.hi + l.in_ch_off + (long long)in_img_off * l.H * l.W * in.C; v.a_plane = in.plane; v.a_pix_stride = in.C;
         v.w_hi = reinterpret_cast<const op_t *>(c->d_blob + l.off_whi);
         v.w_plane = (long long)(l.off_wlo - l.off_whi) / 2; v.w_ld = l.ldw;
         if ((rc = launch_conv_simt(v, p, st))) return fail(-2, "conv_simt launch: %s", cudaGetErrorString((cudaError_t)rc));
@@ -797,9 +824,10 @@ static int run_conv(b2t_ctx *c, ConvLayer &l, int B, float *f32_dst, cudaStream_
         c->launches += 2;
         return 0;
     }
+    { static const int dbg = dev_env("B2T_DBG", 0); p.dbg = dbg; }
+#endif
     if (c->cfg.engine == B2T_ENGINE_TCGEN05 && l.pm && !f32_dst) {
         p.splits = 1;
-        p.dbg = getenv("B2T_DBG") ? atoi(getenv("B2T_DBG")) : 0;
         p.pm_mode = 0;
         p.pm_n = round_up(l.cout, 32);
         p.pm_tmem_cols = 4 * p.pm_n <= 128 ? 128 : 4 * p.pm_n <= 256 ? 256 : 512;
@@ -824,7 +852,7 @@ static int run_conv(b2t_ctx *c, ConvLayer &l, int B, float *f32_dst, cudaStream_
         c->launches += 1;
         return 0;
     }
-    if (c->cfg.engine == B2T_ENGINE_TCGEN05 && l.flat1x1) {
+    if (c->cfg.engine == B2T_ENGINE_TCGEN05 && l.flat1x1 && !in_img_off) {
         const int npx = B * l.H * l.W;
         const int items = ((npx + 127) / 128) * ((l.cout + 127) / 128);
         if (items >= c->n_sm) {                 // enough tiles to fill the machine without a K split
@@ -837,7 +865,6 @@ static int run_conv(b2t_ctx *c, ConvLayer &l, int B, float *f32_dst, cudaStream_
             p.pw_tile_bytes = 2 * l.w_rows * p.kbytes;
             const int room = 222 * 1024 - 1024 - 1024 - 2 * p.pw_patch_bytes - p.pw_stage_bytes;
             p.pw_stages = room / p.pw_tile_bytes > 16 ? 16 : room / p.pw_tile_bytes;
-            { static const int dbg = getenv("B2T_DBG") ? atoi(getenv("B2T_DBG")) : 0; p.dbg = dbg; }
             if ((rc = launch_conv_halo_persist(c->n_sm, l.tmXf_hi, l.tmXf_lo, l.tmWp_hi, l.tmWp_lo, p, st)))
                 return fail(-2, "conv_halo_persist launch (conv %d): %s", l.index, cudaGetErrorString((cudaError_t)rc));
             c->launches += 1;
@@ -851,7 +878,7 @@ static int run_conv(b2t_ctx *c, ConvLayer &l, int B, float *f32_dst, cudaStream_
         p.splits = choose_splits_halo(ctas, p.cin_chunks, l.k * l.k, c->n_sm);
         if (p.splits > 1 && (size_t)p.splits * B * l.H * l.W * p.ldp * 4 > c->partial_bytes)
             return fail(-2, "internal: split-K workspace too small for conv %d", l.index);
-        static const int persist_mode = getenv("B2T_PERSIST") ? atoi(getenv("B2T_PERSIST")) : 2;
+        static const int persist_mode = dev_env("B2T_PERSIST", 2);
         // persistent variant (one CTA per SM, TMEM double buffering) for every short-K layer with enough tiles;
         // B2T_PERSIST=1 restricts it to 1x1 layers and layers whose weights stay resident, 0 disables it
         bool persist = persist_mode && l.h_small && p.splits == 1 && p.hN <= 128 && ctas > 2 * c->n_sm &&
@@ -866,7 +893,7 @@ static int run_conv(b2t_ctx *c, ConvLayer &l, int B, float *f32_dst, cudaStream_
             p.pw_stages = room / p.pw_tile_bytes > 16 ? 16 : room / p.pw_tile_bytes;
             if (p.pw_stages < 2) persist = false;
         }
-        { static const int dbg = getenv("B2T_DBG") ? atoi(getenv("B2T_DBG")) : 0; p.dbg = dbg; }
+#ifdef B2T_DEV
         static long long *d_trace = nullptr;
         const char *tr = getenv("B2T_TRACE_CONV");
         if (tr && atoi(tr) == l.index) {
@@ -874,31 +901,30 @@ static int run_conv(b2t_ctx *c, ConvLayer &l, int B, float *f32_dst, cudaStream_
             cudaMemsetAsync(d_trace, 0, 64 * 8 * 8, st);
             p.trace = d_trace;
         }
+#endif
         if (persist)
             rc = launch_conv_halo_persist(c->n_sm, l.tmX_hi, l.tmX_lo, l.tmWp_hi, l.tmWp_lo, p, st);
-        if (persist && p.trace) {
+        else
+            rc = launch_conv_halo(c->n_sm, l.h_small, l.tmX_hi, l.tmX_lo, l.tmW_hi, l.tmW_lo, p, st);
+#ifdef B2T_DEV
+        if (p.trace) {
             long long h[64 * 8];
             cudaStreamSynchronize(st);
             cudaMemcpy(h, d_trace, sizeof h, cudaMemcpyDeviceToHost);
             const long long t0 = h[1];
-            fprintf(stderr, "[trace conv_%d] item: patch_issue | mma: wait_acc_begin acc_ok patch_ok | epi: wait_begin acc_full done (cycles rel.)\n", l.index);
-            for (int j = 0; j < 12; ++j)
-                fprintf(stderr, "  %2d: %7lld | %7lld %7lld %7lld | %7lld %7lld %7lld\n", j, h[j * 8] - t0, h[j * 8 + 1] - t0,
-                        h[j * 8 + 2] - t0, h[j * 8 + 3] - t0, h[j * 8 + 4] - t0, h[j * 8 + 5] - t0, h[j * 8 + 6] - t0);
-        }
-        if (!persist) {
-            rc = launch_conv_halo(c->n_sm, l.h_small, l.tmX_hi, l.tmX_lo, l.tmW_hi, l.tmW_lo, p, st);
-            if (p.trace) {
-                long long h[64 * 8];
-                cudaStreamSynchronize(st);
-                cudaMemcpy(h, d_trace, sizeof h, cudaMemcpyDeviceToHost);
-                const long long t0 = h[1];
+            if (persist) {
+                fprintf(stderr, "[trace conv_%d] item: patch_issue | mma: wait_acc_begin acc_ok patch_ok | epi: wait_begin acc_full done (cycles rel.)\n", l.index);
+                for (int j = 0; j < 12; ++j)
+                    fprintf(stderr, "  %2d: %7lld | %7lld %7lld %7lld | %7lld %7lld %7lld\n", j, h[j * 8] - t0, h[j * 8 + 1] - t0,
+                            h[j * 8 + 2] - t0, h[j * 8 + 3] - t0, h[j * 8 + 4] - t0, h[j * 8 + 5] - t0, h[j * 8 + 6] - t0);
+            } else {
                 fprintf(stderr, "[trace conv_%d N=%d splits=%d] item: mma: start acc_ok patch_ok issue_end | epi: wait accum_ok done ; last phase1 %lld\n", l.index, p.hN, p.splits, h[511] - t0);
                 for (int j = 0; j < 4; ++j)
                     fprintf(stderr, "  %2d: %7lld %7lld %7lld %7lld | %7lld %7lld %7lld\n", j, h[j * 8 + 1] - t0, h[j * 8 + 2] - t0,
                             h[j * 8 + 3] - t0, h[j * 8 + 7] - t0, h[j * 8 + 4] - t0, h[j * 8 + 5] - t0, h[j * 8 + 6] - t0);
             }
         }
+#endif
         if (rc)
             return fail(-2, "conv_halo launch (conv %d): %s", l.index, cudaGetErrorString((cudaError_t)rc));
         c->launches += 1;
@@ -908,6 +934,7 @@ static int run_conv(b2t_ctx *c, ConvLayer &l, int B, float *f32_dst, cudaStream_
         }
         return 0;
     }
+#ifdef B2T_DEV
     const int tiles = B * p.tiles_x * p.tiles_y * ((l.cout + l.BN - 1) / l.BN);
     p.splits = choose_splits(tiles, p.chunks_total, c->n_sm);
     if (p.splits > 1 && (size_t)p.splits * B * l.H * l.W * p.ldp * 4 > c->partial_bytes)
@@ -920,6 +947,9 @@ static int run_conv(b2t_ctx *c, ConvLayer &l, int B, float *f32_dst, cudaStream_
         c->launches += 1;
     }
     return 0;
+#else
+    return fail(-1, "engine %d is not part of the release build", c->cfg.engine);
+#endif
 }
 
 static int run_conv1(b2t_ctx *c, const void *frames, int dtype, int B, cudaStream_t st) {
@@ -943,16 +973,19 @@ static int run_conv1(b2t_ctx *c, const void *frames, int dtype, int B, cudaStrea
         p.pw_patch_bytes = l.pm_plane_bytes;
         p.pw_stage_bytes = 0;                                  // mode 1 pools in registers: no staging buffers
         p.pm_w = c->d_blob + c->off_w1pm; p.pm_w_bytes = 3 * 4096;
-        p.dbg = getenv("B2T_DBG") ? atoi(getenv("B2T_DBG")) : 0;
         p.magic_tx = magic_for(p.h_tiles_x); p.magic_ty = magic_for(p.h_tiles_y);
+#ifdef B2T_DEV
+        { static const int dbg = dev_env("B2T_DBG", 0); p.dbg = dbg; }
         static long long *d_trace = nullptr;
         if (getenv("B2T_TRACE_CONV") && atoi(getenv("B2T_TRACE_CONV")) == 1) {
             if (!d_trace) cudaMalloc(&d_trace, 64 * 16 * 8);
             cudaMemsetAsync(d_trace, 0, 64 * 16 * 8, st);
             p.trace = d_trace;
         }
+#endif
         if ((rc = launch_conv_pm(c->n_sm, l.tmXp_hi, l.tmXp_lo, l.tmXp_hi, l.tmXp_lo, p, st)))
             return fail(-2, "conv_pm launch (conv 1): %s", cudaGetErrorString((cudaError_t)rc));
+#ifdef B2T_DEV
         if (p.trace) {
             long long h[64 * 16];
             cudaStreamSynchronize(st);
@@ -964,6 +997,7 @@ static int run_conv1(b2t_ctx *c, const void *frames, int dtype, int B, cudaStrea
                         h[j * 16 + 2] - t0, h[j * 16 + 3] - t0, h[j * 16 + 4] - t0, h[j * 16 + 5] - t0, h[j * 16 + 6] - t0,
                         h[j * 16 + 7] - t0, h[j * 16 + 8] - t0);
         }
+#endif
         c->launches += 2;
         return 0;
     }
@@ -1206,22 +1240,25 @@ extern "C" int b2t_lstm_reset(b2t_lstm *l, int s, void *stream) {
     return 0;
 }
 
-extern "C" int b2t_lstm_step(b2t_lstm *l, const float *fv, int fv_stride, const float *det, int det_stride, int S,
-                             float *y, int y_stride, int hard_sigmoid, void *stream) {
+// streams [slot0, slot0 + S) of the head's state are stepped; every other stream keeps its (h, c)
+extern "C" int b2t_lstm_step_slots(b2t_lstm *l, int slot0, const float *fv, int fv_stride, const float *det, int det_stride,
+                                   int S, float *y, int y_stride, int hard_sigmoid, void *stream) {
     if (!l || !l->have) return fail(-1, "b2t_lstm_step: weights not set");
     if (!fv || (!det && l->n_det) || !y) return fail(-1, "b2t_lstm_step: null pointer");
-    if (S < 1 || S > l->max_streams) return fail(-1, "n_streams %d outside [1,%d]", S, l->max_streams);
+    if (S < 1 || slot0 < 0 || slot0 + S > l->max_streams)
+        return fail(-1, "streams [%d,%d) outside [0,%d)", slot0, slot0 + S, l->max_streams);
     cudaStream_t st = (cudaStream_t)stream;
     if (fv_stride <= 0) fv_stride = l->n_feat;
     if (det_stride <= 0) det_stride = l->n_det;
     if (y_stride <= 0) y_stride = l->n_out;
     const int nxt = l->cur ^ 1;
+    const size_t o = (size_t)slot0 * l->units;
     {
         LstmParams p;
         memset(&p, 0, sizeof p);
         p.wp = l->d_wp; p.bias = l->d_bias; p.fv = fv; p.det = det;
         p.fv_stride = fv_stride; p.det_stride = det_stride;
-        p.h_in = l->d_h[l->cur]; p.h_out = l->d_h[nxt]; p.c = l->d_c;
+        p.h_in = l->d_h[l->cur] + o; p.h_out = l->d_h[nxt] + o; p.c = l->d_c + o;
         p.n_feat = l->n_feat; p.n_det = l->n_det; p.units = l->units; p.S = S;
         p.hard_sigmoid = hard_sigmoid;
         const int rc = launch_lstm_gates(p, st);
@@ -1229,14 +1266,21 @@ extern "C" int b2t_lstm_step(b2t_lstm *l, const float *fv, int fv_stride, const 
         if (l->ctx) l->ctx->launches += 1;
     }
     // streams not stepped keep their state: copy them across the double buffer
-    if (S < l->max_streams)
-        CK(cudaMemcpyAsync(l->d_h[nxt] + (size_t)S * l->units, l->d_h[l->cur] + (size_t)S * l->units,
-                           (size_t)(l->max_streams - S) * l->units * 4, cudaMemcpyDeviceToDevice, st));
+    if (slot0 > 0)
+        CK(cudaMemcpyAsync(l->d_h[nxt], l->d_h[l->cur], o * 4, cudaMemcpyDeviceToDevice, st));
+    if (slot0 + S < l->max_streams)
+        CK(cudaMemcpyAsync(l->d_h[nxt] + o + (size_t)S * l->units, l->d_h[l->cur] + o + (size_t)S * l->units,
+                           (size_t)(l->max_streams - slot0 - S) * l->units * 4, cudaMemcpyDeviceToDevice, st));
     l->cur = nxt;
-    const int rc = launch_dense_sigmoid(l->d_h[l->cur], l->d_wd, l->d_bd, l->units, l->n_out, S, y, y_stride, st);
+    const int rc = launch_dense_sigmoid(l->d_h[l->cur] + o, l->d_wd, l->d_bd, l->units, l->n_out, S, y, y_stride, st);
     if (rc) return fail(-2, "dense launch: %s", cudaGetErrorString((cudaError_t)rc));
     if (l->ctx) l->ctx->launches += 1;
     return 0;
+}
+
+extern "C" int b2t_lstm_step(b2t_lstm *l, const float *fv, int fv_stride, const float *det, int det_stride, int S,
+                             float *y, int y_stride, int hard_sigmoid, void *stream) {
+    return b2t_lstm_step_slots(l, 0, fv, fv_stride, det, det_stride, S, y, y_stride, hard_sigmoid, stream);
 }
 
 extern "C" int b2t_lstm_sequence(b2t_lstm *l, const float *fv, const float *det, int S, int T, float *y, int reset,
@@ -1395,35 +1439,59 @@ extern "C" int b2t_select_detection(b2t_ctx *c, const float *dets, const int *co
 }
 
 // ------------------------------------------------------------------------------------------------ ConvLSTM
-extern "C" int b2t_convlstm_reset(b2t_ctx *c, void *stream) {
-    if (!c || !c->L_CIN || !c->finalized) return fail(-1, "convlstm not configured");
-    cudaStream_t st = (cudaStream_t)stream;
+static int convlstm_reset_slots(b2t_ctx *c, int slot0, int n, cudaStream_t st) {
     const ActBuf &h = c->bufs[c->buf_hrec];
-    CK(cudaMemsetAsync(h.hi, 0, (size_t)h.plane * 2 * 2, st));
-    CK(cudaMemsetAsync(c->d_ws + c->off_cstate, 0, (size_t)c->G * c->G * c->cfg.convlstm_units * 4, st));
+    const size_t per = (size_t)c->G * c->G * c->cfg.convlstm_units;
+    CK(cudaMemsetAsync(h.hi + (size_t)slot0 * per, 0, n * per * 2, st));
+    CK(cudaMemsetAsync(h.hi + h.plane + (size_t)slot0 * per, 0, n * per * 2, st));
+    CK(cudaMemsetAsync(c->d_ws + c->off_cstate + (size_t)slot0 * per * 4, 0, n * per * 4, st));
     return 0;
 }
 
-extern "C" int b2t_convlstm_window(b2t_ctx *c, int B, float *trk_logits, int hard_sigmoid, void *stream) {
+extern "C" int b2t_convlstm_reset(b2t_ctx *c, void *stream) {
     if (!c || !c->L_CIN || !c->finalized) return fail(-1, "convlstm not configured");
-    if (B < 1 || B > c->cfg.max_batch || !trk_logits) return fail(-1, "b2t_convlstm_window: bad arguments");
+    return convlstm_reset_slots(c, 0, c->cfg.max_batch, (cudaStream_t)stream);
+}
+
+extern "C" int b2t_convlstm_reset_slots(b2t_ctx *c, int slot0, int n_slots, void *stream) {
+    if (!c || !c->L_CIN || !c->finalized) return fail(-1, "convlstm not configured");
+    if (slot0 < 0 || n_slots < 1 || slot0 + n_slots > c->cfg.max_batch) return fail(-1, "b2t_convlstm_reset_slots: slots [%d,%d) outside [0,%d)", slot0, slot0 + n_slots, c->cfg.max_batch);
+    return convlstm_reset_slots(c, slot0, n_slots, (cudaStream_t)stream);
+}
+
+// S streams x T consecutive frames of the last b2t_yolo_forward (frame index s*T + t).  The input convolution W*z and
+// the 1x1 head are one batched launch each over all S*T frames; only U*h + the gate maths are sequential, batched over
+// the S streams (pixels of all streams share one pass over the recurrent weights).
+extern "C" int b2t_convlstm_sequence(b2t_ctx *c, int S, int T, int slot0, int reset, float *trk_logits, int hard_sigmoid,
+                                     void *stream) {
+    if (!c || !c->L_CIN || !c->finalized) return fail(-1, "convlstm not configured");
+    if (S < 1 || T < 1 || S * T > c->cfg.max_batch || !trk_logits) return fail(-1, "b2t_convlstm_sequence: S=%d x T=%d frames outside [1, max_batch=%d]", S, T, c->cfg.max_batch);
+    if (slot0 < 0 || slot0 + S > c->cfg.max_batch) return fail(-1, "b2t_convlstm_sequence: state slots [%d,%d) outside [0,%d)", slot0, slot0 + S, c->cfg.max_batch);
     cudaStream_t st = (cudaStream_t)stream;
     const int u = c->cfg.convlstm_units, M = c->G * c->G;
     float *gates = reinterpret_cast<float *>(c->d_ws + c->off_gates);
     int rc;
-    // input convolution for all T steps at once (does not depend on h)
-    if ((rc = run_conv(c, c->conv[c->L_CIN], B, gates, st))) return rc;
-    for (int t = 0; t < B; ++t) {
-        float *g = gates + (size_t)t * M * 4 * u;
-        if ((rc = run_conv(c, c->conv[c->L_CREC], 1, g, st))) return rc;       // += U * h_{t-1}
+    if (reset && (rc = convlstm_reset_slots(c, slot0, S, st))) return rc;
+    // input convolution for all S*T frames at once (does not depend on h)
+    if ((rc = run_conv(c, c->conv[c->L_CIN], S * T, gates, st))) return rc;
+    for (int t = 0; t < T; ++t) {
+        // += U * h_{t-1}: frame s*T + t of the gate buffer <- state slot slot0 + s.  After a reset h_{-1} = 0 and the
+        // term vanishes exactly: the launch is skipped.
+        if (!(reset && t == 0))
+            if ((rc = run_conv(c, c->conv[c->L_CREC], S, gates + (size_t)t * M * 4 * u, st, (long long)T * M, slot0))) return rc;
         ConvLstmGateParams p;
         memset(&p, 0, sizeof p);
-        p.g = g; p.c = reinterpret_cast<float *>(c->d_ws + c->off_cstate);
+        p.g = gates; p.c = reinterpret_cast<float *>(c->d_ws + c->off_cstate);
         p.h_rec = dest_planes(c, c->buf_hrec, 0, c->G, c->G, DEST_PLAIN);
         p.h_seq = dest_planes(c, c->buf_hseq, 0, c->G, c->G, DEST_PLAIN);
-        p.M = M; p.units = u; p.G = c->G; p.t = t; p.hard_sigmoid = hard_sigmoid;
+        p.M = M; p.units = u; p.G = c->G; p.S = S; p.T = T; p.t = t; p.slot0 = slot0; p.hard_sigmoid = hard_sigmoid;
         if ((rc = launch_convlstm_gates(p, st))) return fail(-2, "gates launch: %s", cudaGetErrorString((cudaError_t)rc));
         c->launches += 1;
     }
-    return run_conv(c, c->conv[c->L_HEAD], B, trk_logits, st);
+    return run_conv(c, c->conv[c->L_HEAD], S * T, trk_logits, st);
+}
+
+// frames [0,batch) of the last forward = consecutive time steps of ONE stream (state slot 0), state carried over
+extern "C" int b2t_convlstm_window(b2t_ctx *c, int B, float *trk_logits, int hard_sigmoid, void *stream) {
+    return b2t_convlstm_sequence(c, 1, B, 0, 0, trk_logits, hard_sigmoid, stream);
 }

@@ -79,8 +79,8 @@ __device__ __forceinline__ void halo_epilogue(const ConvParams &p, float *stage,
     tc_fence_before();
     asm volatile("bar.sync 1, 256;" ::: "memory");
     if (acc_free && et == 0) mbar_arrive(acc_free);
-    if (p.trace && blockIdx.x == 0 && et == 0) p.trace[511] = clock64();   // last phase-1 completion (developer trace)
-    if (p.dbg & 4) return;
+    if (B2T_TRACE_PTR(p) && blockIdx.x == 0 && et == 0) B2T_TRACE_PTR(p)[511] = clock64();   // last phase-1 completion (developer trace)
+    if (B2T_DBG_BITS(p) & 4) return;
     epilogue_store(p, stage, kStageLd, 4, b, y0, x0, cout0, zsplit, et, kEpiThreads);
 }
 
@@ -209,8 +209,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_consta
                 uint8_t *hdst = s_halo + hb * kHaloBufBytes;
                 if (elect_one()) {
                     mbar_expect_tx(&halo_full[hb], halo_tx);
-                    tma_load_4d(&tmX_hi, &halo_full[hb], hdst, ci * kelems, x0 - pad, y0 - pad, b, kEvictNormal);
-                    tma_load_4d(&tmX_lo, &halo_full[hb], hdst + p.h_plane_bytes, ci * kelems, x0 - pad, y0 - pad, b, kEvictNormal);
+                    tma_load_4d(&tmX_hi, &halo_full[hb], hdst, ci * kelems, x0 - pad, y0 - pad, b + p.b_in_off, kEvictNormal);
+                    tma_load_4d(&tmX_lo, &halo_full[hb], hdst + p.h_plane_bytes, ci * kelems, x0 - pad, y0 - pad, b + p.b_in_off, kEvictNormal);
                 }
                 __syncwarp();
                 for (int tap = 0; tap < taps; ++tap, ++seq)
@@ -225,7 +225,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_consta
         const uint32_t kb16 = p.kbytes >> 4, row16 = p.hP * kb16 - (p.ksize - 1) * kb16;
         const uint32_t w16_0 = umma_desc_lo(smem_u32(s_w)), h16_0 = umma_desc_lo(smem_u32(s_halo));
         const uint32_t xl_off = p.h_plane_bytes >> 4;
-        const bool k128 = p.kbytes == 128, issue = !(p.dbg & 8);
+        const bool k128 = p.kbytes == 128, issue = !(B2T_DBG_BITS(p) & 8);
         int ws = 0, g_it = 0, k = 0;
         uint32_t wphase = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
@@ -233,16 +233,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_consta
             decode_item(item, b, y0, x0, cout0, z, c_begin, n_chunks);
             const int n_main = max(1, min(min(p.n_main, Cfg::kTmemCols / N - 1), n_chunks * taps));
             const uint32_t t_corr = tmem_base + n_main * N;
-            const bool tr = p.trace && blockIdx.x == 0 && k < 64 && lane == 0;
-            if (tr) p.trace[k * 8 + 1] = clock64();
+            const bool tr = B2T_TRACE_PTR(p) && blockIdx.x == 0 && k < 64 && lane == 0;
+            if (tr) B2T_TRACE_PTR(p)[k * 8 + 1] = clock64();
             if (k > 0) { mbar_wait(acc_empty, (k - 1) & 1); tc_fence_after(); }   // the epilogue has read the accumulators
-            if (tr) p.trace[k * 8 + 2] = clock64();
+            if (tr) B2T_TRACE_PTR(p)[k * 8 + 2] = clock64();
             int mi = 0;
             uint32_t first = 1, am = 0;
             for (int it = 0; it < n_chunks; ++it, ++g_it) {
                 const int hb = g_it % kHaloBufs;
                 mbar_wait(&halo_full[hb], (g_it / kHaloBufs) & 1);
-                if (tr && it == 0) p.trace[k * 8 + 3] = clock64();
+                if (tr && it == 0) B2T_TRACE_PTR(p)[k * 8 + 3] = clock64();
                 uint32_t xh = h16_0 + hb * (kHaloBufBytes >> 4);
                 int kw = 0;
                 for (int tap = 0; tap < taps; ++tap) {
@@ -273,7 +273,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_consta
                     if (++ws == kWStages) { ws = 0; wphase ^= 1; }
                 }
             }
-            if (tr) p.trace[k * 8 + 7] = clock64();
+            if (tr) B2T_TRACE_PTR(p)[k * 8 + 7] = clock64();
         }
     } else {
         // ===================== epilogue (the patch buffers are dead once accum_bar fires) =====================
@@ -282,15 +282,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_consta
             int b, y0, x0, cout0, z, c_begin, n_chunks;
             decode_item(item, b, y0, x0, cout0, z, c_begin, n_chunks);
             const int n_main = max(1, min(min(p.n_main, Cfg::kTmemCols / N - 1), n_chunks * taps));
-            const bool tr = p.trace && blockIdx.x == 0 && k < 64 && threadIdx.x == 64;
-            if (tr) p.trace[k * 8 + 4] = clock64();
+            const bool tr = B2T_TRACE_PTR(p) && blockIdx.x == 0 && k < 64 && threadIdx.x == 64;
+            if (tr) B2T_TRACE_PTR(p)[k * 8 + 4] = clock64();
             mbar_wait(accum_bar, k & 1);
             tc_fence_after();
-            if (tr) p.trace[k * 8 + 5] = clock64();
+            if (tr) B2T_TRACE_PTR(p)[k * 8 + 5] = clock64();
             halo_epilogue(p, reinterpret_cast<float *>(smem), tmem_base, n_main + 1, N, b, y0, x0, cout0, z, acc_empty);
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (threadIdx.x == 64) mbar_arrive(stage_free);
-            if (tr) p.trace[k * 8 + 6] = clock64();
+            if (tr) B2T_TRACE_PTR(p)[k * 8 + 6] = clock64();
         }
     }
     tc_fence_before();
@@ -386,22 +386,22 @@ conv_halo_persist_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
             for (int ci = 0; ci < p.cin_chunks; ++ci, ++g_chunk) {
                 const int hb = g_chunk & 1;
                 mbar_wait(&patch_empty[hb], ((g_chunk >> 1) & 1) ^ 1);
-                if (p.trace && blockIdx.x == 0 && ci == 0 && g_chunk < 64 && lane == 0) p.trace[g_chunk * 8 + 0] = clock64();
+                if (B2T_TRACE_PTR(p) && blockIdx.x == 0 && ci == 0 && g_chunk < 64 && lane == 0) B2T_TRACE_PTR(p)[g_chunk * 8 + 0] = clock64();
                 uint8_t *hdst = s_patch + hb * kPPatchBytes;
-                const bool skip_x = (p.dbg & 2) && g_chunk >= 2;
+                const bool skip_x = (B2T_DBG_BITS(p) & 2) && g_chunk >= 2;
                 if (elect_one()) {
                     if (skip_x) mbar_arrive(&patch_full[hb]);
                     else {
                         mbar_expect_tx(&patch_full[hb], patch_tx);
-                        tma_load_4d(&tmX_hi, &patch_full[hb], hdst, ci * kelems, x0 - pad, y0 - pad, b, kEvictNormal);
-                        tma_load_4d(&tmX_lo, &patch_full[hb], hdst + p.h_plane_bytes, ci * kelems, x0 - pad, y0 - pad, b, kEvictNormal);
+                        tma_load_4d(&tmX_hi, &patch_full[hb], hdst, ci * kelems, x0 - pad, y0 - pad, b + p.b_in_off, kEvictNormal);
+                        tma_load_4d(&tmX_lo, &patch_full[hb], hdst + p.h_plane_bytes, ci * kelems, x0 - pad, y0 - pad, b + p.b_in_off, kEvictNormal);
                     }
                 }
                 __syncwarp();
                 if (resident) continue;
                 for (int tap = 0; tap < taps; ++tap) {
                     mbar_wait(&w_empty[ws], wphase ^ 1);
-                    const bool skip_w = (p.dbg & 1) && n_loaded >= n_ws;
+                    const bool skip_w = (B2T_DBG_BITS(p) & 1) && n_loaded >= n_ws;
                     if (elect_one()) {
                         if (skip_w) mbar_arrive(&w_full[ws]);
                         else load_w(ws, ci, tap, cout0);
@@ -418,22 +418,22 @@ conv_halo_persist_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
         const uint32_t kb16 = p.kbytes >> 4, row16 = p.hP * kb16 - (p.ksize - 1) * kb16;
         const uint32_t w16_0 = umma_desc_lo(smem_u32(s_w)), p16_0 = umma_desc_lo(smem_u32(s_patch));
         const uint32_t xl_off = p.h_plane_bytes >> 4, wl_off = w_plane >> 4, wt16 = w_tile >> 4, pb16 = kPPatchBytes >> 4;
-        const bool k128 = p.kbytes == 128, issue = !(p.dbg & 8);
+        const bool k128 = p.kbytes == 128, issue = !(B2T_DBG_BITS(p) & 8);
         int g_chunk = 0, j = 0, ws = 0;
         uint32_t wphase = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
             const int ab = j & 1;
-            if (p.trace && blockIdx.x == 0 && j < 64 && lane == 0) p.trace[j * 8 + 1] = clock64();
+            if (B2T_TRACE_PTR(p) && blockIdx.x == 0 && j < 64 && lane == 0) B2T_TRACE_PTR(p)[j * 8 + 1] = clock64();
             mbar_wait(&acc_empty[ab], ((j >> 1) & 1) ^ 1);       // the epilogue has drained this accumulator set
             tc_fence_after();
-            if (p.trace && blockIdx.x == 0 && j < 64 && lane == 0) p.trace[j * 8 + 2] = clock64();
+            if (B2T_TRACE_PTR(p) && blockIdx.x == 0 && j < 64 && lane == 0) B2T_TRACE_PTR(p)[j * 8 + 2] = clock64();
             const uint32_t t_main = tmem_base + ab * 2 * N, t_corr = t_main + N;
             uint32_t acc = 0;                                     // first MMA of the item overwrites
             if (resident) ws = 0;
             for (int ci = 0; ci < p.cin_chunks; ++ci, ++g_chunk) {
                 const int hb = g_chunk & 1;
                 mbar_wait(&patch_full[hb], (g_chunk >> 1) & 1);
-                if (p.trace && blockIdx.x == 0 && j < 64 && lane == 0 && ci == 0) p.trace[j * 8 + 3] = clock64();
+                if (B2T_TRACE_PTR(p) && blockIdx.x == 0 && j < 64 && lane == 0 && ci == 0) B2T_TRACE_PTR(p)[j * 8 + 3] = clock64();
                 uint32_t xh = p16_0 + hb * pb16;
                 int kw = 0;
                 for (int tap = 0; tap < taps; ++tap) {
@@ -468,13 +468,13 @@ conv_halo_persist_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
             int b, y0, x0, cout0;
             decode_item(item, b, y0, x0, cout0);
             const int ab = j & 1;
-            if (p.trace && blockIdx.x == 0 && j < 64 && threadIdx.x == 64) p.trace[j * 8 + 4] = clock64();
+            if (B2T_TRACE_PTR(p) && blockIdx.x == 0 && j < 64 && threadIdx.x == 64) B2T_TRACE_PTR(p)[j * 8 + 4] = clock64();
             mbar_wait(&acc_full[ab], (j >> 1) & 1);
             tc_fence_after();
-            if (p.trace && blockIdx.x == 0 && j < 64 && threadIdx.x == 64) p.trace[j * 8 + 5] = clock64();
+            if (B2T_TRACE_PTR(p) && blockIdx.x == 0 && j < 64 && threadIdx.x == 64) B2T_TRACE_PTR(p)[j * 8 + 5] = clock64();
             halo_epilogue(p, stage, tmem_base + ab * 2 * N, 2, N, b, y0, x0, cout0, 0, &acc_empty[ab]);
             asm volatile("bar.sync 1, 256;" ::: "memory");       // stage buffer free for the next item
-            if (p.trace && blockIdx.x == 0 && j < 64 && threadIdx.x == 64) p.trace[j * 8 + 6] = clock64();
+            if (B2T_TRACE_PTR(p) && blockIdx.x == 0 && j < 64 && threadIdx.x == 64) B2T_TRACE_PTR(p)[j * 8 + 6] = clock64();
         }
     }
     tc_fence_before();

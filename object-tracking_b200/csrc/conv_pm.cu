@@ -129,8 +129,8 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant
                 const int hb = g_chunk & 1;
                 mbar_wait(&patch_empty[hb], ((g_chunk >> 1) & 1) ^ 1);
                 uint8_t *hdst = s_patch + hb * p.pw_patch_bytes;
-                const bool skip_x = (p.dbg & 2) && g_chunk >= 2;
-                if (p.trace && blockIdx.x == 0 && g_chunk < 64 && lane == 0) p.trace[g_chunk * 16 + 0] = clock64();
+                const bool skip_x = (B2T_DBG_BITS(p) & 2) && g_chunk >= 2;
+                if (B2T_TRACE_PTR(p) && blockIdx.x == 0 && g_chunk < 64 && lane == 0) B2T_TRACE_PTR(p)[g_chunk * 16 + 0] = clock64();
                 if (elect_one()) {
                     if (skip_x) mbar_arrive(&patch_full[hb]);
                     else {
@@ -152,11 +152,11 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant
         if (!ints) { mbar_wait(w_full, 0); tc_fence_after(); }
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
             const int ab = j & 1;
-            const bool tr = p.trace && blockIdx.x == 0 && j < 64 && lane == 0;
-            if (tr) p.trace[j * 16 + 1] = clock64();
+            const bool tr = B2T_TRACE_PTR(p) && blockIdx.x == 0 && j < 64 && lane == 0;
+            if (tr) B2T_TRACE_PTR(p)[j * 16 + 1] = clock64();
             mbar_wait(&acc_empty[ab], ((j >> 1) & 1) ^ 1);       // the epilogue has drained this accumulator set
             tc_fence_after();
-            if (tr) p.trace[j * 16 + 2] = clock64();
+            if (tr) B2T_TRACE_PTR(p)[j * 16 + 2] = clock64();
             const uint32_t t_main = tmem_base + ab * 2 * N, t_corr = t_main + N;
             if (ints) {
                 // conv_1: A rows = pixels (16 B each, SBO 128 B, LBO 16 B -> a row spans 4 pixels = K 32);
@@ -164,7 +164,7 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant
                 const int hb = g_chunk & 1;
                 mbar_wait(&patch_full[hb], (g_chunk >> 1) & 1);
                 tc_fence_after();
-                if (tr) p.trace[j * 16 + 3] = clock64();
+                if (tr) B2T_TRACE_PTR(p)[j * 16 + 3] = clock64();
                 const uint32_t a_hi = (128u >> 4) | (1u << 14), b_hi = (512u >> 4) | (1u << 14);
                 const uint32_t xa = p16_0 + hb * pb16;                       // LBO field = 1 (16 B) from umma_desc_lo
                 const uint32_t wb = w16 | ((128u >> 4) << 16);
@@ -183,7 +183,7 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant
                                 const uint64_t dwh = umma_desc_make(wb + kh * (4096 >> 4) + ks * (256 >> 4), b_hi);
                                 const uint64_t dwl = umma_desc_make(wb + kh * (4096 >> 4) + (2048 >> 4) + ks * (256 >> 4), b_hi);
                                 const uint32_t acc = (kh | ks) ? 1u : 0u;
-                                if (p.dbg & 8) continue;
+                                if (B2T_DBG_BITS(p) & 8) continue;
                                 umma_f16(t_buf + r * N, da, dwh, idesc, acc);
                                 umma_f16(t_buf + r * N, da, dwl, idesc, 1u);
                             }
@@ -193,7 +193,7 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant
                     umma_commit(&acc_full[ab]);
                 }
                 __syncwarp();
-                if (tr) p.trace[j * 16 + 4] = clock64();
+                if (tr) B2T_TRACE_PTR(p)[j * 16 + 4] = clock64();
                 ++g_chunk;
                 continue;
             }
@@ -212,11 +212,11 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant
                     const uint32_t xl = xh + xl_off, wl = wh + wl_off;
                     const bool last_tap = tap == taps - 1;
                     if (elect_one()) {
-                        if (!(p.dbg & 8)) {
+                        if (!(B2T_DBG_BITS(p) & 8)) {
                         umma_pm3(t_main, t_corr, xh, xl, wh, wl, dhi, idesc, acc);
                         umma_pm3(t_main, t_corr, xh + 2, xl + 2, wh + 2, wl + 2, dhi, idesc, 1u);
                         }
-                        if (k128 && !(p.dbg & 8)) {
+                        if (k128 && !(B2T_DBG_BITS(p) & 8)) {
                             umma_pm3(t_main, t_corr, xh + 4, xl + 4, wh + 4, wl + 4, dhi, idesc, 1u);
                             umma_pm3(t_main, t_corr, xh + 6, xl + 6, wh + 6, wl + 6, dhi, idesc, 1u);
                         }
@@ -245,11 +245,11 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant
             int b, y0, x0;
             decode_item(item, b, y0, x0);
             const int jj = 2 * k + grp;
-            const bool tr = p.trace && blockIdx.x == 0 && jj < 64 && et == 0;
-            if (tr) p.trace[jj * 16 + 5] = clock64();
+            const bool tr = B2T_TRACE_PTR(p) && blockIdx.x == 0 && jj < 64 && et == 0;
+            if (tr) B2T_TRACE_PTR(p)[jj * 16 + 5] = clock64();
             mbar_wait(&acc_full[grp], k & 1);
             tc_fence_after();
-            if (tr) p.trace[jj * 16 + 6] = clock64();
+            if (tr) B2T_TRACE_PTR(p)[jj * 16 + 6] = clock64();
             if (ints) {
                 // conv_1: the item is one pooled row.  TMEM lane = image column c; the item's buffer holds
                 // [row 0 main | row 0 corr | row 1 main | row 1 corr] x 32 channels.  The 2x2 max-pool runs in
@@ -288,8 +288,8 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant
                 tc_fence_before();
                 if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
                 if (et == 0) mbar_arrive(&acc_empty[grp]);             // TMEM buffer drained by all four warps
-                if (tr) p.trace[jj * 16 + 7] = clock64();
-                if (valid && !(p.dbg & 4)) {
+                if (tr) B2T_TRACE_PTR(p)[jj * 16 + 7] = clock64();
+                if (valid && !(B2T_DBG_BITS(p) & 4)) {
                     const int ch0 = 16 * half_mine;
                     uint32_t hw[8], lw[8];                       // 16 channels as packed fp16 pairs (hi plane, lo plane)
 #pragma unroll
@@ -313,7 +313,7 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant
                     reinterpret_cast<uint4 *>(dst + p.pout.plane_stride)[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                     reinterpret_cast<uint4 *>(dst + p.pout.plane_stride)[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
                 }
-                if (tr) p.trace[jj * 16 + 8] = clock64();
+                if (tr) B2T_TRACE_PTR(p)[jj * 16 + 8] = clock64();
                 continue;
             }
             for (int c0 = 0; c0 < N; c0 += 32) {               // N is a multiple of 32 here (32 or 64)
@@ -338,10 +338,10 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant
             tc_fence_before();
             if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
             if (et == 0) mbar_arrive(&acc_empty[grp]);
-            if (tr) p.trace[jj * 16 + 7] = clock64();
-            if (!(p.dbg & 4)) epilogue_store(p, my_stage, ld, p.pm_glog, b, y0, x0, 0, 0, et, 128);
+            if (tr) B2T_TRACE_PTR(p)[jj * 16 + 7] = clock64();
+            if (!(B2T_DBG_BITS(p) & 4)) epilogue_store(p, my_stage, ld, p.pm_glog, b, y0, x0, 0, 0, et, 128);
             if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
-            if (tr) p.trace[jj * 16 + 8] = clock64();
+            if (tr) B2T_TRACE_PTR(p)[jj * 16 + 8] = clock64();
         }
     }
     tc_fence_before();

@@ -20,6 +20,8 @@ struct Dest {
     int pix_stride_f;
     int ch_off_f;
     int accumulate_f;       // fp32 dest: add to what is there (ConvLSTM recurrent term)
+    long long img_stride_f; // fp32 dest: pixels between consecutive images (0 = H*W, dense); the recurrent conv of
+                            // time step t writes stream s to frame s*T + t of the (S*T)-frame gate buffer
     int H, W;               // spatial dims of the SOURCE tensor the coordinates refer to
     int mode;               // DEST_*
 };
@@ -63,10 +65,21 @@ struct ConvParams {
     const unsigned char *pm_w;   // mode 1: packed weights [kh][plane][32 cout x 32 k, 128-byte core matrices]
     int pm_w_bytes;
     unsigned int magic_tx, magic_ty;   // ceil(2^32 / h_tiles_x), ceil(2^32 / h_tiles_y) (0 when the divisor is 1): fast item decode
-    int dbg;                // developer experiments (0 in production): 1 = weight TMA only for the first ring pass,
-                            // 2 = patch TMA only for the first buffers, 4 = no epilogue stores, 8 = no MMAs (results are wrong)
-    long long *trace;       // developer instrumentation (NULL in production): per-item clock64 stamps of CTA 0
+    int b_in_off;           // added to the image index of the INPUT view only (state slot of the first stream)
+#ifdef B2T_DEV              // developer builds only (make DEV=1); the release library has neither field nor the code behind them
+    int dbg;                // experiments: 1 = weight TMA only for the first ring pass, 2 = patch TMA only for the
+                            // first buffers, 4 = no epilogue stores, 8 = no MMAs (results are wrong)
+    long long *trace;       // per-item clock64 stamps of CTA 0
+#endif
 };
+
+#ifdef B2T_DEV
+#define B2T_DBG_BITS(p) ((p).dbg)
+#define B2T_TRACE_PTR(p) ((p).trace)
+#else
+#define B2T_DBG_BITS(p) 0
+#define B2T_TRACE_PTR(p) (static_cast<long long *>(nullptr))
+#endif
 
 __device__ __forceinline__ float leaky(float v) { return v > 0.f ? v : 0.1f * v; }
 
@@ -121,6 +134,7 @@ __device__ __forceinline__ void emit8(const Dest &d, int b, int y, int x, int c,
         }
     }
     if (d.f32) {
+        if (d.img_stride_f) pix = (long long)b * d.img_stride_f + (long long)y * d.W + x;   // plain mode only
         float *p = d.f32 + pix * d.pix_stride_f + d.ch_off_f + cc;
         if (nvalid == 8 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
             float4 a = make_float4(v[0], v[1], v[2], v[3]), bq = make_float4(v[4], v[5], v[6], v[7]);
@@ -226,6 +240,7 @@ __device__ __forceinline__ void emit1(const Dest &d, int b, int y, int x, int c,
         p[d.plane_stride] = l;
     }
     if (d.f32) {
+        if (d.img_stride_f) pix = (long long)b * d.img_stride_f + (long long)y * d.W + x;   // plain mode only
         float *p = d.f32 + pix * d.pix_stride_f + d.ch_off_f + cc;
         *p = d.accumulate_f ? *p + v : v;
     }

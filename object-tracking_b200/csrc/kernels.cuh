@@ -88,20 +88,25 @@ struct LetterboxParams {
 };
 
 struct ConvLstmGateParams {
-    const float *g;       // (M, 4u) pre-activations (input conv + bias + recurrent conv)
-    float *c;             // (M, u) cell state, in place
-    Dest h_rec;           // h' as split planes for the next recurrent conv
-    Dest h_seq;           // h' as split planes at this time step's slot (input of the 1x1 head)
+    const float *g;       // (S*T, M, 4u) pre-activations (input conv + bias + recurrent conv), frame = s*T + t
+    float *c;             // (slots, M, u) cell state, in place
+    Dest h_rec;           // h' as split planes for the next recurrent conv (image = state slot)
+    Dest h_seq;           // h' as split planes at frame s*T + t (input of the 1x1 head)
     int M, units, G;      // M = G*G pixels of one stream
-    int t;                // time-step slot (batch index in h_seq)
+    int S, T, t;          // streams of this call, steps per stream in the gate buffer, current step
+    int slot0;            // state slot of stream 0
     int hard_sigmoid;
 };
 
 // Launch with programmatic stream serialization (the kernel MUST call griddep_wait() before touching anything its
-// predecessor wrote).  B2T_PDL=0 falls back to a plain launch.
+// predecessor wrote).  Developer builds: B2T_PDL=0 falls back to a plain launch.
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+#ifdef B2T_DEV
     static const bool pdl = !(getenv("B2T_PDL") && atoi(getenv("B2T_PDL")) == 0);
+#else
+    constexpr bool pdl = true;
+#endif
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute at[1];

@@ -457,12 +457,16 @@ __global__ void box_from_heatmap_kernel(const float *heat, int n, int size, floa
 // ---------------------------------------------------------------- ConvLSTM2D gates
 
 __global__ void convlstm_gates_kernel(const ConvLstmGateParams p) {
+    // one thread = 8 units of one pixel of one stream; stream s of this call lives in state slot slot0 + s and its
+    // time step t is frame s*T + t of the gate / h_seq buffers
     const int groups = p.units / 8;
-    const long long total = (long long)p.M * groups;
+    const long long total = (long long)p.S * p.M * groups;
     for (long long tt = blockIdx.x * (long long)blockDim.x + threadIdx.x; tt < total;
          tt += (long long)gridDim.x * blockDim.x) {
-        const int m = int(tt / groups), u0 = int(tt - (long long)m * groups) * 8;
-        const float *g = p.g + (long long)m * 4 * p.units;
+        const int u0 = int(tt % groups) * 8;
+        const int sm = int(tt / groups), s = sm / p.M, m = sm - s * p.M;
+        const float *g = p.g + ((long long)(s * p.T + p.t) * p.M + m) * 4 * p.units;
+        float *c = p.c + ((long long)(p.slot0 + s) * p.M + m) * p.units;
         float h8[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -471,13 +475,13 @@ __global__ void convlstm_gates_kernel(const ConvLstmGateParams p) {
             const float ig = p.hard_sigmoid ? hard_sigmoid_f(zi) : sigmoid_f(zi);
             const float fg = p.hard_sigmoid ? hard_sigmoid_f(zf) : sigmoid_f(zf);
             const float og = p.hard_sigmoid ? hard_sigmoid_f(zo) : sigmoid_f(zo);
-            const float cn = fmaf(fg, p.c[(long long)m * p.units + u], ig * tanhf(zc));
-            p.c[(long long)m * p.units + u] = cn;
+            const float cn = fmaf(fg, c[u], ig * tanhf(zc));
+            c[u] = cn;
             h8[i] = og * tanhf(cn);
         }
         const int y = m / p.G, x = m - y * p.G;
-        emit8(p.h_rec, 0, y, x, u0, p.units, h8);
-        emit8(p.h_seq, p.t, y, x, u0, p.units, h8);
+        emit8(p.h_rec, p.slot0 + s, y, x, u0, p.units, h8);
+        emit8(p.h_seq, s * p.T + p.t, y, x, u0, p.units, h8);
     }
 }
 
@@ -541,7 +545,7 @@ int launch_box_from_heatmap(const float *heat, int n, int size, float thresh, in
     return (int)cudaGetLastError();
 }
 int launch_convlstm_gates(const ConvLstmGateParams &p, cudaStream_t st) {
-    const long long total = (long long)p.M * (p.units / 8);
+    const long long total = (long long)p.S * p.M * (p.units / 8);
     convlstm_gates_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(p);
     return (int)cudaGetLastError();
 }

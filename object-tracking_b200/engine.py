@@ -188,13 +188,14 @@ class DetectorEngine:
 
     # ---------------------------------------------------------------- decode
     def decode(self, logits: torch.Tensor, obj_threshold: float = 0.5, nms_threshold: float = 0.45,
-               anchors: Optional[Sequence[float]] = None, max_boxes: Optional[int] = None):
-        """decode_netout on the device.  logits (B,G,G,A,5+C) fp32 -> (boxes (B,max,8), counts (B))."""
+               anchors: Optional[Sequence[float]] = None, max_boxes: Optional[int] = None, tag: str = ""):
+        """decode_netout on the device.  logits (B,G,G,A,5+C) fp32 -> (boxes (B,max,8), counts (B)).  The result
+        tensors are engine-owned scratch reused by the next decode of the same shape and `tag`."""
         B, gh, gw, nb, d = logits.shape
         anc = self._anchors if anchors is None else (C.c_float * (2 * nb))(*anchors)
         mb = max_boxes or gh * gw * nb
-        boxes = self._buf(("boxes", B, mb), (B, mb, 8), torch.float32)
-        counts = self._buf(("counts", B), (B,), torch.int32)
+        boxes = self._buf(("boxes", B, mb, tag), (B, mb, 8), torch.float32)
+        counts = self._buf(("counts", B, tag), (B,), torch.int32)
         N.check(self.lib.b2t_decode_nms(self.h, logits.data_ptr(), B, gh, gw, nb, d - 5, obj_threshold, nms_threshold,
                                         anc, boxes.data_ptr(), counts.data_ptr(), mb, _stream()))
         return boxes, counts
@@ -273,9 +274,23 @@ class DetectorEngine:
     def convlstm_reset(self) -> None:
         N.check(self.lib.b2t_convlstm_reset(self.h, _stream()))
 
+    def convlstm_reset_slots(self, slot0: int, n: int = 1) -> None:
+        N.check(self.lib.b2t_convlstm_reset_slots(self.h, slot0, n, _stream()))
+
     def convlstm_window(self, B: int, hard_sigmoid: bool = True) -> torch.Tensor:
+        """Frames [0,B) of the last forward = B consecutive steps of one stream (state slot 0, carried over)."""
         out = self._buf(("trk", B), (B, self.grid, self.grid, self.n_box, 5 + self.n_class), torch.float32)
         N.check(self.lib.b2t_convlstm_window(self.h, B, out.data_ptr(), 1 if hard_sigmoid else 0, _stream()))
+        return out
+
+    def convlstm_sequence(self, S: int, T: int, slot0: int = 0, reset: bool = True,
+                          hard_sigmoid: bool = True) -> torch.Tensor:
+        """Frames [0,S*T) of the last forward = S streams x T consecutive steps (frame s*T + t), stream s in state
+        slot slot0 + s -> tracker logits (S*T,G,G,A,5+C).  One batched input conv, T recurrent convs over the S
+        streams, one batched head."""
+        out = self._buf(("trk", S * T), (S * T, self.grid, self.grid, self.n_box, 5 + self.n_class), torch.float32)
+        N.check(self.lib.b2t_convlstm_sequence(self.h, S, T, slot0, 1 if reset else 0, out.data_ptr(),
+                                               1 if hard_sigmoid else 0, _stream()))
         return out
 
     @property
@@ -328,13 +343,14 @@ class LstmHead:
         return y
 
     def step(self, fv: torch.Tensor, det: torch.Tensor, hard_sigmoid: bool = True,
-             out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """fv (S,n_feat), det (S,n_det): rows may be strided views (e.g. x[:, t] of an (S,T,F) tensor)."""
+             out: Optional[torch.Tensor] = None, slot0: int = 0) -> torch.Tensor:
+        """fv (S,n_feat), det (S,n_det): rows may be strided views (e.g. x[:, t] of an (S,T,F) tensor).  The S rows
+        step the state slots [slot0, slot0+S); the other streams keep their (h, c)."""
         S = fv.shape[0]
         if fv.stride(-1) != 1 or det.stride(-1) != 1:
             raise ValueError("feature rows must be contiguous")
         y = out if out is not None else torch.empty((S, self.n_out), dtype=torch.float32, device=fv.device)
-        N.check(self.lib.b2t_lstm_step(self.h, fv.data_ptr(), fv.stride(0) if S > 1 else 0, det.data_ptr(),
-                                       det.stride(0) if S > 1 else 0, S, y.data_ptr(), y.stride(0) if S > 1 else 0,
-                                       1 if hard_sigmoid else 0, _stream()))
+        N.check(self.lib.b2t_lstm_step_slots(self.h, slot0, fv.data_ptr(), fv.stride(0) if S > 1 else 0, det.data_ptr(),
+                                             det.stride(0) if S > 1 else 0, S, y.data_ptr(),
+                                             y.stride(0) if S > 1 else 0, 1 if hard_sigmoid else 0, _stream()))
         return y

@@ -70,7 +70,11 @@ class BaseTracker(object):
     # ------------------------------------------------------------------ new per-frame API
     def reset(self, stream: int = -1):
         self.head.reset(stream)
-        self._steps = 0
+        steps = self.__dict__.setdefault("_stream_steps", {})
+        if stream < 0:
+            steps.clear()
+        else:
+            steps[stream] = 0
 
     def _detect_and_pool(self, frames: torch.Tensor, heat_size: int = 0):
         self.model_detector.engine.forward(frames)
@@ -198,17 +202,33 @@ class BaseTracker(object):
         eng.add_graph_launches(n_kernels)
         return static_out
 
-    def step(self, frame, stream: int = 0) -> np.ndarray:
-        """One frame of one stream (online use).  frame: HWC uint8 array or GPU tensor.  State persists;
-        it is reset every ``sequence_length`` steps like the reference's stateless 4-frame windows."""
-        if self.max_streams != 1 and stream != 0:
-            raise NotImplementedError("per-stream online stepping uses one tracker object per stream")
+    def step(self, frame, det_bbox=None, stream: int = 0) -> np.ndarray:
+        """One frame of stream `stream` (online use).  frame: HWC uint8 array or GPU tensor.
+        det_bbox: optional [cx, cy, w, h] in pixels of the frame that REPLACES the detector's own choice (e.g. the
+        ground-truth box of the first frame, or an external detector's output); None = the highest-probability
+        detection of an allowed class (zeros if none, preprocessing.py:434-449).
+        The (h, c) state of every stream persists in its own slot of the head (max_streams slots) and is reset every
+        ``sequence_length`` steps of that stream, like the reference's stateless 4-frame windows."""
+        if not 0 <= stream < self.max_streams:
+            raise ValueError(f"stream {stream} outside [0, max_streams={self.max_streams})")
+        eng = self.model_detector.engine
         t = torch.as_tensor(np.ascontiguousarray(frame) if isinstance(frame, np.ndarray) else frame)
-        t = t.to(self.model_detector.engine.device)
-        if getattr(self, "_steps", 0) % self.sequence_length == 0:
-            self.head.reset(-1)
-        self._steps = getattr(self, "_steps", 0) + 1
+        t = t.to(eng.device)
+        steps = self.__dict__.setdefault("_stream_steps", {})
+        n = steps.get(stream, 0)
+        if n % self.sequence_length == 0:
+            self.head.reset(stream)
+        steps[stream] = n + 1
         t = t[None].contiguous()
-        self.model_detector.engine.forward(t)
-        fv, xin = self._tracker_inputs_from_state(1, t.shape[2], t.shape[1])
-        return self.head.step(fv, xin)[0].cpu().numpy()
+        H, W = t.shape[1], t.shape[2]
+        eng.forward(t)
+        fv, xin = self._tracker_inputs_from_state(1, W, H)
+        if det_bbox is not None:
+            box = torch.tensor([[float(det_bbox[0]) / W, float(det_bbox[1]) / H, float(det_bbox[2]) / W,
+                                 float(det_bbox[3]) / H]], dtype=torch.float32, device=eng.device)
+            if xin.shape[1] == 4:
+                xin = box
+            else:                                   # heat-map trackers take the box's top-left corner (:452-456)
+                tl = torch.cat([box[:, :2] - box[:, 2:] / 2, box[:, 2:]], dim=1).contiguous()
+                xin = eng.heatmap_from_box(tl, int(round(xin.shape[1] ** 0.5)))
+        return self.head.step(fv, xin, slot0=stream)[0].cpu().numpy()

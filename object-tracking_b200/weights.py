@@ -240,19 +240,40 @@ def synthetic_lstm_weights(n_in: int, units: int, n_out: int, seed: int = 1) -> 
     }
 
 
-def synthetic_convlstm_weights(cin: int, units: int, n_out: int, seed: int = 2) -> Dict[str, np.ndarray]:
+def synthetic_convlstm_weights(cin: int, units: int, n_out: int, seed: int = 2, n_class: int = 0,
+                               head_class_gain: float = 1.0, head_obj_bias: float = 0.0,
+                               head_wh_gain: float = 1.0) -> Dict[str, np.ndarray]:
     """Keras-2 ConvLSTM2D(units,3x3,same) + 1x1 head: kernel (3,3,cin,4u), recurrent_kernel
     (3,3,u,4u), bias (4u,), gate order i,f,c,o; head_kernel (1,1,u,n_out), head_bias
-    (MultiObjDetTracker.py:176-183)."""
+    (MultiObjDetTracker.py:176-183).  With ``n_class`` the head's class columns are scaled by ``head_class_gain``
+    and its objectness bias shifted by ``head_obj_bias`` (n_out = 5*(5+n_class)): a random head never clears the
+    0.5 class-score threshold, the shaped one yields MOT17-like box counts per frame (SURVEY.md section 8d);
+    ``head_wh_gain`` scales the t_w / t_h columns (boxes of a random head are otherwise many images wide)."""
     rng = np.random.default_rng(seed)
     g = lambda *s, sc: (rng.standard_normal(s, dtype=np.float32) * np.float32(sc))
     b = np.zeros(4 * units, np.float32)
     b[units:2 * units] = 1.0
     b += g(4 * units, sc=0.05)
-    return {
+    w = {
         "kernel": g(3, 3, cin, 4 * units, sc=1.0 / np.sqrt(9 * cin)),
         "recurrent_kernel": g(3, 3, units, 4 * units, sc=1.0 / np.sqrt(9 * units)),
         "bias": b,
         "head_kernel": g(1, 1, units, n_out, sc=2.0 / np.sqrt(units)),
         "head_bias": g(n_out, sc=0.1),
     }
+    if n_class:
+        d = 5 + n_class
+        assert n_out == N_BOX * d
+        w["head_kernel"].reshape(units, N_BOX, d)[:, :, 5:] *= np.float32(head_class_gain)
+        w["head_bias"].reshape(N_BOX, d)[:, 5:] *= np.float32(head_class_gain)
+        w["head_bias"].reshape(N_BOX, d)[:, 4] += np.float32(head_obj_bias)
+        w["head_kernel"].reshape(units, N_BOX, d)[:, :, 2:4] *= np.float32(head_wh_gain)
+        w["head_bias"].reshape(N_BOX, d)[:, 2:4] *= np.float32(head_wh_gain)
+    return w
+
+
+def synthetic_multiobj_weights(n_class: int, units: int = 512, seed: int = 2) -> Dict[str, np.ndarray]:
+    """The random-init tracker head MultiObjDetTracker, its tests and bench.py share when no trained checkpoint exists."""
+    n_out = N_BOX * (5 + n_class)
+    return synthetic_convlstm_weights(n_out + 1024, units, n_out, seed=seed, n_class=n_class, head_class_gain=4.0,
+                                      head_obj_bias=-0.3, head_wh_gain=0.25)

@@ -10,6 +10,7 @@ import torch
 from oracle import darknet_oracle, decode_oracle, tracker_oracle, yolo_oracle
 from oracle.cases import DECODE_KINDS, DECODE_SPECS, decode_case
 from object_tracking_b200 import weights as W
+from parity_util import compare_rows
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
@@ -69,7 +70,13 @@ def test_batch_one_and_float_frames_agree(keras_c2):
 
 
 def test_tcgen05_engine_matches_simt_engine(keras_c2):
+    """Developer cross-check engines (make DEV=1 + B2T_USE_DEV_LIB=1); the release library has one conv path."""
     z, w, frames, e = keras_c2
+    if not e.lib.b2t_dev_build():
+        from object_tracking_b200._native import B2TError
+        with pytest.raises(B2TError):
+            _engine(n_class=2, max_batch=2, engine="simt")
+        pytest.skip("release build: the simt / tile engines are compiled out")
     s = _engine(n_class=2, max_batch=2, engine="simt")
     s.set_weights(w)
     s.finalize()
@@ -286,23 +293,7 @@ def test_tiny_tracker_window_end_to_end():
     y_graph2 = trk.track_windows(fr, graph=True).clone()           # replay
     y_eager = trk.track_windows(fr, graph=False)
     assert torch.equal(y_graph, y_eager) and torch.equal(y_graph, y_graph2)
-    # oracle chain
-    w = W.synthetic_yolo_weights(80, seed=0)
-    wl = {k: v.astype(np.float64) for k, v in W.synthetic_lstm_weights(1028, 512, 4, seed=1).items()}
-    o = yolo_oracle.yolo_forward(yolo_oracle.normalize(frames[0]), w, 80, dtype=np.float64, mode="darknet", want=["norm_20"])
-    names = trk.model_detector.names
-    h = np.zeros((1, 512)); c = np.zeros((1, 512))
-    n_with_det = 0
-    for t in range(4):
-        logits = np.transpose(o["logits"][t].reshape(13, 13, -1), (2, 0, 1)).astype(np.float32)
-        region = darknet_oracle.region_forward(logits, 80)
-        boxes, obj, prob = darknet_oracle.detect(region, 416, 416, 416, 416, 0.5, 0.45, 80)
-        lst = [d for d in darknet_oracle.yolo_detect_list(boxes, obj, prob, names) if d[0] in ("person", "car")]
-        n_with_det += bool(lst)
-        det_in = tracker_oracle.detection_to_tracker_input(lst, 416, 416).astype(np.float64)[None]
-        fv = o["norm_20"][t].max(axis=(0, 1))[None]
-        y, h, c = tracker_oracle.tracker_step(fv, det_in, h, c, wl)
-        assert np.abs(y_eager[0, t].cpu().numpy() - y[0]).max() < 1e-3, t
+    # (the oracle chain for this path: tests/test_gpu_parity_r2.py::test_tiny_tracker_positive_detection_branch)
     # online stepping gives the same window
     ys = np.stack([trk.step(frames[0, t]) for t in range(4)])
     assert np.abs(ys - y_eager[0].cpu().numpy()).max() < 1e-5
@@ -379,11 +370,10 @@ def test_heatmap_tracker_window():
     assert tuple(rect.shape) == (2, 4, 4)
 
 
-def test_keras_yolo_and_multiobj_plugins(tmp_path):
-    """KerasYOLO.predict / extract with image files and MultiObjDetTracker.predict (MOT17-shaped, C=12)."""
+def test_keras_yolo_plugin(tmp_path):
+    """KerasYOLO.predict / extract with image files (MultiObjDetTracker.predict: tests/test_gpu_parity_r2.py)."""
     import cv2
     from object_tracking_b200.models_detection.KerasYOLO import KerasYOLO
-    from object_tracking_b200.models_tracking.MultiObjDetTracker import MultiObjDetTracker
     rng = np.random.default_rng(5)
     paths = []
     for i in range(4):
@@ -405,15 +395,6 @@ def test_keras_yolo_and_multiobj_plugins(tmp_path):
         assert a.get_label() == b.get_label() and abs(a.x - b.x) < 1e-3 and abs(a.w - b.w) < 1e-3
     feat = ky.extract(paths[0], "conv_feat")
     assert feat.shape == (13, 13, 1024) and np.abs(feat - o["feat"][0]).max() < 3e-3
-    del ky
-    mt = MultiObjDetTracker(convlstm_units=64)
-    assert mt.CLASS == 12 and mt.detector.BATCH_SIZE == 4
-    outs = [str(tmp_path / f"t{i}.png") for i in range(4)]
-    trk = mt.predict(paths, outs)
-    assert len(trk) == 4 and all(os.path.exists(p) for p in outs)
-    x = np.stack([cv2.resize(cv2.imread(p), (416, 416)) for p in paths])
-    trk2, det2 = mt.track_window(x)
-    assert [len(b) for b in trk2] == [len(b) for b in trk]
 
 
 @pytest.mark.gpu
@@ -488,14 +469,14 @@ def test_benchmark_batch_bbox_parity():
         ref = decode_oracle.boxes_to_array(decode_oracle.decode_netout(o["logits"][b].astype(np.float32), 0.5, 0.45, W.ANCHORS, C))
         n = int(counts.cpu()[b])
         rows = boxes.cpu().numpy()[b, :n].astype(np.float64)
-        # class scores of the oracle that sit within 5e-3 of the threshold may legitimately flip: skip such frames
-        if n != len(ref):
-            sc = ref[:, 4:6] if len(ref) else np.zeros((0, 2))
-            continue
-        checked += 1
-        assert np.array_equal(rows[:, 6:8], ref[:, 6:8]), b             # label, anchor order
-        if n:
-            worst = max(worst, np.abs(rows[:, :4] - ref[:, :4]).max())
+        # boxes are matched by (anchor id, label); a box present on one side only must be explained by a class score
+        # within 5e-3 of the threshold or an IoU on the NMS threshold (tests/parity_util.py)
+        r = compare_rows(rows, ref)
+        assert not r["unexplained"], (b, r["unexplained"])
+        if n == len(ref):
+            checked += 1
+            assert np.array_equal(rows[:, 6:8], ref[:, 6:8]), b         # label, anchor order
+        worst = max(worst, r["worst"])
     assert checked >= B - 2, checked                                    # at most two frames with a threshold flip
     assert worst < 1e-3, worst
 
