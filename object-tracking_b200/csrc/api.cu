@@ -117,6 +117,8 @@ struct b2t_ctx {
     bool finalized = false;
     long launches = 0;
     int n_sm = 148;
+    int chain_max_batch = 8;                      // batches up to this size run conv_2..23 in conv_chain_kernel (0 = never)
+    unsigned int *d_chain_counter = nullptr;      // its grid-barrier arrival counter
     PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
     // b2t_resize_frames: coefficient tables of the last (src, dst) geometry
     int rs_geom[4] = {0, 0, 0, 0};
@@ -293,6 +295,7 @@ extern "C" int b2t_create(const b2t_config *cfg, b2t_ctx **out) {
     b2t_ctx *c = new b2t_ctx();
     c->cfg = *cfg;
     c->keep_prepool = cfg->reserved[0];
+    if (cfg->reserved[1]) c->chain_max_batch = cfg->reserved[1] < 0 ? 0 : cfg->reserved[1];
     c->G = cfg->image_h / 32;
     c->D = 5 + cfg->n_class;
     const int AD = c->A * c->D;
@@ -445,6 +448,7 @@ extern "C" void b2t_destroy(b2t_ctx *c) {
     if (c->own_blob && c->d_blob) cudaFree(c->d_blob);
     if (c->own_ws && c->d_ws) cudaFree(c->d_ws);
     if (c->d_rs_tab) cudaFree(c->d_rs_tab);
+    if (c->d_chain_counter) cudaFree(c->d_chain_counter);
     delete c;
 }
 
@@ -661,6 +665,7 @@ extern "C" int b2t_finalize(b2t_ctx *c, int upload, void *stream) {
             if (c->conv[i].index && !c->conv[i].have_weights) return fail(-1, "conv layer %zu has no weights", i);
     if (!c->d_blob) { CK(cudaMalloc(&c->d_blob, c->weight_bytes)); c->own_blob = true; }
     if (!c->d_ws) { CK(cudaMalloc(&c->d_ws, c->ws_bytes)); c->own_ws = true; }
+    if (!c->d_chain_counter) CK(cudaMalloc(&c->d_chain_counter, 256));
     if (!c->encode) {
         void *fn = nullptr;
         cudaDriverEntryPointQueryResult q;
@@ -785,9 +790,9 @@ static Dest dest_planes(const b2t_ctx *c, int buf, int ch_off, int srcH, int src
 
 // f32_img_stride (pixels, 0 = dense) and in_img_off (images) serve the ConvLSTM recurrent conv: stream s of a step reads
 // state slot in_img_off + s and accumulates into frame s*T + t of the gate buffer.
-static int run_conv(b2t_ctx *c, ConvLayer &l, int B, float *f32_dst, cudaStream_t st, long long f32_img_stride = 0,
-                    int in_img_off = 0) {
-    ConvParams p;
+// layer-independent part of a conv launch's parameter block
+static void base_params(b2t_ctx *c, ConvLayer &l, int B, float *f32_dst, long long f32_img_stride, int in_img_off,
+                        ConvParams &p) {
     memset(&p, 0, sizeof p);
     p.B = B; p.H = l.H; p.W = l.W; p.ksize = l.k; p.cin_chunks = l.cin_pad / l.kchunk; p.Cout = l.cout;
     p.kbytes = l.kchunk * 2;
@@ -810,6 +815,29 @@ static int run_conv(b2t_ctx *c, ConvLayer &l, int B, float *f32_dst, cudaStream_
         p.out.img_stride_f = f32_img_stride;
     }
     p.b_in_off = in_img_off;
+}
+
+// tile geometry + K split of the halo engine (conv_halo_kernel / conv_chain_kernel) for `B` frames
+static int halo_geometry(b2t_ctx *c, ConvLayer &l, int B, ConvParams &p) {
+    p.hC = l.hC; p.hP = l.hP; p.hR = l.hR; p.hN = l.hN; p.h_rows = l.h_rows; p.h_plane_bytes = l.h_plane_bytes;
+    p.h_tiles_x = (l.W + l.hC - 1) / l.hC; p.h_tiles_y = (l.H + l.hR - 1) / l.hR;
+    const int ctas = B * p.h_tiles_x * p.h_tiles_y * ((l.cout + 127) / 128);
+    p.splits = choose_splits_halo(ctas, p.cin_chunks, l.k * l.k, c->n_sm);
+    if (p.splits > 1 && (size_t)p.splits * B * l.H * l.W * p.ldp * 4 > c->partial_bytes)
+        return fail(-2, "internal: split-K workspace too small for conv %d", l.index);
+    return ctas;
+}
+
+// Small batches: can this layer run inside conv_chain_kernel (the big resource shape of the halo engine)?
+static bool chain_eligible(const b2t_ctx *c, const ConvLayer &l) {
+    return c->cfg.engine == B2T_ENGINE_TCGEN05 && l.index >= 2 && l.index <= 23 && l.h_rows * l.hP <= 256 && l.hN <= 256 &&
+           2 * l.h_plane_bytes <= 65536;
+}
+
+static int run_conv(b2t_ctx *c, ConvLayer &l, int B, float *f32_dst, cudaStream_t st, long long f32_img_stride = 0,
+                    int in_img_off = 0) {
+    ConvParams p;
+    base_params(c, l, B, f32_dst, f32_img_stride, in_img_off, p);
     int rc;
 #ifdef B2T_DEV
     if (c->cfg.engine == B2T_ENGINE_SIMT) {
@@ -872,12 +900,8 @@ static int run_conv(b2t_ctx *c, ConvLayer &l, int B, float *f32_dst, cudaStream_
         }
     }
     if (c->cfg.engine == B2T_ENGINE_TCGEN05) {
-        p.hC = l.hC; p.hP = l.hP; p.hR = l.hR; p.hN = l.hN; p.h_rows = l.h_rows; p.h_plane_bytes = l.h_plane_bytes;
-        p.h_tiles_x = (l.W + l.hC - 1) / l.hC; p.h_tiles_y = (l.H + l.hR - 1) / l.hR;
-        const int ctas = B * p.h_tiles_x * p.h_tiles_y * ((l.cout + 127) / 128);
-        p.splits = choose_splits_halo(ctas, p.cin_chunks, l.k * l.k, c->n_sm);
-        if (p.splits > 1 && (size_t)p.splits * B * l.H * l.W * p.ldp * 4 > c->partial_bytes)
-            return fail(-2, "internal: split-K workspace too small for conv %d", l.index);
+        const int ctas = halo_geometry(c, l, B, p);
+        if (ctas < 0) return ctas;
         static const int persist_mode = dev_env("B2T_PERSIST", 2);
         // persistent variant (one CTA per SM, TMEM double buffering) for every short-K layer with enough tiles;
         // B2T_PERSIST=1 restricts it to 1x1 layers and layers whose weights stay resident, 0 disables it
@@ -1030,10 +1054,41 @@ static int forward_impl(b2t_ctx *c, const void *frames, int dtype, int B, float 
         if (ev) cudaEventRecord(ev[1], st);
     }
     float *logits = reinterpret_cast<float *>(c->d_ws + c->off_logits);
+    // small batches: consecutive layers run inside ONE persistent cooperative launch (conv_chain_kernel); per-layer
+    // event timing (b2t_profile_forward) keeps the one-kernel-per-layer schedule
+    const bool chain = !ev && c->chain_max_batch > 0 && B <= c->chain_max_batch && c->d_chain_counter;
+    ChainBuilder *cb = nullptr;
+    auto flush_chain = [&]() -> int {
+        if (!cb) return 0;
+        int r = 0;
+        if (chain_layers(cb) > 0) {
+            r = launch_conv_chain(c->n_sm, cb, st);
+            c->launches += 1;
+        }
+        chain_free(cb);
+        cb = nullptr;
+        return r ? fail(-2, "conv_chain launch: %s", cudaGetErrorString((cudaError_t)r)) : 0;
+    };
     for (int i = first < 2 ? 2 : first; i <= last; ++i) {
-        if ((rc = run_conv(c, c->conv[i], B, i == 23 ? logits : nullptr, st))) return rc;
+        ConvLayer &l = c->conv[i];
+        if (chain && chain_eligible(c, l)) {
+            ConvParams p;
+            base_params(c, l, B, i == 23 ? logits : nullptr, 0, 0, p);
+            const int ctas = halo_geometry(c, l, B, p);
+            if (ctas < 0) { if (cb) chain_free(cb); return ctas; }
+            if (!cb) cb = chain_new(c->d_chain_counter);
+            if (chain_add(cb, l.tmX_hi, l.tmX_lo, l.tmW_hi, l.tmW_lo, p)) {       // full: launch what we have, start anew
+                if ((rc = flush_chain())) return rc;
+                cb = chain_new(c->d_chain_counter);
+                chain_add(cb, l.tmX_hi, l.tmX_lo, l.tmW_hi, l.tmW_lo, p);
+            }
+            continue;
+        }
+        if ((rc = flush_chain())) return rc;
+        if ((rc = run_conv(c, l, B, i == 23 ? logits : nullptr, st))) return rc;
         if (ev) cudaEventRecord(ev[i], st);
     }
+    if ((rc = flush_chain())) return rc;
     if (last == 23 && logits_user && logits_user != logits)
         CK(cudaMemcpyAsync(logits_user, logits, (size_t)B * c->G * c->G * c->A * c->D * 4, cudaMemcpyDeviceToDevice, st));
     return 0;

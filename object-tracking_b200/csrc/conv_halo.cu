@@ -24,6 +24,8 @@
 // * persistent: one CTA per SM walks a static list of (pixel tile, cout tile, K split) items; one elected thread per
 //   role issues (TMA producer warp, MMA warp), all role arithmetic is warp-uniform so that ptxas keeps descriptors in
 //   uniform registers and emits back-to-back UTCHMMA ('The issuing thread').
+#include <string.h>
+
 #include "kernels.cuh"
 
 namespace b2t {
@@ -482,6 +484,268 @@ conv_halo_persist_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
     if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
+// ------------------------------------------------------------------------------------------------
+// conv_chain_kernel -- a RUN of consecutive conv layers in ONE persistent cooperative launch, for small batches
+// (one stream frame by frame, BASELINE configs 2 and 4: 1..8 frames per step).
+//
+// At batch 1 a layer is a few microseconds of MMAs on each SM; launched one kernel per layer (plus a split-K finish
+// kernel) the step is the sum of 40 kernel boundaries: grid drain, launch, barrier init, TMEM allocation, descriptor
+// fetch, first-TMA latency -- 20 us per layer against 2-5 us of work.  Here one grid of gridDim.x = #SM CTAs walks the
+// layer list (kernel parameters carry every layer's ConvParams and TMA descriptors): the main loop of each layer is
+// conv_halo_kernel<big>'s (same roles, barriers, TMEM and weight ring, alive across layers), and layers are
+// separated by a grid barrier (monotonic arrival counter in global memory, release/acquire at gpu scope):
+//   * the producer warp requests the first WEIGHT tiles of layer L+1 before it waits for layer L to complete (weights
+//     do not depend on activations), so the weight stream from HBM -- the roofline of this regime -- keeps flowing
+//     across the barrier;
+//   * a split-K layer is finished in place: after the barrier that says "all partials are written" the 256 epilogue
+//     threads of every CTA reduce a slice of the partial buffer in fixed order (splitk_finish_range, deterministic)
+//     and a second barrier releases the next layer -- no second kernel.
+// Activations written by other SMs' generic stores are read by TMA (async proxy) after an acquire of the counter and
+// a fence.proxy.async; partials are read with ld.global.cg (see splitk_finish_range).
+// The grid barrier needs every CTA resident: the launch is cooperative (refused otherwise), one CTA per SM.
+constexpr int kChainMaxLayers = 20;
+struct alignas(64) ChainLayer {
+    CUtensorMap x_hi, x_lo, w_hi, w_lo;
+    ConvParams p;
+};
+struct alignas(64) ChainParams {
+    ChainLayer L[kChainMaxLayers];
+    unsigned int *counter;        // zeroed by the host before the launch
+    int n_layers;
+};
+static_assert(sizeof(ChainParams) <= 32000, "kernel parameter space (32764 bytes on sm_70+ with CUDA >= 12.1)");
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// one thread: wait until `target` arrivals have been counted; traps instead of hanging the device if that never happens
+__device__ __forceinline__ void grid_wait(const unsigned int *ctr, unsigned int target) {
+    const long long t0 = clock64();
+    while (ld_acquire_gpu(ctr) < target)
+        if (clock64() - t0 > (1ll << 31)) __trap();
+}
+
+__global__ void __launch_bounds__(kHaloThreads, 1) conv_chain_kernel(const __grid_constant__ ChainParams cp) {
+    using Cfg = HaloCfg<false>;
+    constexpr int kHaloBufs = Cfg::kHaloBufs, kHaloBufBytes = Cfg::kHaloBufBytes, kWStages = Cfg::kWStages;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *s_halo = smem;
+    uint8_t *s_w = smem + kHaloBufs * kHaloBufBytes;
+    uint8_t *tail = s_w + kWStages * kWStageBytes;
+    uint64_t *halo_full = reinterpret_cast<uint64_t *>(tail);   // [2]
+    uint64_t *halo_empty = halo_full + 2;                       // [2]
+    uint64_t *w_full = halo_empty + 2;                          // [kWStages]
+    uint64_t *w_empty = w_full + kWStages;                      // [kWStages]
+    uint64_t *accum_bar = w_empty + kWStages;
+    uint64_t *acc_empty = accum_bar + 1;
+    uint64_t *stage_free = acc_empty + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(stage_free + 1);
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform (see above)
+    const unsigned int G = gridDim.x;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < kHaloBufs; ++i) { mbar_init(&halo_full[i], 1); mbar_init(&halo_empty[i], 1); }
+        for (int i = 0; i < kWStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+        mbar_init(accum_bar, 1); mbar_init(acc_empty, 1); mbar_init(stage_free, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+    // item = (pixel tile, cout tile, K split) of one layer; every role walks the same list
+    struct Geo { int gx, gy, n_items, per; };
+    auto geometry = [&](const ConvParams &p) {
+        Geo g;
+        g.gx = p.B * p.h_tiles_x * p.h_tiles_y; g.gy = (p.Cout + 127) >> 7;
+        g.n_items = g.gx * g.gy * p.splits;
+        g.per = (p.cin_chunks + p.splits - 1) / p.splits;
+        return g;
+    };
+    auto decode_item = [&](const ConvParams &p, const Geo &g, int item, int &b, int &y0, int &x0, int &cout0, int &z,
+                           int &c_begin, int &n_chunks) {
+        int t = item % g.gx;
+        const int rest = item / g.gx;
+        const int tx = t % p.h_tiles_x;  t /= p.h_tiles_x;
+        const int ty = t % p.h_tiles_y;
+        b = t / p.h_tiles_y;
+        x0 = tx * p.hC; y0 = ty * p.hR;
+        cout0 = (rest % g.gy) * 128;
+        z = rest / g.gy;
+        c_begin = z * g.per;
+        n_chunks = min(p.cin_chunks, c_begin + g.per) - c_begin;
+    };
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        int ws = 0, g_it = 0, kk = 0;
+        uint32_t wphase = 0;
+        bool prev_hits_w = false;          // the previous item's staged tile reaches into the weight ring
+        unsigned int ready = 0;            // arrivals that complete the previous layer
+        for (int L = 0; L < cp.n_layers; ++L) {
+            const ConvParams &p = cp.L[L].p;
+            const CUtensorMap *tmX_hi = &cp.L[L].x_hi, *tmX_lo = &cp.L[L].x_lo, *tmW_hi = &cp.L[L].w_hi, *tmW_lo = &cp.L[L].w_lo;
+            const Geo g = geometry(p);
+            const int pad = p.ksize >> 1, taps = p.ksize * p.ksize, N = p.hN;
+            const bool stage_hits_w = N * kStageLd * 4 > kHaloBufs * kHaloBufBytes;
+            const uint32_t halo_tx = 2u * p.h_rows * p.hP * p.kbytes, w_tx = 2u * 128u * p.kbytes;
+            const int kelems = p.kbytes / 2;
+            bool input_ready = false;
+            if (lane == 0 && (int)blockIdx.x < g.n_items) {
+                tma_prefetch_desc(tmX_hi); tma_prefetch_desc(tmX_lo);
+                tma_prefetch_desc(tmW_hi); tma_prefetch_desc(tmW_lo);
+            }
+            for (int item = blockIdx.x; item < g.n_items; item += G, ++kk) {
+                int b, y0, x0, cout0, z, c_begin, n_chunks;
+                decode_item(p, g, item, b, y0, x0, cout0, z, c_begin, n_chunks);
+                int w_it = 0, w_tap = 0, w_seq = 0;
+                auto issue_next_w = [&]() {
+                    mbar_wait(&w_empty[ws], wphase ^ 1);
+                    uint8_t *wdst = s_w + ws * kWStageBytes;
+                    const int kcoord = (w_tap * p.cin_chunks + c_begin + w_it) * kelems;
+                    if (elect_one()) {
+                        mbar_expect_tx(&w_full[ws], w_tx);
+                        tma_load_2d(tmW_hi, &w_full[ws], wdst, kcoord, cout0, kEvictLast);
+                        tma_load_2d(tmW_lo, &w_full[ws], wdst + kWTileBytes, kcoord, cout0, kEvictLast);
+                    }
+                    __syncwarp();
+                    ++w_seq;
+                    if (++w_tap == taps) { w_tap = 0; ++w_it; }
+                    if (++ws == kWStages) { ws = 0; wphase ^= 1; }
+                };
+                // weights first: they do not depend on the previous layer (nor on the previous item's staged tile,
+                // unless that tile reaches into the weight ring)
+                if (kk == 0 || !prev_hits_w) {
+                    const int pf = min(kWStages, n_chunks * taps);
+                    while (w_seq < pf) issue_next_w();
+                }
+                if (kk > 0) mbar_wait(stage_free, (kk - 1) & 1);     // the previous item's staged tile has left the patch buffers
+                if (!input_ready) {
+                    if (L > 0) {                                     // the previous layer is complete on every SM
+                        if (lane == 0) grid_wait(cp.counter, ready);
+                        __syncwarp();
+                        asm volatile("fence.proxy.async.global;" ::: "memory");   // generic-proxy stores -> TMA reads
+                    }
+                    input_ready = true;
+                }
+                int seq = 0;
+                for (int it = 0; it < n_chunks; ++it, ++g_it) {
+                    const int ci = c_begin + it, hb = g_it % kHaloBufs;
+                    mbar_wait(&halo_empty[hb], ((g_it / kHaloBufs) & 1) ^ 1);
+                    uint8_t *hdst = s_halo + hb * kHaloBufBytes;
+                    if (elect_one()) {
+                        mbar_expect_tx(&halo_full[hb], halo_tx);
+                        tma_load_4d(tmX_hi, &halo_full[hb], hdst, ci * kelems, x0 - pad, y0 - pad, b, kEvictNormal);
+                        tma_load_4d(tmX_lo, &halo_full[hb], hdst + p.h_plane_bytes, ci * kelems, x0 - pad, y0 - pad, b, kEvictNormal);
+                    }
+                    __syncwarp();
+                    for (int tap = 0; tap < taps; ++tap, ++seq)
+                        if (seq == w_seq) issue_next_w();
+                }
+                prev_hits_w = stage_hits_w;
+            }
+            ready += G * (p.splits > 1 ? 2u : 1u);
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (warp-uniform arithmetic, one elected lane issues) =====================
+        const uint32_t w16_0 = umma_desc_lo(smem_u32(s_w)), h16_0 = umma_desc_lo(smem_u32(s_halo));
+        int ws = 0, g_it = 0, kk = 0;
+        uint32_t wphase = 0;
+        for (int L = 0; L < cp.n_layers; ++L) {
+            const ConvParams &p = cp.L[L].p;
+            const Geo g = geometry(p);
+            const int taps = p.ksize * p.ksize, N = p.hN;
+            const uint32_t idesc = umma_idesc_f16(128, N), dhi = umma_desc_hi(p.kbytes);
+            const uint32_t kb16 = p.kbytes >> 4, row16 = p.hP * kb16 - (p.ksize - 1) * kb16;
+            const uint32_t xl_off = p.h_plane_bytes >> 4;
+            const bool k128 = p.kbytes == 128;
+            for (int item = blockIdx.x; item < g.n_items; item += G, ++kk) {
+                int b, y0, x0, cout0, z, c_begin, n_chunks;
+                decode_item(p, g, item, b, y0, x0, cout0, z, c_begin, n_chunks);
+                const int n_main = max(1, min(min(p.n_main, Cfg::kTmemCols / N - 1), n_chunks * taps));
+                const uint32_t t_corr = tmem_base + n_main * N;
+                if (kk > 0) { mbar_wait(acc_empty, (kk - 1) & 1); tc_fence_after(); }   // the epilogue has read the accumulators
+                int mi = 0;
+                uint32_t first = 1, am = 0;
+                for (int it = 0; it < n_chunks; ++it, ++g_it) {
+                    const int hb = g_it % kHaloBufs;
+                    mbar_wait(&halo_full[hb], (g_it / kHaloBufs) & 1);
+                    uint32_t xh = h16_0 + hb * (kHaloBufBytes >> 4);
+                    int kw = 0;
+                    for (int tap = 0; tap < taps; ++tap) {
+                        mbar_wait(&w_full[ws], wphase);
+                        tc_fence_after();
+                        const uint32_t wh = w16_0 + ws * (kWStageBytes >> 4), wl = wh + (kWTileBytes >> 4);
+                        const uint32_t xl = xh + xl_off;
+                        const uint32_t t_main = tmem_base + mi * N;
+                        const uint32_t ac = first ^ 1u;
+                        const bool last_tap = tap == taps - 1;
+                        if (elect_one()) {
+                            umma_kstep(t_main, t_corr, wh, wl, xh, xl, dhi, idesc, am, ac);
+                            umma_kstep(t_main, t_corr, wh + 2, wl + 2, xh + 2, xl + 2, dhi, idesc, 1u, 1u);
+                            if (k128) {
+                                umma_kstep(t_main, t_corr, wh + 4, wl + 4, xh + 4, xl + 4, dhi, idesc, 1u, 1u);
+                                umma_kstep(t_main, t_corr, wh + 6, wl + 6, xh + 6, xl + 6, dhi, idesc, 1u, 1u);
+                            }
+                            umma_commit(&w_empty[ws]);
+                            if (last_tap) umma_commit(&halo_empty[hb]);
+                            if (last_tap && it == n_chunks - 1) umma_commit(accum_bar);
+                        }
+                        __syncwarp();
+                        first = 0;
+                        if (++mi == n_main) { mi = 0; am = 1; }
+                        if (++kw == p.ksize) { kw = 0; xh += row16; } else xh += kb16;
+                        if (++ws == kWStages) { ws = 0; wphase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue + grid barrier + split-K finish =====================
+        const int et = threadIdx.x - 64;
+        int kk = 0;
+        unsigned int done = 0;
+        for (int L = 0; L < cp.n_layers; ++L) {
+            const ConvParams &p = cp.L[L].p;
+            const Geo g = geometry(p);
+            const int taps = p.ksize * p.ksize, N = p.hN;
+            for (int item = blockIdx.x; item < g.n_items; item += G, ++kk) {
+                int b, y0, x0, cout0, z, c_begin, n_chunks;
+                decode_item(p, g, item, b, y0, x0, cout0, z, c_begin, n_chunks);
+                const int n_main = max(1, min(min(p.n_main, Cfg::kTmemCols / N - 1), n_chunks * taps));
+                mbar_wait(accum_bar, kk & 1);
+                tc_fence_after();
+                halo_epilogue(p, reinterpret_cast<float *>(smem), tmem_base, n_main + 1, N, b, y0, x0, cout0, z, acc_empty);
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (threadIdx.x == 64) mbar_arrive(stage_free);
+            }
+            // this CTA's part of layer L is in global memory: arrive on the grid barrier
+            __threadfence();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (et == 0) atomicAdd(cp.counter, 1u);
+            done += G;
+            if (p.splits > 1) {
+                if (et == 0) { grid_wait(cp.counter, done); __threadfence(); }     // every CTA's partials are written
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                splitk_finish_range(p, (long long)blockIdx.x * kEpiThreads + et, (long long)G * kEpiThreads);
+                __threadfence();
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (et == 0) atomicAdd(cp.counter, 1u);
+                done += G;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
 int conv_halo_init() {
     cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          HaloCfg<false>::kSmemBytes);
@@ -492,7 +756,43 @@ int conv_halo_init() {
     e = cudaFuncSetAttribute(conv_halo_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(conv_halo_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(conv_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<false>::kSmemBytes);
     return (int)e;
+}
+
+// ---- conv_chain_kernel host side: the parameter block is assembled layer by layer by api.cu
+struct ChainBuilder { ChainParams cp; };
+ChainBuilder *chain_new(unsigned int *counter) {
+    ChainBuilder *b = new ChainBuilder();
+    memset(&b->cp, 0, sizeof b->cp);
+    b->cp.counter = counter;
+    return b;
+}
+void chain_free(ChainBuilder *b) { delete b; }
+int chain_add(ChainBuilder *b, const CUtensorMap &x_hi, const CUtensorMap &x_lo, const CUtensorMap &w_hi,
+              const CUtensorMap &w_lo, const ConvParams &p) {
+    if (b->cp.n_layers >= kChainMaxLayers) return -1;
+    ChainLayer &l = b->cp.L[b->cp.n_layers++];
+    l.x_hi = x_hi; l.x_lo = x_lo; l.w_hi = w_hi; l.w_lo = w_lo; l.p = p;
+    return 0;
+}
+int chain_layers(const ChainBuilder *b) { return b->cp.n_layers; }
+int launch_conv_chain(int n_sm, const ChainBuilder *b, cudaStream_t st) {
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, conv_chain_kernel, kHaloThreads,
+                                                                  HaloCfg<false>::kSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    if (per_sm < 1) return (int)cudaErrorCooperativeLaunchTooLarge;
+    e = cudaMemsetAsync(b->cp.counter, 0, sizeof(unsigned int), st);
+    if (e != cudaSuccess) return (int)e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_sm); cfg.blockDim = dim3(kHaloThreads); cfg.dynamicSmemBytes = HaloCfg<false>::kSmemBytes; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, conv_chain_kernel, b->cp);
 }
 
 int launch_conv_halo_persist(int n_sm, const CUtensorMap &x_hi, const CUtensorMap &x_lo, const CUtensorMap &w_hi,

@@ -246,4 +246,52 @@ __device__ __forceinline__ void emit1(const Dest &d, int b, int y, int x, int c,
     }
 }
 
+// Finishes a split-K convolution: fixed-order sum of the raw fp32 partials, scale/bias/leaky, optional 2x2 max-pool,
+// hi/lo split, same destinations as the fused epilogue.  One work item = 8 channels of one pixel (or of one 2x2 quad
+// when pooling); the caller walks items start, start + step, ...  The partials are read with ld.global.cg: inside
+// conv_chain_kernel they were written by other SMs of the SAME grid, and an L1 line of an earlier layer's partials at
+// the same address would be stale.
+__device__ __forceinline__ void splitk_finish_range(const ConvParams &p, long long start, long long step) {
+    const int cgroups = (p.Cout + 7) / 8;
+    const int Hq = p.pool ? p.H / 2 : p.H, Wq = p.pool ? p.W / 2 : p.W;
+    const long long total = (long long)p.B * Hq * Wq * cgroups;
+    const long long mtot = (long long)p.B * p.H * p.W;
+    for (long long t = start; t < total; t += step) {
+        const int cg = int(t % cgroups);
+        long long q = t / cgroups;
+        const int xq = int(q % Wq);  q /= Wq;
+        const int yq = int(q % Hq);
+        const int b = int(q / Hq);
+        const int c = cg * 8;
+        float s8[8], b8[8], mx[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const bool ok = c + i < p.Cout;
+            s8[i] = ok ? __ldg(p.scale + c + i) : 0.f;
+            b8[i] = ok ? __ldg(p.bias + c + i) : 0.f;
+            mx[i] = -INFINITY;
+        }
+        const int npix = p.pool ? 4 : 1;
+        for (int k = 0; k < npix; ++k) {
+            const int y = p.pool ? 2 * yq + (k >> 1) : yq, x = p.pool ? 2 * xq + (k & 1) : xq;
+            const long long pix = ((long long)b * p.H + y) * p.W + x;
+            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int z = 0; z < p.splits; ++z) {  // ldp is a multiple of 32 -> both float4 are in bounds
+                const float4 *src = reinterpret_cast<const float4 *>(p.partial + ((long long)z * mtot + pix) * p.ldp + c);
+                const float4 a = __ldcg(src), bq = __ldcg(src + 1);
+                v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+                v[4] += bq.x; v[5] += bq.y; v[6] += bq.z; v[7] += bq.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float tt = fmaf(v[i], s8[i], b8[i]);
+                v[i] = p.act ? leaky(tt) : tt;
+                mx[i] = fmaxf(mx[i], v[i]);
+            }
+            if (p.out.hi || p.out.f32) emit8(p.out, b, y, x, c, p.Cout, v);
+        }
+        if (p.pool) emit8(p.pout, b, yq, xq, c, p.Cout, mx);
+    }
+}
+
 }  // namespace b2t

@@ -124,6 +124,14 @@ int launch_conv_halo(int n_sm, bool small, const CUtensorMap &x_hi, const CUtens
                      const CUtensorMap &w_lo, const ConvParams &p, cudaStream_t st);
 int launch_conv_halo_persist(int n_sm, const CUtensorMap &x_hi, const CUtensorMap &x_lo, const CUtensorMap &w_hi,
                              const CUtensorMap &w_lo, const ConvParams &p, cudaStream_t st);
+// conv_chain_kernel: a run of layers in one persistent cooperative launch (small batches); parameters built layer by layer
+struct ChainBuilder;
+ChainBuilder *chain_new(unsigned int *counter_dev);
+void chain_free(ChainBuilder *b);
+int chain_add(ChainBuilder *b, const CUtensorMap &x_hi, const CUtensorMap &x_lo, const CUtensorMap &w_hi,
+              const CUtensorMap &w_lo, const ConvParams &p);      // -1 = full
+int chain_layers(const ChainBuilder *b);
+int launch_conv_chain(int n_sm, const ChainBuilder *b, cudaStream_t st);
 int conv_pm_init();
 int conv_pm_smem_bytes(const ConvParams &p);
 int launch_conv_pm(int n_sm, const CUtensorMap &x_hi, const CUtensorMap &x_lo, const CUtensorMap &w_hi,

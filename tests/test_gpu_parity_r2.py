@@ -347,3 +347,32 @@ def test_c5_608_batch8_heatmap_tracker_pool_max():
         yy, h, c = tracker_oracle.tracker_step(ref_fv[None], heat[s][None].astype(np.float64), h, c, wl)
         assert np.abs(y[s, 0] - yy[0]).max() < 1e-3, s
     assert (chosen.cpu().numpy() >= 0).sum() >= 2
+
+
+# ------------------------------------------------------------------------------------------------ small-batch schedule
+@pytest.mark.parametrize("B", [1, 3, 8])
+def test_chain_schedule_matches_per_layer_schedule(B):
+    """conv_chain_kernel (conv_2..23 in one persistent cooperative launch, grid barrier between layers, split-K finished
+    in place) against the one-kernel-per-layer schedule and the fp64 oracle, every kept layer."""
+    C = 2
+    w = W.synthetic_yolo_weights(C, seed=0)
+    frames = np.random.default_rng(40 + B).integers(0, 256, (B, 416, 416, 3), dtype=np.uint8)
+    fr = torch.from_numpy(frames).cuda()
+    a = _engine(n_class=C, max_batch=B)                          # default: chain for B <= 8
+    b = _engine(n_class=C, max_batch=B, chain_max_batch=-1)      # never
+    for e in (a, b):
+        e.set_weights(w)
+        e.finalize()
+    la, lb = a.forward(fr).clone(), b.forward(fr).clone()
+    assert a.launches < b.launches - 15                          # 3 launches instead of ~40
+    assert (la - lb).abs().max().item() < 3e-4                   # conv_2 / conv_4 take a different kernel, same maths
+    names = [f"norm_{i}" for i in (3, 4, 6, 7, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20)] + ["concat", "conv_feat"]
+    o = yolo_oracle.yolo_forward(yolo_oracle.normalize(frames), w, C, dtype=np.float64, want=names)
+    for n in names:
+        got = a.extract(n, B).cpu().numpy()
+        ref = o[n] if n != "conv_feat" else o["feat"]
+        rel = np.abs(got - ref).max() / np.abs(ref).max()
+        assert rel < 2e-5, (n, rel)
+    assert np.abs(la.cpu().numpy() - o["logits"]).max() < 5e-4
+    # replays are bit-identical (fixed-order split-K finish, no atomics on data)
+    assert torch.equal(a.forward(fr), la)
