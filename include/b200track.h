@@ -49,7 +49,8 @@ typedef struct {
     int convlstm_units;       /* 0 = no MultiObjDetTracker head; else ConvLSTM2D filters (512)   */
     int reserved[7];          /* reserved[0] = 1: also keep the pre-pool outputs of conv_1,2,5,8 (KerasYOLO.extract)
                                  reserved[1]: largest batch that runs conv_2..23 as ONE persistent cooperative launch
-                                 (conv_chain_kernel, the small-batch schedule); 0 = default (8), -1 = never           */
+                                 (conv_chain_kernel, the batch-1 schedule); 0 = default (1: measured faster only
+                                 for a single frame, profiles/r2_batch_sweep_416.txt), -1 = never                        */
 } b2t_config;
 
 const char *b2t_last_error(void);

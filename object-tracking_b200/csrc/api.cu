@@ -117,7 +117,7 @@ struct b2t_ctx {
     bool finalized = false;
     long launches = 0;
     int n_sm = 148;
-    int chain_max_batch = 8;                      // batches up to this size run conv_2..23 in conv_chain_kernel (0 = never)
+    int chain_max_batch = 1;                      // batches up to this size run conv_2..23 in conv_chain_kernel (0 = never)
     unsigned int *d_chain_counter = nullptr;      // its grid-barrier arrival counter
     PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
     // b2t_resize_frames: coefficient tables of the last (src, dst) geometry
@@ -164,6 +164,9 @@ static void choose_halo_tile(int H, int W, int ksize, bool pool, ConvLayer &l) {
         if (pool && (P & 1)) continue;
         for (int R = 1; R <= H; ++R) {
             if (pool && (R & 1)) continue;
+            // the reorg layer's epilogue is a per-element scatter (2-byte stores): keep its tiles small so that even one
+            // frame spreads over many SMs -- its MMA time is negligible (0.04 GFLOP)
+            if (l.index == 21 && R > 2) break;
             const int rows = R + 2 * pad + (wrap ? 1 : 0);
             const int N = round_up(R * P, 16);
             if (rows * P > max_rows || N > max_n || (pool && N > 240)) break;
@@ -220,6 +223,28 @@ static int choose_splits_halo(int ctas, int cin_chunks, int taps, int n_sm) {
         if (per * taps * 4 > chain_cap && s < max_s) continue;
         const long waves = ((long)ctas * s + n_sm - 1) / n_sm;
         const double cost = (double)waves * (per * taps + 10.0) + (s > 1 ? 3.0 * s : 0.0);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best_s = s; }
+    }
+    return best_s;
+}
+
+// K split of conv_chain_kernel (small batches): in units of one (channel chunk, tap) pair = 12 MMAs.  The split-K
+// reduction costs a grid barrier + an in-place finish there, not a second kernel, and idle SMs are the dominant loss at
+// batch 1, so the split is much finer than choose_splits_halo's.  Cost in units: one wave of items = per + ~4 (first
+// patch latency + epilogue), a reduction = ~6 + 0.15 per split.
+static int choose_splits_chain(int ctas, int units, int n_sm) {
+    static const int chain_cap = dev_env("B2T_CHAIN", 320);
+    int best_s = 1;
+    double best_cost = 1e30;
+    for (int s = 1; s <= 32 && s <= units; ++s) {
+        const int per = (units + s - 1) / s;
+        if ((units + per - 1) / per != s) continue;
+        if (per * 4 > chain_cap && s < 32 && s < units) continue;    // keep one accumulation chain short
+        const long waves = ((long)ctas * s + n_sm - 1) / n_sm;
+        // measured on B200 (profiles/r2_chain_trace_b1.txt), in units of 12 MMAs ~ 1.2k clocks: first-patch latency ~1.5,
+        // staged epilogue of an unsplit item ~7 (few CTAs format the whole output), register-to-partial epilogue of a
+        // split item ~4, then barrier + in-place finish (every SM formats a slice) + barrier ~9
+        const double cost = s == 1 ? (double)waves * (per + 8.5) : (double)waves * (per + 5.5) + 9.0 + 0.1 * s;
         if (cost < best_cost - 1e-9) { best_cost = cost; best_s = s; }
     }
     return best_s;
@@ -426,6 +451,10 @@ extern "C" int b2t_create(const b2t_config *cfg, b2t_ctx **out) {
             if (cfg->engine == B2T_ENGINE_TCGEN05) {
                 const int ctas = ((l.W + l.hC - 1) / l.hC) * ((l.H + l.hR - 1) / l.hR) * ((l.cout + 127) / 128) * bsz;
                 s = choose_splits_halo(ctas, l.cin_pad / l.kchunk, l.k * l.k, 148);
+                if (bsz <= c->chain_max_batch) {
+                    const size_t s2 = choose_splits_chain(ctas, l.cin_pad / l.kchunk * l.k * l.k, 148);
+                    if (s2 > s) s = s2;
+                }
                 if (s == 1) continue;
             }
             const size_t need = s * (size_t)bsz * l.H * l.W * ldp * 4;
@@ -818,11 +847,17 @@ static void base_params(b2t_ctx *c, ConvLayer &l, int B, float *f32_dst, long lo
 }
 
 // tile geometry + K split of the halo engine (conv_halo_kernel / conv_chain_kernel) for `B` frames
-static int halo_geometry(b2t_ctx *c, ConvLayer &l, int B, ConvParams &p) {
+static int halo_geometry(b2t_ctx *c, ConvLayer &l, int B, ConvParams &p, bool chain = false) {
     p.hC = l.hC; p.hP = l.hP; p.hR = l.hR; p.hN = l.hN; p.h_rows = l.h_rows; p.h_plane_bytes = l.h_plane_bytes;
     p.h_tiles_x = (l.W + l.hC - 1) / l.hC; p.h_tiles_y = (l.H + l.hR - 1) / l.hR;
     const int ctas = B * p.h_tiles_x * p.h_tiles_y * ((l.cout + 127) / 128);
-    p.splits = choose_splits_halo(ctas, p.cin_chunks, l.k * l.k, c->n_sm);
+    if (chain) {
+        const int units = p.cin_chunks * l.k * l.k;
+        p.splits = choose_splits_chain(ctas, units, c->n_sm);
+        p.k_per_units = (units + p.splits - 1) / p.splits;
+    } else {
+        p.splits = choose_splits_halo(ctas, p.cin_chunks, l.k * l.k, c->n_sm);
+    }
     if (p.splits > 1 && (size_t)p.splits * B * l.H * l.W * p.ldp * 4 > c->partial_bytes)
         return fail(-2, "internal: split-K workspace too small for conv %d", l.index);
     return ctas;
@@ -1058,12 +1093,29 @@ static int forward_impl(b2t_ctx *c, const void *frames, int dtype, int B, float 
     // event timing (b2t_profile_forward) keeps the one-kernel-per-layer schedule
     const bool chain = !ev && c->chain_max_batch > 0 && B <= c->chain_max_batch && c->d_chain_counter;
     ChainBuilder *cb = nullptr;
+#ifdef B2T_DEV
+    static long long *chain_trace = nullptr;
+    int chain_idx[32], chain_splits[32];
+    if (dev_env("B2T_TRACE_CONV", 0) == 100 && !chain_trace) cudaMalloc(&chain_trace, 24 * 8 * 8);
+#endif
     auto flush_chain = [&]() -> int {
         if (!cb) return 0;
         int r = 0;
         if (chain_layers(cb) > 0) {
             r = launch_conv_chain(c->n_sm, cb, st);
             c->launches += 1;
+#ifdef B2T_DEV
+            if (!r && chain_trace) {
+                long long h[24 * 8];
+                cudaStreamSynchronize(st);
+                cudaMemcpy(h, chain_trace, sizeof h, cudaMemcpyDeviceToHost);
+                fprintf(stderr, "[trace chain B=%d] layer: input_ready patch_ok w_ok | epi: acc_ok items_done barrier_A done (clocks rel. to the first stamp)\n", B);
+                long long t0 = h[0];
+                for (int j = 0; j < chain_layers(cb); ++j)
+                    fprintf(stderr, "  conv_%-2d splits=%-2d: %8lld %8lld %8lld | %8lld %8lld %8lld %8lld\n", chain_idx[j], chain_splits[j], h[j * 8] - t0,
+                            h[j * 8 + 1] - t0, h[j * 8 + 2] - t0, h[j * 8 + 3] - t0, h[j * 8 + 4] - t0, h[j * 8 + 5] - t0, h[j * 8 + 6] - t0);
+            }
+#endif
         }
         chain_free(cb);
         cb = nullptr;
@@ -1074,9 +1126,13 @@ static int forward_impl(b2t_ctx *c, const void *frames, int dtype, int B, float 
         if (chain && chain_eligible(c, l)) {
             ConvParams p;
             base_params(c, l, B, i == 23 ? logits : nullptr, 0, 0, p);
-            const int ctas = halo_geometry(c, l, B, p);
+            const int ctas = halo_geometry(c, l, B, p, true);
             if (ctas < 0) { if (cb) chain_free(cb); return ctas; }
             if (!cb) cb = chain_new(c->d_chain_counter);
+#ifdef B2T_DEV
+            if (chain_trace && chain_layers(cb) == 0) { cudaMemsetAsync(chain_trace, 0, 24 * 8 * 8, st); p.trace = chain_trace; }
+            if (chain_layers(cb) < 32) { chain_idx[chain_layers(cb)] = i; chain_splits[chain_layers(cb)] = p.splits; }
+#endif
             if (chain_add(cb, l.tmX_hi, l.tmX_lo, l.tmW_hi, l.tmW_lo, p)) {       // full: launch what we have, start anew
                 if ((rc = flush_chain())) return rc;
                 cb = chain_new(c->d_chain_counter);

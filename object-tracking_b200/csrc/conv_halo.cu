@@ -503,7 +503,7 @@ conv_halo_persist_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __gri
 // Activations written by other SMs' generic stores are read by TMA (async proxy) after an acquire of the counter and
 // a fence.proxy.async; partials are read with ld.global.cg (see splitk_finish_range).
 // The grid barrier needs every CTA resident: the launch is cooperative (refused otherwise), one CTA per SM.
-constexpr int kChainMaxLayers = 20;
+constexpr int kChainMaxLayers = 22;               // conv_2 .. conv_23
 struct alignas(64) ChainLayer {
     CUtensorMap x_hi, x_lo, w_hi, w_lo;
     ConvParams p;
@@ -515,10 +515,57 @@ struct alignas(64) ChainParams {
 };
 static_assert(sizeof(ChainParams) <= 32000, "kernel parameter space (32764 bytes on sm_70+ with CUDA >= 12.1)");
 
+// Epilogue of a split-K item: raw fp32 sums go straight from registers to the partial buffer
+// [split][pixel][channel].  A thread owns one output channel (its TMEM lane) and half of the tile's pixel columns; the
+// 32 lanes of a warp are 32 consecutive channels, so every store instruction writes 128 contiguous bytes of one
+// pixel -- no shared-memory staging and no second pass.
+__device__ __forceinline__ void chain_partial_epilogue(const ConvParams &p, uint32_t tmem_acc, int n_acc, int N, int b, int y0,
+                                                       int x0, int cout0, int zsplit, uint64_t *acc_free) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int ch = cout0 + q * 32 + lane;
+    const bool ch_ok = ch < p.ldp;
+    const uint32_t lane_addr = tmem_acc + (uint32_t(q * 32) << 16);
+    const int rows_valid = min(p.hR, p.H - y0), cols_valid = min(p.hC, p.W - x0);
+    const long long mtot = (long long)p.B * p.H * p.W;
+    float *base = p.partial + ((long long)zsplit * mtot + ((long long)b * p.H + y0) * p.W + x0) * p.ldp + ch;
+#pragma unroll 1
+    for (int n0 = half * 16; n0 < N; n0 += 32) {
+        uint32_t a[16], c2[16];
+        float v[16];
+        tmem_ld16(lane_addr + n0, a);
+        tmem_ld16(lane_addr + (n_acc - 1) * N + n0, c2);   // the correction accumulator is the last one
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(a[i]) + __uint_as_float(c2[i]);
+#pragma unroll 1
+        for (int m = 1; m < n_acc - 1; ++m) {
+            tmem_ld16(lane_addr + m * N + n0, a);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += __uint_as_float(a[i]);
+        }
+        int r = small_div(n0, p.hP), c = n0 - r * p.hP;     // column n = r*hP + c of the tile
+        float *ptr = base + ((long long)r * p.W + c) * p.ldp;
+        const long long wrap = (long long)(p.W - p.hP + 1) * p.ldp;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if (ch_ok && r < rows_valid && c < cols_valid) *ptr = v[i];
+            if (++c == p.hP) { c = 0; ++r; ptr += wrap; } else ptr += p.ldp;
+        }
+    }
+    tc_fence_before();
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (acc_free && threadIdx.x == 64) mbar_arrive(acc_free);
+}
+
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p) {
     unsigned int v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ void grid_arrive(unsigned int *ctr) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
 }
 // one thread: wait until `target` arrivals have been counted; traps instead of hanging the device if that never happens
 __device__ __forceinline__ void grid_wait(const unsigned int *ctr, unsigned int target) {
@@ -560,16 +607,19 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_chain_kernel(const __gri
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     // item = (pixel tile, cout tile, K split) of one layer; every role walks the same list
-    struct Geo { int gx, gy, n_items, per; };
+    // The K dimension is split in units of one (channel chunk, tap) pair = 12 MMAs, chunk-major: finer than whole
+    // chunks, so that a 13x13 layer at batch 1 (8 cout tiles x 72 units) spreads over every SM.  Split z owns units
+    // [u0, u0 + n_units).
+    struct Geo { int gx, gy, n_items, units; };
     auto geometry = [&](const ConvParams &p) {
         Geo g;
         g.gx = p.B * p.h_tiles_x * p.h_tiles_y; g.gy = (p.Cout + 127) >> 7;
         g.n_items = g.gx * g.gy * p.splits;
-        g.per = (p.cin_chunks + p.splits - 1) / p.splits;
+        g.units = p.cin_chunks * p.ksize * p.ksize;
         return g;
     };
     auto decode_item = [&](const ConvParams &p, const Geo &g, int item, int &b, int &y0, int &x0, int &cout0, int &z,
-                           int &c_begin, int &n_chunks) {
+                           int &u0, int &n_units) {
         int t = item % g.gx;
         const int rest = item / g.gx;
         const int tx = t % p.h_tiles_x;  t /= p.h_tiles_x;
@@ -578,8 +628,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_chain_kernel(const __gri
         x0 = tx * p.hC; y0 = ty * p.hR;
         cout0 = (rest % g.gy) * 128;
         z = rest / g.gy;
-        c_begin = z * g.per;
-        n_chunks = min(p.cin_chunks, c_begin + g.per) - c_begin;
+        u0 = z * p.k_per_units;
+        n_units = min(g.units, u0 + p.k_per_units) - u0;                // host guarantees >= 1
     };
 
     if (warp == 0) {
@@ -602,13 +652,14 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_chain_kernel(const __gri
                 tma_prefetch_desc(tmW_hi); tma_prefetch_desc(tmW_lo);
             }
             for (int item = blockIdx.x; item < g.n_items; item += G, ++kk) {
-                int b, y0, x0, cout0, z, c_begin, n_chunks;
-                decode_item(p, g, item, b, y0, x0, cout0, z, c_begin, n_chunks);
-                int w_it = 0, w_tap = 0, w_seq = 0;
+                int b, y0, x0, cout0, z, u0, n_units;
+                decode_item(p, g, item, b, y0, x0, cout0, z, u0, n_units);
+                // weight tiles are requested strictly in unit order; (w_ci, w_tap) is the next one
+                int w_ci = u0 / taps, w_tap = u0 - w_ci * taps, w_seq = 0;
                 auto issue_next_w = [&]() {
                     mbar_wait(&w_empty[ws], wphase ^ 1);
                     uint8_t *wdst = s_w + ws * kWStageBytes;
-                    const int kcoord = (w_tap * p.cin_chunks + c_begin + w_it) * kelems;
+                    const int kcoord = (w_tap * p.cin_chunks + w_ci) * kelems;
                     if (elect_one()) {
                         mbar_expect_tx(&w_full[ws], w_tx);
                         tma_load_2d(tmW_hi, &w_full[ws], wdst, kcoord, cout0, kEvictLast);
@@ -616,13 +667,13 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_chain_kernel(const __gri
                     }
                     __syncwarp();
                     ++w_seq;
-                    if (++w_tap == taps) { w_tap = 0; ++w_it; }
+                    if (++w_tap == taps) { w_tap = 0; ++w_ci; }
                     if (++ws == kWStages) { ws = 0; wphase ^= 1; }
                 };
                 // weights first: they do not depend on the previous layer (nor on the previous item's staged tile,
                 // unless that tile reaches into the weight ring)
                 if (kk == 0 || !prev_hits_w) {
-                    const int pf = min(kWStages, n_chunks * taps);
+                    const int pf = min(kWStages, n_units);
                     while (w_seq < pf) issue_next_w();
                 }
                 if (kk > 0) mbar_wait(stage_free, (kk - 1) & 1);     // the previous item's staged tile has left the patch buffers
@@ -632,11 +683,13 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_chain_kernel(const __gri
                         __syncwarp();
                         asm volatile("fence.proxy.async.global;" ::: "memory");   // generic-proxy stores -> TMA reads
                     }
+                    if (B2T_TRACE_PTR(cp.L[0].p) && blockIdx.x == 0 && lane == 0) B2T_TRACE_PTR(cp.L[0].p)[L * 8 + 0] = clock64();
                     input_ready = true;
                 }
                 int seq = 0;
-                for (int it = 0; it < n_chunks; ++it, ++g_it) {
-                    const int ci = c_begin + it, hb = g_it % kHaloBufs;
+                for (int u = u0; u < u0 + n_units; ++g_it) {
+                    const int ci = u / taps, t0 = u - ci * taps, t1 = min(taps, t0 + (u0 + n_units - u));
+                    const int hb = g_it % kHaloBufs;
                     mbar_wait(&halo_empty[hb], ((g_it / kHaloBufs) & 1) ^ 1);
                     uint8_t *hdst = s_halo + hb * kHaloBufBytes;
                     if (elect_one()) {
@@ -645,10 +698,12 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_chain_kernel(const __gri
                         tma_load_4d(tmX_lo, &halo_full[hb], hdst + p.h_plane_bytes, ci * kelems, x0 - pad, y0 - pad, b, kEvictNormal);
                     }
                     __syncwarp();
-                    for (int tap = 0; tap < taps; ++tap, ++seq)
+                    for (int tap = t0; tap < t1; ++tap, ++seq)
                         if (seq == w_seq) issue_next_w();
+                    u += t1 - t0;
                 }
-                prev_hits_w = stage_hits_w;
+                // a split layer's epilogue writes its partials straight from registers: nothing is staged
+                prev_hits_w = stage_hits_w && p.splits == 1;
             }
             ready += G * (p.splits > 1 ? 2u : 1u);
         }
@@ -666,26 +721,33 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_chain_kernel(const __gri
             const uint32_t xl_off = p.h_plane_bytes >> 4;
             const bool k128 = p.kbytes == 128;
             for (int item = blockIdx.x; item < g.n_items; item += G, ++kk) {
-                int b, y0, x0, cout0, z, c_begin, n_chunks;
-                decode_item(p, g, item, b, y0, x0, cout0, z, c_begin, n_chunks);
-                const int n_main = max(1, min(min(p.n_main, Cfg::kTmemCols / N - 1), n_chunks * taps));
+                int b, y0, x0, cout0, z, u0, n_units;
+                decode_item(p, g, item, b, y0, x0, cout0, z, u0, n_units);
+                const int n_main = max(1, min(min(p.n_main, Cfg::kTmemCols / N - 1), n_units));
                 const uint32_t t_corr = tmem_base + n_main * N;
                 if (kk > 0) { mbar_wait(acc_empty, (kk - 1) & 1); tc_fence_after(); }   // the epilogue has read the accumulators
                 int mi = 0;
                 uint32_t first = 1, am = 0;
-                for (int it = 0; it < n_chunks; ++it, ++g_it) {
+                for (int u = u0; u < u0 + n_units; ++g_it) {
+                    const int ci = u / taps, t0 = u - ci * taps, t1 = min(taps, t0 + (u0 + n_units - u));
                     const int hb = g_it % kHaloBufs;
                     mbar_wait(&halo_full[hb], (g_it / kHaloBufs) & 1);
-                    uint32_t xh = h16_0 + hb * (kHaloBufBytes >> 4);
-                    int kw = 0;
-                    for (int tap = 0; tap < taps; ++tap) {
+                    if (B2T_TRACE_PTR(cp.L[0].p) && blockIdx.x == 0 && lane == 0 && u == u0 && item == (int)blockIdx.x)
+                        B2T_TRACE_PTR(cp.L[0].p)[L * 8 + 1] = clock64();
+                    // tap t reads the patch shifted by (kh*hP + kw) rows
+                    const int kh0 = t0 / p.ksize;
+                    int kw = t0 - kh0 * p.ksize;
+                    uint32_t xh = h16_0 + hb * (kHaloBufBytes >> 4) + (kh0 * p.hP + kw) * kb16;
+                    for (int tap = t0; tap < t1; ++tap) {
                         mbar_wait(&w_full[ws], wphase);
                         tc_fence_after();
                         const uint32_t wh = w16_0 + ws * (kWStageBytes >> 4), wl = wh + (kWTileBytes >> 4);
                         const uint32_t xl = xh + xl_off;
                         const uint32_t t_main = tmem_base + mi * N;
                         const uint32_t ac = first ^ 1u;
-                        const bool last_tap = tap == taps - 1;
+                        const bool last_tap = tap == t1 - 1;
+                        if (B2T_TRACE_PTR(cp.L[0].p) && blockIdx.x == 0 && lane == 0 && u == u0 && tap == t0 && item == (int)blockIdx.x)
+                            B2T_TRACE_PTR(cp.L[0].p)[L * 8 + 2] = clock64();
                         if (elect_one()) {
                             umma_kstep(t_main, t_corr, wh, wl, xh, xl, dhi, idesc, am, ac);
                             umma_kstep(t_main, t_corr, wh + 2, wl + 2, xh + 2, xl + 2, dhi, idesc, 1u, 1u);
@@ -695,7 +757,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_chain_kernel(const __gri
                             }
                             umma_commit(&w_empty[ws]);
                             if (last_tap) umma_commit(&halo_empty[hb]);
-                            if (last_tap && it == n_chunks - 1) umma_commit(accum_bar);
+                            if (last_tap && u + (t1 - t0) == u0 + n_units) umma_commit(accum_bar);
                         }
                         __syncwarp();
                         first = 0;
@@ -703,6 +765,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_chain_kernel(const __gri
                         if (++kw == p.ksize) { kw = 0; xh += row16; } else xh += kb16;
                         if (++ws == kWStages) { ws = 0; wphase ^= 1; }
                     }
+                    u += t1 - t0;
                 }
             }
         }
@@ -711,34 +774,48 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_chain_kernel(const __gri
         const int et = threadIdx.x - 64;
         int kk = 0;
         unsigned int done = 0;
+        long long *trace = B2T_TRACE_PTR(cp.L[0].p);            // developer builds: per-layer clock stamps of CTA 0
+        const bool tr = trace && blockIdx.x == 0 && et == 0;
         for (int L = 0; L < cp.n_layers; ++L) {
             const ConvParams &p = cp.L[L].p;
             const Geo g = geometry(p);
-            const int taps = p.ksize * p.ksize, N = p.hN;
+            const int N = p.hN;
+            bool first = true;
             for (int item = blockIdx.x; item < g.n_items; item += G, ++kk) {
-                int b, y0, x0, cout0, z, c_begin, n_chunks;
-                decode_item(p, g, item, b, y0, x0, cout0, z, c_begin, n_chunks);
-                const int n_main = max(1, min(min(p.n_main, Cfg::kTmemCols / N - 1), n_chunks * taps));
+                int b, y0, x0, cout0, z, u0, n_units;
+                decode_item(p, g, item, b, y0, x0, cout0, z, u0, n_units);
+                const int n_main = max(1, min(min(p.n_main, Cfg::kTmemCols / N - 1), n_units));
                 mbar_wait(accum_bar, kk & 1);
                 tc_fence_after();
-                halo_epilogue(p, reinterpret_cast<float *>(smem), tmem_base, n_main + 1, N, b, y0, x0, cout0, z, acc_empty);
+                if (tr && first) trace[L * 8 + 3] = clock64();
+                first = false;
+                if (p.splits > 1)
+                    chain_partial_epilogue(p, tmem_base, n_main + 1, N, b, y0, x0, cout0, z, acc_empty);
+                else
+                    halo_epilogue(p, reinterpret_cast<float *>(smem), tmem_base, n_main + 1, N, b, y0, x0, cout0, z, acc_empty);
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 if (threadIdx.x == 64) mbar_arrive(stage_free);
             }
-            // this CTA's part of layer L is in global memory: arrive on the grid barrier
-            __threadfence();
+            // This CTA's part of layer L is in global memory: arrive on the grid barrier, then WAIT for the phase to
+            // complete before arriving anywhere else -- a CTA without items in the next layer would otherwise count
+            // for that layer's phase while another CTA is still in this one, and the monotonic counter would release
+            // waiters early.
+            if (tr) trace[L * 8 + 4] = clock64();
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (et == 0) atomicAdd(cp.counter, 1u);
             done += G;
-            if (p.splits > 1) {
-                if (et == 0) { grid_wait(cp.counter, done); __threadfence(); }     // every CTA's partials are written
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (et == 0) { grid_arrive(cp.counter); grid_wait(cp.counter, done); }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (tr) trace[L * 8 + 5] = clock64();
+            if (p.splits > 1) {                                   // every CTA's partials are written: finish a slice
                 splitk_finish_range(p, (long long)blockIdx.x * kEpiThreads + et, (long long)G * kEpiThreads);
-                __threadfence();
+                asm volatile("fence.acq_rel.gpu;" ::: "memory");
                 asm volatile("bar.sync 1, 256;" ::: "memory");
-                if (et == 0) atomicAdd(cp.counter, 1u);
                 done += G;
+                if (et == 0) { grid_arrive(cp.counter); grid_wait(cp.counter, done); }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
             }
+            if (tr) trace[L * 8 + 6] = clock64();
         }
     }
     tc_fence_before();

@@ -66,6 +66,7 @@ struct ConvParams {
     int pm_w_bytes;
     unsigned int magic_tx, magic_ty;   // ceil(2^32 / h_tiles_x), ceil(2^32 / h_tiles_y) (0 when the divisor is 1): fast item decode
     int b_in_off;           // added to the image index of the INPUT view only (state slot of the first stream)
+    int k_per_units;        // conv_chain_kernel: (chunk, tap) units per K split, chunk-major (finer than whole chunks)
 #ifdef B2T_DEV              // developer builds only (make DEV=1); the release library has neither field nor the code behind them
     int dbg;                // experiments: 1 = weight TMA only for the first ring pass, 2 = patch TMA only for the
                             // first buffers, 4 = no epilogue stores, 8 = no MMAs (results are wrong)
@@ -83,6 +84,27 @@ struct ConvParams {
 
 __device__ __forceinline__ float leaky(float v) { return v > 0.f ? v : 0.1f * v; }
 
+// n / d for 0 <= n < 2^20, 1 <= d < 2^12, exact: the quotient of (n + 0.5) / d is at least 0.5 / d away from an integer,
+// far more than the error of the approximate fp32 division
+__device__ __forceinline__ int small_div(int n, int d) { return __float2int_rz(__fdividef((float)n + 0.5f, (float)d)); }
+
+// darknet/src/blas.c:9-30 reorg_cpu(stride 2, forward = 0) as a scatter of source element (c, y, x) of a (C, H, W)
+// tensor: the CHW source is read as if shaped (C/4, 2H, 2W).  With q = c*H + y (row of the (C*H) x W matrix) the flat
+// source index is s = q*W + x, so  w2 = s % 2W = (q & 1)*W + x,  h2 = (s / 2W) % 2H = (q >> 1) % 2H,
+// c2 = s / 4WH = (q >> 1) / 2H;  out channel k = ((h2 & 1)*2 + (w2 & 1))*(C/4) + c2 and the element lands at flat index
+// o = (w2 >> 1) + W*((h2 >> 1) + H*k) of the (4C, H/2, W/2) destination: row R = o / (W/2), column o % (W/2).
+__device__ __forceinline__ void reorg_darknet_dest(int c, int y, int x, int H, int W, int Cout, int &cd, int &yd, int &xd) {
+    const int q = c * H + y, qh = q >> 1;
+    const int c2 = small_div(qh, 2 * H), h2 = qh - c2 * 2 * H, w2 = (q & 1) * W + x;
+    const int k = ((h2 & 1) * 2 + (w2 & 1)) * (Cout >> 2) + c2;
+    const int Wd = W >> 1, Hd = H >> 1, wh = w2 >> 1;
+    const int a = wh >= Wd ? 1 : 0;
+    xd = wh - a * Wd;
+    const int R = a + 2 * ((h2 >> 1) + H * k);
+    cd = small_div(R, Hd);
+    yd = R - cd * Hd;
+}
+
 // Write up to 8 consecutive channels [c, c+8) of source pixel (b,y,x).  Cout = channels of the source tensor.
 __device__ __forceinline__ void emit8(const Dest &d, int b, int y, int x, int c, int Cout, const float (&v)[8]) {
     const int nvalid = min(8, Cout - c);
@@ -91,13 +113,10 @@ __device__ __forceinline__ void emit8(const Dest &d, int b, int y, int x, int c,
         // darknet/src/blas.c:9-30 reorg_cpu(forward=0) expressed as a scatter of source element (c,y,x):
         // the CHW source is read as if shaped (C/4, 2H, 2W); see DESIGN.md section 3.
         const int H = d.H, W = d.W;                 // source dims (26x26), dest is (4C, H/2, W/2)
-        const int Hd = H / 2, Wd = W / 2, out_c = Cout / 4;
+        const int Hd = H / 2, Wd = W / 2;
         for (int i = 0; i < nvalid; ++i) {
-            const int s = ((c + i) * H + y) * W + x;          // flat CHW source index
-            const int w2 = s % (2 * W), h2 = (s / (2 * W)) % (2 * H), c2 = s / (4 * W * H);
-            const int k = ((h2 & 1) * 2 + (w2 & 1)) * out_c + c2;
-            const int o = (w2 >> 1) + W * ((h2 >> 1) + H * k);  // flat index in the (C,H,W)-shaped loop space
-            const int cd = o / (Hd * Wd), yd = (o / Wd) % Hd, xd = o % Wd;
+            int cd, yd, xd;
+            reorg_darknet_dest(c + i, y, x, H, W, Cout, cd, yd, xd);
             const long long pix = ((long long)b * Hd + yd) * Wd + xd;
             if (d.hi) {
                 op_t h, l;
@@ -219,13 +238,9 @@ __device__ __forceinline__ void emit1(const Dest &d, int b, int y, int x, int c,
     long long pix;
     int cc = c;
     if (d.mode == DEST_REORG_DARKNET) {
-        const int H = d.H, W = d.W, Hd = H / 2, Wd = W / 2, out_c = Cout / 4;
-        const int s = (c * H + y) * W + x;
-        const int w2 = s % (2 * W), h2 = (s / (2 * W)) % (2 * H), c2 = s / (4 * W * H);
-        const int k = ((h2 & 1) * 2 + (w2 & 1)) * out_c + c2;
-        const int o = (w2 >> 1) + W * ((h2 >> 1) + H * k);
-        cc = o / (Hd * Wd);
-        pix = ((long long)b * Hd + (o / Wd) % Hd) * Wd + o % Wd;
+        int yd, xd;
+        reorg_darknet_dest(c, y, x, d.H, d.W, Cout, cc, yd, xd);
+        pix = ((long long)b * (d.H / 2) + yd) * (d.W / 2) + xd;
     } else if (d.mode == DEST_S2D_TF) {
         pix = ((long long)b * (d.H / 2) + (y >> 1)) * (d.W / 2) + (x >> 1);
         cc = ((y & 1) * 2 + (x & 1)) * Cout + c;
@@ -256,12 +271,25 @@ __device__ __forceinline__ void splitk_finish_range(const ConvParams &p, long lo
     const int Hq = p.pool ? p.H / 2 : p.H, Wq = p.pool ? p.W / 2 : p.W;
     const long long total = (long long)p.B * Hq * Wq * cgroups;
     const long long mtot = (long long)p.B * p.H * p.W;
+    // item -> (image, row, column, channel group): 32-bit arithmetic and exact float divisions (small_div) whenever the
+    // counts allow -- 64-bit integer divisions cost more than the reduction itself
+    const bool small = total < (1ll << 31) && (long long)p.B * Hq * Wq < (1 << 20);
     for (long long t = start; t < total; t += step) {
-        const int cg = int(t % cgroups);
-        long long q = t / cgroups;
-        const int xq = int(q % Wq);  q /= Wq;
-        const int yq = int(q % Hq);
-        const int b = int(q / Hq);
+        int cg, xq, yq, b;
+        if (small) {
+            const int qi = (int)t / cgroups;
+            cg = (int)t - qi * cgroups;
+            const int row = small_div(qi, Wq);
+            xq = qi - row * Wq;
+            b = small_div(row, Hq);
+            yq = row - b * Hq;
+        } else {
+            cg = int(t % cgroups);
+            long long q = t / cgroups;
+            xq = int(q % Wq);  q /= Wq;
+            yq = int(q % Hq);
+            b = int(q / Hq);
+        }
         const int c = cg * 8;
         float s8[8], b8[8], mx[8];
 #pragma unroll
@@ -276,8 +304,26 @@ __device__ __forceinline__ void splitk_finish_range(const ConvParams &p, long lo
             const int y = p.pool ? 2 * yq + (k >> 1) : yq, x = p.pool ? 2 * xq + (k & 1) : xq;
             const long long pix = ((long long)b * p.H + y) * p.W + x;
             float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            for (int z = 0; z < p.splits; ++z) {  // ldp is a multiple of 32 -> both float4 are in bounds
-                const float4 *src = reinterpret_cast<const float4 *>(p.partial + ((long long)z * mtot + pix) * p.ldp + c);
+            // fixed order z = 0, 1, 2, ...; eight splits' loads are in flight at a time (ldp is a multiple of 32, so
+            // both float4 are in bounds)
+            const float *base = p.partial + pix * p.ldp + c;
+            const long long zs = mtot * p.ldp;
+            int z = 0;
+            for (; z + 8 <= p.splits; z += 8) {
+                float4 a[8], bq[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 *src = reinterpret_cast<const float4 *>(base + (long long)(z + j) * zs);
+                    a[j] = __ldcg(src); bq[j] = __ldcg(src + 1);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    v[0] += a[j].x; v[1] += a[j].y; v[2] += a[j].z; v[3] += a[j].w;
+                    v[4] += bq[j].x; v[5] += bq[j].y; v[6] += bq[j].z; v[7] += bq[j].w;
+                }
+            }
+            for (; z < p.splits; ++z) {
+                const float4 *src = reinterpret_cast<const float4 *>(base + (long long)z * zs);
                 const float4 a = __ldcg(src), bq = __ldcg(src + 1);
                 v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
                 v[4] += bq.x; v[5] += bq.y; v[6] += bq.z; v[7] += bq.w;

@@ -51,7 +51,7 @@ class DetectorEngine:
                  bn_eps: float = 1e-3, engine: str = "tcgen05", device: int = 0, convlstm_units: int = 0,
                  keep_prepool: bool = False, chain_max_batch: int = 0):
         """chain_max_batch: largest batch whose conv_2..23 run as one persistent cooperative launch (the small-batch
-        schedule, conv_chain_kernel); 0 = library default (8), -1 = never."""
+        schedule, conv_chain_kernel); 0 = library default (1), -1 = never."""
         if not torch.cuda.is_available():
             raise N.B2TError("no CUDA device: the B200 path has no CPU fallback")
         self.lib = N.lib()
