@@ -60,8 +60,8 @@ def test_every_layer_against_fp64_oracle(keras_c2):
 def test_batch_one_and_float_frames_agree(keras_c2):
     z, w, frames, e = keras_c2
     a = e.forward(torch.from_numpy(frames).cuda()).clone()
-    b = e.forward(torch.from_numpy(frames[:1]).cuda()).clone()         # different split-K plan, same numbers
-    assert (a[0] - b[0]).abs().max().item() < 1e-4
+    b = e.forward(torch.from_numpy(frames[:1]).cuda()).clone()         # batch 1: conv_chain_kernel, other K splits
+    assert (a[0] - b[0]).abs().max().item() < 3e-4
     xf = torch.from_numpy(yolo_oracle.normalize(frames).astype(np.float32)).cuda()
     c = e.forward(xf)
     # uint8 frames take conv_1 through the tensor cores (exact integer operands, 1/255 folded into the scale);
