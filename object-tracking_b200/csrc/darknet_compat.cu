@@ -17,6 +17,9 @@
 #include "../../include/darknet_compat.h"
 
 int b2t_fail_internal(int code, const char *msg);
+namespace b2t {
+bool jpeg_decode_rgb(const uint8_t *data, size_t size, std::vector<uint8_t> &rgb, int &width, int &height, std::string &error);
+}
 
 namespace {
 
@@ -267,28 +270,78 @@ image make_image(int w, int h, int c) {
     return im;
 }
 
+// image.c:1442-1482 load_image_color -> load_image_stb(filename, 3): decode, then CHW float RGB = byte / 255.
+// JPEG (what YOLO.py:141 passes) is decoded by jpeg_decode.cu, bit-exactly like the reference's decoder; binary PPM (P6)
+// is read directly; a (w, h) request resizes like load_image (resize_image, image.c:1347-1389).
+// resize_image (image.c:1347-1389): separable bilinear with the (n-1)/(m-1) scale, horizontal pass first, in darknet's
+// float operation order (the same arithmetic as the device letterbox kernels)
+static image resize_image_host(image im, int w, int h) {
+    image part = make_image(w, im.h, im.c), out = make_image(w, h, im.c);
+    const float w_scale = (float)(im.w - 1) / (w - 1), h_scale = (float)(im.h - 1) / (h - 1);
+    for (int k = 0; k < im.c; ++k)
+        for (int r = 0; r < im.h; ++r) {
+            const float *src = im.data + ((size_t)k * im.h + r) * im.w;
+            float *dst = part.data + ((size_t)k * im.h + r) * w;
+            for (int c = 0; c < w; ++c) {
+                if (c == w - 1 || im.w == 1) { dst[c] = src[im.w - 1]; continue; }
+                const float sx = c * w_scale;
+                const int ix = (int)sx;
+                const float dx = sx - ix;
+                dst[c] = (1 - dx) * src[ix] + dx * src[ix + 1];
+            }
+        }
+    for (int k = 0; k < im.c; ++k)
+        for (int r = 0; r < h; ++r) {
+            const float sy = r * h_scale;
+            const int iy = (int)sy;
+            const float dy = sy - iy;
+            float *dst = out.data + ((size_t)k * h + r) * w;
+            const float *p0 = part.data + ((size_t)k * im.h + iy) * w;
+            for (int c = 0; c < w; ++c) dst[c] = (1 - dy) * p0[c];
+            if (r == h - 1 || im.h == 1) continue;
+            for (int c = 0; c < w; ++c) dst[c] += dy * p0[w + c];
+        }
+    free(part.data);
+    return out;
+}
+
 image load_image_color(char *filename, int w, int h) {
-    (void)w; (void)h;       // YOLO.py always passes 0,0 (no resize)
     image im = {0, 0, 0, nullptr};
     FILE *f = filename ? fopen(filename, "rb") : nullptr;
     if (!f) { err(std::string("load_image_color: cannot open ") + (filename ? filename : "(null)")); return im; }
-    char magic[3] = {0};
-    int iw = 0, ih = 0, maxv = 0;
-    if (fscanf(f, "%2s %d %d %d", magic, &iw, &ih, &maxv) != 4 || strcmp(magic, "P6") || maxv != 255 || iw < 1 || ih < 1) {
-        fclose(f);
-        err("load_image_color: only binary PPM (P6, maxval 255) is decoded by the compat layer; decode other formats in "
-            "the caller and use make_image()");
+    std::vector<unsigned char> file;
+    unsigned char chunk[65536];
+    size_t got;
+    while ((got = fread(chunk, 1, sizeof chunk, f)) > 0) file.insert(file.end(), chunk, chunk + got);
+    fclose(f);
+    std::vector<unsigned char> buf;
+    int iw = 0, ih = 0;
+    if (file.size() >= 2 && file[0] == 0xFF && file[1] == 0xD8) {
+        std::string e;
+        if (!b2t::jpeg_decode_rgb(file.data(), file.size(), buf, iw, ih, e)) { err(std::string("load_image_color: ") + filename + ": " + e); return im; }
+    } else if (file.size() >= 2 && file[0] == 'P' && file[1] == '6') {
+        int maxv = 0, pos = 0;
+        if (sscanf((const char *)file.data(), "P6 %d %d %d%n", &iw, &ih, &maxv, &pos) != 3 || maxv != 255 || iw < 1 || ih < 1 ||
+            file.size() < (size_t)pos + 1 + (size_t)iw * ih * 3) {
+            err("load_image_color: bad or truncated PPM (binary P6 with maxval 255 expected)");
+            return im;
+        }
+        buf.assign(file.begin() + pos + 1, file.begin() + pos + 1 + (size_t)iw * ih * 3);
+    } else {
+        err(std::string("load_image_color: ") + filename + ": the compat layer decodes JPEG (sequential DCT) and binary PPM; "
+            "decode other formats in the caller and use make_image()");
         return im;
     }
-    fgetc(f);
-    std::vector<unsigned char> buf((size_t)iw * ih * 3);
-    const size_t got = fread(buf.data(), 1, buf.size(), f);
-    fclose(f);
-    if (got != buf.size()) { err("load_image_color: truncated PPM"); return im; }
     im = make_image(iw, ih, 3);
-    for (int k = 0; k < 3; ++k)           // CHW, RGB, /255. (image.c load_image_stb)
+    for (int k = 0; k < 3; ++k)           // CHW, RGB, (float)byte / 255.  (image.c load_image_stb)
         for (int y = 0; y < ih; ++y)
-            for (int x = 0; x < iw; ++x) im.data[((size_t)k * ih + y) * iw + x] = (float)buf[((size_t)y * iw + x) * 3 + k] / 255.f;
+            for (int x = 0; x < iw; ++x)
+                im.data[((size_t)k * ih + y) * iw + x] = (float)((double)buf[((size_t)y * iw + x) * 3 + k] / 255.);
+    if (w && h && (w != iw || h != ih)) {
+        image r = resize_image_host(im, w, h);
+        free(im.data);
+        im = r;
+    }
     return im;
 }
 

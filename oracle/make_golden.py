@@ -13,6 +13,7 @@ What is produced (all small, committed):
                        fv_layer 25 feature (max-pooled), post-NMS detections
   keras_416_c2.npz     fp64 oracle outputs for the Keras-semantics graph (C=2; regression vector)
   tracker_cases.npz    fp64 oracle outputs of the LSTM / heat-map / ConvLSTM steps
+  jpeg/*.jpg, jpeg_cases.npz   synthetic JPEG files + what the reference library's load_image_color decodes from them
   heatmap_cases.npz    outputs of the reference's OWN generate_heatmap_feat / generate_rectangle_from_heatmap
                        (utility/utils.py:53-79 exec'd from /root/reference) on seeded boxes / heat-maps
 """
@@ -218,9 +219,59 @@ def make_resize_golden():
     print(f"[resize] {len(out) - 1} cv2 outputs written (cv2 {cv2.__version__}); restatement bit-exact on the sweep")
 
 
+def make_jpeg_golden():
+    """JPEG fixtures (synthetic images written by OpenCV's libjpeg: every chroma subsampling, restart intervals, grey,
+    optimised Huffman tables, tiny sizes) and what the REFERENCE library's load_image_color (stb_image path,
+    image.c:1442-1482) decodes from them, as bytes (the library returns byte / 255.)."""
+    import ctypes as C
+    import cv2
+
+    class IMAGE(C.Structure):
+        _fields_ = [("w", C.c_int), ("h", C.c_int), ("c", C.c_int), ("data", C.POINTER(C.c_float))]
+
+    ref = C.CDLL(darknet_ref.LIB_PATH)
+    ref.load_image_color.restype = IMAGE
+    ref.load_image_color.argtypes = [C.c_char_p, C.c_int, C.c_int]
+    ref.free_image.argtypes = [IMAGE]
+    d = os.path.join(GOLD, "jpeg")
+    os.makedirs(d, exist_ok=True)
+    rng = np.random.default_rng(2025)
+    smooth = cv2.GaussianBlur(rng.integers(0, 256, (90, 134, 3), dtype=np.uint8), (9, 9), 3)
+    yy, xx = np.mgrid[0:75, 0:101]
+    ramp = np.stack([(xx * 2.5) % 256, (yy * 3.3) % 256, ((xx + yy) * 1.7) % 256], -1).astype(np.uint8)
+    noise = rng.integers(0, 256, (37, 51, 3), dtype=np.uint8)
+    sf = {"444": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444, "422": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422,
+          "420": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, "440": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_440,
+          "411": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_411}
+    files = []
+    for k, v in sf.items():
+        img = {"444": smooth, "422": ramp, "420": smooth, "440": ramp, "411": noise}[k]
+        p = os.path.join(d, f"s{k}.jpg")
+        cv2.imwrite(p, img, [cv2.IMWRITE_JPEG_QUALITY, 60 if k != "411" else 92, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, v])
+        files.append(p)
+    p = os.path.join(d, "rst3.jpg"); cv2.imwrite(p, smooth, [cv2.IMWRITE_JPEG_RST_INTERVAL, 3, cv2.IMWRITE_JPEG_QUALITY, 75]); files.append(p)
+    p = os.path.join(d, "grey.jpg"); cv2.imwrite(p, cv2.cvtColor(ramp, cv2.COLOR_BGR2GRAY)); files.append(p)
+    p = os.path.join(d, "opt.jpg"); cv2.imwrite(p, noise, [cv2.IMWRITE_JPEG_OPTIMIZE, 1, cv2.IMWRITE_JPEG_QUALITY, 50]); files.append(p)
+    for w, h in ((1, 1), (7, 3), (16, 17)):
+        p = os.path.join(d, f"tiny_{w}x{h}.jpg"); cv2.imwrite(p, rng.integers(0, 256, (h, w, 3), dtype=np.uint8)); files.append(p)
+    # the frame the GPU side-by-side test feeds both libraries: non-square, letterboxed by network_predict_image
+    p = os.path.join(d, "frame_500x300.jpg")
+    cv2.imwrite(p, rng.integers(0, 256, (300, 500, 3), dtype=np.uint8), [cv2.IMWRITE_JPEG_QUALITY, 95]); files.append(p)
+    out = {}
+    for p in files:
+        im = ref.load_image_color(p.encode(), 0, 0)
+        a = np.ctypeslib.as_array(im.data, shape=(im.c, im.h, im.w)).copy()
+        ref.free_image(im)
+        b = np.rint(a * 255.0).astype(np.uint8)
+        assert np.array_equal((b.astype(np.float64) / 255.0).astype(np.float32), a)     # the library's float is byte / 255.
+        out[os.path.basename(p)] = b
+    np.savez_compressed(os.path.join(GOLD, "jpeg_cases.npz"), **out)
+    print(f"[jpeg] {len(files)} fixtures, {sum(os.path.getsize(p) for p in files)} bytes; reference outputs written")
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    what = sys.argv[1:] or ["decode", "darknet", "keras", "tracker", "resize", "heatmap"]
+    what = sys.argv[1:] or ["decode", "darknet", "keras", "tracker", "resize", "heatmap", "jpeg"]
     if "decode" in what:
         make_decode_goldens()
     if "darknet" in what:
@@ -233,3 +284,5 @@ if __name__ == "__main__":
         make_resize_golden()
     if "heatmap" in what:
         make_heatmap_golden()
+    if "jpeg" in what:
+        make_jpeg_golden()

@@ -170,3 +170,42 @@ def test_letterbox_and_detections_side_by_side_with_reference_library(files):
         assert [x[0] for x in a] == [x[0] for x in b], (h, w)
         for (n1, p1, b1), (n2, p2, b2) in zip(a, b):
             assert abs(p1 - p2) < 2e-4 and np.abs(np.array(b1) - np.array(b2)).max() < 5e-2
+
+
+@pytest.mark.skipif(not darknet_ref.available(), reason="oracle/_ref/libdarknet.so not present")
+def test_yolo_detect_on_a_jpeg_path_side_by_side(files):
+    """the reference's own call sequence on a .jpg PATH (YOLO.py:140-162: load_image_color ->
+    network_predict_image -> get_network_boxes -> do_nms_obj -> free_image), non-square frame, through both
+    libraries; then the Python plugin YOLO.detect(path) against the same reference result."""
+    cfg, wts, data = files
+    ref = bind(C.CDLL(darknet_ref.LIB_PATH))
+    ours = bind(C.CDLL(_native.LIB_PATH))
+    cwd = os.getcwd()
+    net_r = ref.load_network(cfg.encode(), wts.encode(), 0)
+    net_o = ours.load_network(cfg.encode(), wts.encode(), 0)
+    os.chdir(cwd)
+    meta = ours.get_metadata(data.encode())
+    path = os.path.join(GOLD, "jpeg", "frame_500x300.jpg")
+    out = []
+    for lib, net in ((ref, net_r), (ours, net_o)):
+        im = lib.load_image_color(path.encode(), 0, 0)
+        assert im.data and (im.w, im.h, im.c) == (500, 300, 3)
+        out.append(detect(lib, net, meta, im))
+        lib.free_image(im)
+    a, b = out
+    assert len(a) > 0 and [x[0] for x in a] == [x[0] for x in b]
+    for (n1, p1, b1), (n2, p2, b2) in zip(a, b):
+        assert abs(p1 - p2) < 2e-4 and np.abs(np.array(b1) - np.array(b2)).max() < 5e-2      # pixels of a 500x300 frame
+    # the plugin class on the same path: cv2 decodes the file (libjpeg, not bit-identical to stb on chroma upsampling),
+    # BGR -> RGB, letterbox on the device, boxes un-mapped to the 500x300 frame
+    from object_tracking_b200.models_detection.YOLO import YOLO
+    y = YOLO(weights=W.synthetic_yolo_weights(80, seed=0), max_batch=1)
+    c = y.detect(path)
+    top = {}
+    for n, p, bx in a:
+        top.setdefault(n, (p, bx))
+    hits = 0
+    for n, p, bx in c:
+        if n in top and abs(p - top[n][0]) < 0.05:
+            hits += np.abs(np.array(bx) - np.array(top[n][1])).max() < 3.0             # pixels
+    assert hits >= min(len(c), len(a)) - 1 and hits >= 1
