@@ -182,6 +182,22 @@ int  b2t_convlstm_sequence(b2t_ctx *ctx, int n_streams, int n_steps, int slot0, 
                            int hard_sigmoid, void *stream);
 int  b2t_convlstm_window(b2t_ctx *ctx, int batch, float *trk_logits_dev, int hard_sigmoid, void *stream);
 
+/* ---- CUDA graphs: one launch per step for a plain-C host ---------------- */
+/* Capture every b2t_* call made on `stream` between begin and end (all entry points are stream-ordered; the ones that
+ * synchronise -- b2t_finalize, b2t_lstm_set_weights, the first b2t_resize_frames of a geometry -- must precede the
+ * capture; device pointers passed during the capture are baked into the graph), then replay with b2t_graph_launch. */
+typedef struct b2t_graph b2t_graph;
+int  b2t_graph_begin(b2t_ctx *ctx, void *stream /* non-default */);
+int  b2t_graph_end(b2t_ctx *ctx, void *stream, b2t_graph **out);
+int  b2t_graph_launch(b2t_graph *g, void *stream);
+void b2t_graph_destroy(b2t_graph *g);
+
+/* ---- multi-GPU: the one collective of the path --------------------------------------- */
+/* ncclBroadcast of the packed weight blob from rank `root` over `nccl_comm` (an ncclComm_t; NCCL is resolved with
+ * dlopen at run time).  Every rank calls it after b2t_bind_memory / rank `root` after b2t_finalize(upload=1); the other
+ * ranks then call b2t_finalize(ctx, 0, stream).  Streams are independent units: nothing else is exchanged. */
+int  b2t_broadcast_weights(b2t_ctx *ctx, void *nccl_comm, int root, void *stream);
+
 /* ---- introspection for bench.py ------------------------------------------------------------ */
 long b2t_launch_count(const b2t_ctx *ctx);            /* kernels launched by this context so far */
 /* per-conv timing with CUDA events: runs the forward once, fills ms[23] and (optional) the algorithmic

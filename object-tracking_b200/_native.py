@@ -69,6 +69,11 @@ SIGNATURES = {
     "b2t_convlstm_window": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp]),
     "b2t_convlstm_reset_slots": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "b2t_convlstm_sequence": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp]),
+    "b2t_graph_begin": (C.c_int, [_vp, _vp]),
+    "b2t_graph_end": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
+    "b2t_graph_launch": (C.c_int, [_vp, _vp]),
+    "b2t_graph_destroy": (None, [_vp]),
+    "b2t_broadcast_weights": (C.c_int, [_vp, _vp, C.c_int, _vp]),
     "b2t_launch_count": (C.c_long, [_vp]),
     "b2t_profile_forward": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _fp, C.POINTER(C.c_double), _vp]),
 }

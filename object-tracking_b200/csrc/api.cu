@@ -119,6 +119,7 @@ struct b2t_ctx {
     int n_sm = 148;
     int chain_max_batch = 1;                      // batches up to this size run conv_2..23 in conv_chain_kernel (0 = never)
     unsigned int *d_chain_counter = nullptr;      // its grid-barrier arrival counter
+    long capture_launches0 = 0;                   // b2t_graph_begin: launch counter at the start of the capture
     PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
     // b2t_resize_frames: coefficient tables of the last (src, dst) geometry
     int rs_geom[4] = {0, 0, 0, 0};
@@ -1546,6 +1547,82 @@ extern "C" int b2t_select_detection(b2t_ctx *c, const float *dets, const int *co
     const int rc = launch_select_detection(p, (cudaStream_t)stream);
     if (rc) return fail(-2, "select launch: %s", cudaGetErrorString((cudaError_t)rc));
     if (c) c->launches += 1;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ CUDA graphs
+// A step of this path is 30-45 kernel launches of a few microseconds each: replayed eagerly it is launch-latency
+// bound.  These four calls let a plain-C host capture any sequence of b2t_* calls made on `stream` (every entry point is
+// stream-ordered; the ones that synchronise -- b2t_finalize, b2t_lstm_set_weights, the first b2t_resize_frames of a
+// geometry -- must run before the capture) and replay it with one launch.
+struct b2t_graph {
+    b2t_ctx *ctx;
+    cudaGraph_t graph;
+    cudaGraphExec_t exec;
+    long kernels;                 // kernel nodes per replay (for b2t_launch_count)
+};
+
+extern "C" int b2t_graph_begin(b2t_ctx *c, void *stream) {
+    if (!c || !c->finalized) return fail(-1, "b2t_graph_begin: context not finalized");
+    if (!stream) return fail(-1, "b2t_graph_begin: capture needs a non-default stream");
+    CK(cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeThreadLocal));
+    c->capture_launches0 = c->launches;
+    return 0;
+}
+
+extern "C" int b2t_graph_end(b2t_ctx *c, void *stream, b2t_graph **out) {
+    if (!c || !out) return fail(-1, "b2t_graph_end: null argument");
+    cudaGraph_t g = nullptr;
+    CK(cudaStreamEndCapture((cudaStream_t)stream, &g));
+    if (!g) return fail(-2, "b2t_graph_end: the capture was invalidated (a call synchronised or failed inside it)");
+    b2t_graph *bg = new b2t_graph();
+    bg->ctx = c; bg->graph = g; bg->exec = nullptr;
+    bg->kernels = c->launches - c->capture_launches0;
+    c->launches = c->capture_launches0;               // captured launches did not run; replays are counted instead
+    cudaError_t e = cudaGraphInstantiate(&bg->exec, g, 0);
+    if (e != cudaSuccess) {
+        cudaGraphDestroy(g);
+        delete bg;
+        return fail(-2, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+    }
+    *out = bg;
+    return 0;
+}
+
+extern "C" int b2t_graph_launch(b2t_graph *g, void *stream) {
+    if (!g || !g->exec) return fail(-1, "b2t_graph_launch: null graph");
+    CK(cudaGraphLaunch(g->exec, (cudaStream_t)stream));
+    g->ctx->launches += g->kernels;
+    return 0;
+}
+
+extern "C" void b2t_graph_destroy(b2t_graph *g) {
+    if (!g) return;
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    if (g->graph) cudaGraphDestroy(g->graph);
+    delete g;
+}
+
+// ------------------------------------------------------------------------------------------------ weight broadcast
+// The one collective of the path: the packed blob (backbone + ConvLSTM head) from `root` to every
+// rank of an NCCL communicator, over NVLink / NVSwitch.  NCCL is resolved at run time (dlopen of the library the host
+// process already uses), so the .so has no link-time dependency on it.  Ranks other than root then call
+// b2t_finalize(ctx, upload = 0).
+#include <dlfcn.h>
+extern "C" int b2t_broadcast_weights(b2t_ctx *c, void *nccl_comm, int root, void *stream) {
+    if (!c || !nccl_comm) return fail(-1, "b2t_broadcast_weights: null argument");
+    if (!c->d_blob) return fail(-1, "b2t_broadcast_weights: no device blob yet (b2t_bind_memory or b2t_finalize first)");
+    typedef int (*bcast_fn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+    static bcast_fn fn = nullptr;
+    if (!fn) {
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return fail(-2, "b2t_broadcast_weights: libnccl.so.2 not found (%s)", dlerror());
+        fn = (bcast_fn)dlsym(h, "ncclBroadcast");
+        if (!fn) return fail(-2, "b2t_broadcast_weights: ncclBroadcast not found in libnccl");
+    }
+    const int rc = fn(c->d_blob, c->d_blob, c->weight_bytes, 1 /* ncclUint8 */, root, nccl_comm, (cudaStream_t)stream);
+    if (rc) return fail(-2, "ncclBroadcast failed with ncclResult %d", rc);
     return 0;
 }
 

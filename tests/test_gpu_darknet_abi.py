@@ -176,8 +176,12 @@ def test_letterbox_and_detections_side_by_side_with_reference_library(files):
 def test_yolo_detect_on_a_jpeg_path_side_by_side(files):
     """the reference's own call sequence on a .jpg PATH (YOLO.py:140-162: load_image_color ->
     network_predict_image -> get_network_boxes -> do_nms_obj -> free_image), non-square frame, through both
-    libraries; then the Python plugin YOLO.detect(path) against the same reference result."""
-    cfg, wts, data = files
+    libraries; then the Python plugin YOLO.detect(path) against the same reference result.  Planted detector weights
+    and thresh = 0.25 so that the letterboxed frame carries a dozen detections."""
+    cfg, _, data = files
+    wd = W.synthetic_detector_weights(80, seed=0)
+    wts = os.path.join(os.path.dirname(cfg), "planted.weights")
+    W.write_darknet_weights(wts, wd, 80)
     ref = bind(C.CDLL(darknet_ref.LIB_PATH))
     ours = bind(C.CDLL(_native.LIB_PATH))
     cwd = os.getcwd()
@@ -190,22 +194,26 @@ def test_yolo_detect_on_a_jpeg_path_side_by_side(files):
     for lib, net in ((ref, net_r), (ours, net_o)):
         im = lib.load_image_color(path.encode(), 0, 0)
         assert im.data and (im.w, im.h, im.c) == (500, 300, 3)
-        out.append(detect(lib, net, meta, im))
+        out.append(detect(lib, net, meta, im, thresh=.25))
         lib.free_image(im)
     a, b = out
-    assert len(a) > 0 and [x[0] for x in a] == [x[0] for x in b]
+    assert len(a) >= 5 and [x[0] for x in a] == [x[0] for x in b]
     for (n1, p1, b1), (n2, p2, b2) in zip(a, b):
         assert abs(p1 - p2) < 2e-4 and np.abs(np.array(b1) - np.array(b2)).max() < 5e-2      # pixels of a 500x300 frame
-    # the plugin class on the same path: cv2 decodes the file (libjpeg, not bit-identical to stb on chroma upsampling),
-    # BGR -> RGB, letterbox on the device, boxes un-mapped to the 500x300 frame
+    # the plugin class on the same path: cv2 decodes the file (libjpeg's chroma upsampling is not bit-identical to the
+    # reference decoder's), BGR -> RGB, letterbox on the device, boxes un-mapped to the 500x300 frame
+    import copy
     from object_tracking_b200.models_detection.YOLO import YOLO
-    y = YOLO(weights=W.synthetic_yolo_weights(80, seed=0), max_batch=1)
+    from object_tracking_b200.models_detection._common import load_config
+    conf = copy.deepcopy(load_config(None))
+    conf["model_detector"]["thresh"] = 0.25
+    y = YOLO(config=conf, weights=wd, max_batch=1)
     c = y.detect(path)
-    top = {}
-    for n, p, bx in a:
-        top.setdefault(n, (p, bx))
+    assert len(c) >= 5
     hits = 0
     for n, p, bx in c:
-        if n in top and abs(p - top[n][0]) < 0.05:
-            hits += np.abs(np.array(bx) - np.array(top[n][1])).max() < 3.0             # pixels
-    assert hits >= min(len(c), len(a)) - 1 and hits >= 1
+        for n2, p2, bx2 in a:
+            if n == n2 and abs(p - p2) < 0.03 and np.abs(np.array(bx) - np.array(bx2)).max() < 3.0:    # pixels
+                hits += 1
+                break
+    assert hits >= len(c) - 2, (hits, len(c), len(a))

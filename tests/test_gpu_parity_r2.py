@@ -389,3 +389,54 @@ def test_chain_schedule_matches_per_layer_schedule(B):
     assert np.abs(la.cpu().numpy() - o["logits"]).max() < 7e-4   # 5.0e-4 measured at batch 8 on |logit| <= 15
     # replays are bit-identical (fixed-order split-K finish, no atomics on data)
     assert torch.equal(a.forward(fr), la)
+
+
+# ------------------------------------------------------------------------------------------------ C-ABI: graphs, broadcast
+def test_c_abi_graph_capture_and_weight_broadcast():
+    """b2t_graph_begin/end/launch (a plain-C host replays a whole step with one launch) and b2t_broadcast_weights
+    (ncclBroadcast of the packed blob; exercised here on a one-rank communicator made with NCCL's own C API)."""
+    import ctypes as C
+    from object_tracking_b200 import _native as N
+    B, Cc = 2, 2
+    eng = _engine(n_class=Cc, max_batch=B)
+    eng.set_weights(W.synthetic_yolo_weights(Cc, seed=0))
+    eng.finalize()
+    lib = eng.lib
+    fr = torch.from_numpy(np.random.default_rng(3).integers(0, 256, (B, 416, 416, 3), dtype=np.uint8)).cuda()
+    s = torch.cuda.Stream()
+    anchors = (C.c_float * 10)(*W.ANCHORS)
+    boxes = torch.zeros((B, 845, 8), device="cuda")
+    counts = torch.zeros((B,), dtype=torch.int32, device="cuda")
+    with torch.cuda.stream(s):
+        ref_logits = eng.forward(fr).clone()
+        rb, rc = eng.decode(eng.logits(B), 0.5, 0.45)
+        rb, rc = rb.clone(), rc.clone()
+        s.synchronize()
+        g = C.c_void_p()
+        n_before = lib.b2t_launch_count(eng.h)
+        N.check(lib.b2t_graph_begin(eng.h, s.cuda_stream))
+        N.check(lib.b2t_yolo_forward(eng.h, fr.data_ptr(), N.FRAME_U8, B, None, s.cuda_stream))
+        N.check(lib.b2t_decode_nms(eng.h, eng.logits(B).data_ptr(), B, 13, 13, 5, Cc, 0.5, 0.45, anchors,
+                                   boxes.data_ptr(), counts.data_ptr(), 845, s.cuda_stream))
+        N.check(lib.b2t_graph_end(eng.h, s.cuda_stream, C.byref(g)))
+        assert lib.b2t_launch_count(eng.h) == n_before            # nothing ran during the capture
+        eng.logits(B).zero_()
+        for _ in range(3):
+            N.check(lib.b2t_graph_launch(g, s.cuda_stream))
+        s.synchronize()
+        per_replay = (lib.b2t_launch_count(eng.h) - n_before) // 3
+        assert per_replay >= 20
+        assert torch.equal(eng.logits(B), ref_logits) and torch.equal(counts, rc)
+        for i in range(B):
+            assert torch.equal(boxes[i, :int(rc[i])], rb[i, :int(rc[i])])
+        lib.b2t_graph_destroy(g)
+        assert lib.b2t_graph_begin(eng.h, None) < 0               # the legacy default stream cannot be captured
+    nccl = C.CDLL("libnccl.so.2")
+    comm = C.c_void_p()
+    assert nccl.ncclCommInitAll(C.byref(comm), 1, (C.c_int * 1)(torch.cuda.current_device())) == 0
+    before = eng.blob.clone()
+    N.check(lib.b2t_broadcast_weights(eng.h, comm, 0, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert torch.equal(eng.blob, before)
+    nccl.ncclCommDestroy(comm)
+    assert lib.b2t_broadcast_weights(eng.h, None, 0, None) < 0
