@@ -53,6 +53,18 @@ class BaseTracker(object):
     def load_tracker_model(self):
         raise NotImplementedError
 
+    def load_weights(self, path: Optional[str] = None):
+        """Load the LSTM + Dense head from a checkpoint: the Keras ``.hdf5`` files ``train()`` writes
+        (BaseTracker.py:74-80, ``<saved_model_dir><name>-CHKPNT-<epoch>-<val_loss>.hdf5``; read without h5py) or an
+        ``.npz``.  path=None takes the latest checkpoint under ``self.saved_model_path``.  Returns the file used."""
+        from ..weights import latest_checkpoint, load_checkpoint_arrays, lstm_weights_from_arrays
+        path = path or latest_checkpoint(self.saved_model_path)
+        if path is None:
+            raise FileNotFoundError(f"no checkpoint {self.saved_model_path}-CHKPNT-*.{{hdf5,h5,npz}}")
+        self.head.set_weights(lstm_weights_from_arrays(load_checkpoint_arrays(path)))
+        self.head.reset(-1)
+        return path
+
     def load_data_generators(self):
         raise NotImplementedError("training data generators are out of scope of the B200 hot path")
 

@@ -36,6 +36,7 @@ class MultiObjDetTracker:
     MAX_BOX_PER_IMAGE = 50
     CONVLSTM_UNITS = 512
     LOAD_MODEL = False
+    SAVED_MODEL_PATH = 'models/MultiObjDetTracker-CHKPNT-03-0.55.hdf5'
     model = None
     detector = None
     model_detector = None
@@ -63,11 +64,35 @@ class MultiObjDetTracker:
 
     def load_model(self):
         eng = self.detector.model
-        w = self._tracker_weights or synthetic_multiobj_weights(self.CLASS, self.CONVLSTM_UNITS, seed=2)
+        w = self._tracker_weights
+        if w is None and self.LOAD_MODEL:                  # MultiObjDetTracker.py:132-133
+            w = self._checkpoint_weights(self.SAVED_MODEL_PATH)
+        if w is None:
+            w = synthetic_multiobj_weights(self.CLASS, self.CONVLSTM_UNITS, seed=2)
         eng.set_convlstm_weights(w)
         eng.finalize()
         self.model = self.model_detector = eng
         eng.convlstm_reset()
+
+    def _checkpoint_weights(self, path: str):
+        """MultiObjDetTracker.py:291-293: the checkpoint holds the whole model -- ConvLSTM2D + head and, when present,
+        the detector's conv_k / norm_k layers (set before finalize)."""
+        from ..weights import convlstm_weights_from_arrays, detector_weights_from_arrays, load_checkpoint_arrays
+        arrays = load_checkpoint_arrays(path)
+        det = detector_weights_from_arrays(arrays, self.CLASS)
+        if det is not None:
+            self.model.set_weights(det) if self.model is not None else self.detector.model.set_weights(det)
+        self.INITIAL_EPOCH = int(path.split('-')[2]) if path.count('-') >= 2 and path.split('-')[2].isdigit() else 0
+        return convlstm_weights_from_arrays(arrays)
+
+    def load_weights(self, path: Optional[str] = None):
+        """Keras ``.hdf5`` (read without h5py) or ``.npz`` checkpoint -> ConvLSTM2D + head (+ detector layers if the
+        file has them); re-packs the weight blob."""
+        w = self._checkpoint_weights(path or self.SAVED_MODEL_PATH)
+        self.model.set_convlstm_weights(w)
+        self.model.finalize()
+        self.model.convlstm_reset()
+        self._graphs = {}
 
     def reset(self, stream: int = -1):
         if stream < 0:

@@ -277,3 +277,113 @@ def synthetic_multiobj_weights(n_class: int, units: int = 512, seed: int = 2) ->
     n_out = N_BOX * (5 + n_class)
     return synthetic_convlstm_weights(n_out + 1024, units, n_out, seed=seed, n_class=n_class, head_class_gain=4.0,
                                       head_obj_bias=-0.3, head_wh_gain=0.25)
+
+
+# --------------------------------------------------------------------------------------
+# tracker / detector checkpoints (BaseTracker.py:74-80 ModelCheckpoint files, MultiObjDetTracker.py:291-293)
+# --------------------------------------------------------------------------------------
+
+def _leaf(path: str) -> str:
+    return path.rstrip("/").split("/")[-1].split(":")[0]
+
+
+def load_checkpoint_arrays(path: str) -> Dict[str, np.ndarray]:
+    """Every array of a checkpoint file keyed by its path: Keras ``.hdf5`` / ``.h5`` (read with hdf5_lite -- h5py is not
+    needed) or ``.npz`` (numpy; what ``save_tracker_checkpoint`` writes, or a conversion of a Keras file made where
+    h5py exists: ``np.savez(out, **{name: f[name][()] for name in dataset_names})``)."""
+    if path.endswith(".npz"):
+        with np.load(path) as z:
+            return {k: np.asarray(z[k]) for k in z.files}
+    from .hdf5_lite import read_hdf5
+    return read_hdf5(path)
+
+
+def lstm_weights_from_arrays(arrays: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
+    """Pick the LSTM + Dense weights of TinyTracker / TinyHeatmapTracker (TinyTracker.py:36-37: ``recurrent_layer`` +
+    TimeDistributed(Dense ``output``)) out of a checkpoint by structure: the group that owns a 2-D ``recurrent_kernel``
+    is the LSTM; the Dense kernel is the 2-D ``kernel`` whose rows equal the LSTM's units."""
+    if {"kernel", "recurrent_kernel", "bias", "dense_kernel", "dense_bias"} <= set(arrays):
+        return {k: np.asarray(arrays[k], np.float32) for k in ("kernel", "recurrent_kernel", "bias", "dense_kernel", "dense_bias")}
+    rec = [k for k, v in arrays.items() if _leaf(k) == "recurrent_kernel" and v.ndim == 2]
+    if len(rec) != 1:
+        raise ValueError(f"expected exactly one 2-D recurrent_kernel in the checkpoint, found {len(rec)}")
+    grp = rec[0].rsplit("/", 1)[0]
+    units = arrays[rec[0]].shape[0]
+    pick = lambda leaf: next(v for k, v in arrays.items() if k.startswith(grp + "/") and _leaf(k) == leaf)
+    out = {"kernel": pick("kernel"), "recurrent_kernel": arrays[rec[0]], "bias": pick("bias")}
+    dense = [k for k, v in arrays.items() if _leaf(k) == "kernel" and v.ndim == 2 and v.shape[0] == units and not k.startswith(grp + "/")]
+    if len(dense) != 1:
+        raise ValueError(f"expected exactly one Dense kernel with {units} rows, found {len(dense)}")
+    dg = dense[0].rsplit("/", 1)[0]
+    out["dense_kernel"] = arrays[dense[0]]
+    out["dense_bias"] = next(v for k, v in arrays.items() if k.startswith(dg + "/") and _leaf(k) == "bias")
+    if out["kernel"].shape[1] != 4 * units or out["bias"].shape != (4 * units,):
+        raise ValueError("LSTM kernel / bias shapes do not match its recurrent kernel")
+    return {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in out.items()}
+
+
+def convlstm_weights_from_arrays(arrays: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
+    """ConvLSTM2D ``tconv_lstm`` + 1x1 head ``tconv_2`` of MultiObjDetTracker (MultiObjDetTracker.py:176-183), by
+    structure: the 4-D ``recurrent_kernel`` marks the ConvLSTM group; the head is the 1x1 4-D kernel fed by its units."""
+    if {"kernel", "recurrent_kernel", "bias", "head_kernel", "head_bias"} <= set(arrays):
+        return {k: np.asarray(arrays[k], np.float32) for k in ("kernel", "recurrent_kernel", "bias", "head_kernel", "head_bias")}
+    rec = [k for k, v in arrays.items() if _leaf(k) == "recurrent_kernel" and v.ndim == 4]
+    if len(rec) != 1:
+        raise ValueError(f"expected exactly one 4-D recurrent_kernel in the checkpoint, found {len(rec)}")
+    grp = rec[0].rsplit("/", 1)[0]
+    units = arrays[rec[0]].shape[2]
+    pick = lambda leaf: next(v for k, v in arrays.items() if k.startswith(grp + "/") and _leaf(k) == leaf)
+    head = [k for k, v in arrays.items() if _leaf(k) == "kernel" and v.ndim == 4 and v.shape[:3] == (1, 1, units)
+            and not k.startswith(grp + "/") and not _is_detector_conv(k)]
+    if len(head) != 1:
+        raise ValueError(f"expected exactly one 1x1 head kernel fed by {units} channels, found {len(head)}")
+    hg = head[0].rsplit("/", 1)[0]
+    out = {"kernel": pick("kernel"), "recurrent_kernel": arrays[rec[0]], "bias": pick("bias"), "head_kernel": arrays[head[0]],
+           "head_bias": next(v for k, v in arrays.items() if k.startswith(hg + "/") and _leaf(k) == "bias")}
+    return {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in out.items()}
+
+
+def _is_detector_conv(path: str) -> bool:
+    import re
+    return re.search(r"(^|/)conv_\d+(/|$)", path) is not None
+
+
+def detector_weights_from_arrays(arrays: Dict[str, np.ndarray], n_class: int) -> Optional[Dict[str, np.ndarray]]:
+    """The YOLOv2 layers ``conv_k`` / ``norm_k`` (KerasYOLO.py:277-400 names) of a Keras checkpoint, or None when the
+    file does not hold all of them (a tracker-only checkpoint)."""
+    import re
+    w: Dict[str, np.ndarray] = {}
+    names = {"kernel": "kernel", "gamma": "gamma", "beta": "beta", "moving_mean": "mean", "moving_variance": "var", "bias": "bias"}
+    for k, v in arrays.items():
+        m = re.search(r"(?:^|/)(conv|norm)_(\d+)/[^/]*$", k) or re.search(r"(?:^|/)(conv|norm)_(\d+)/(?:[^/]+/)*[^/]+$", k)
+        if not m or _leaf(k) not in names:
+            continue
+        w[f"{names[_leaf(k)]}_{int(m.group(2))}"] = np.ascontiguousarray(v, dtype=np.float32)
+    for s in yolo_layer_table(n_class):
+        need = [f"kernel_{s.index}"] + ([f"{n}_{s.index}" for n in ("gamma", "beta", "mean", "var")] if s.bn else [f"bias_{s.index}"])
+        if any(n not in w for n in need):
+            return None
+        if w[f"kernel_{s.index}"].shape != (s.ksize, s.ksize, s.cin, s.cout):
+            raise ValueError(f"conv_{s.index}: kernel shape {w[f'kernel_{s.index}'].shape} does not match {n_class} classes")
+    return w
+
+
+def save_tracker_checkpoint(path: str, w: Dict[str, np.ndarray]) -> None:
+    """``.npz`` with this package's own keys (the dict the tracker classes take as ``tracker_weights``)."""
+    np.savez(path, **{k: np.asarray(v, np.float32) for k, v in w.items()})
+
+
+def latest_checkpoint(prefix: str) -> Optional[str]:
+    """BaseTracker.py:74-80 writes ``<prefix>-CHKPNT-<epoch>-<val_loss>.hdf5``: the file of the highest epoch (an
+    ``.npz`` conversion next to it is preferred), or None."""
+    import glob
+    import re
+    best = None
+    for f in glob.glob(prefix + "-CHKPNT-*"):
+        m = re.search(r"-CHKPNT-(\d+)-", f)
+        if not m or not f.endswith((".hdf5", ".h5", ".npz")):
+            continue
+        key = (int(m.group(1)), f.endswith(".npz"))
+        if best is None or key > best[0]:
+            best = (key, f)
+    return best[1] if best else None

@@ -440,3 +440,83 @@ def test_c_abi_graph_capture_and_weight_broadcast():
     assert torch.equal(eng.blob, before)
     nccl.ncclCommDestroy(comm)
     assert lib.b2t_broadcast_weights(eng.h, None, 0, None) < 0
+
+
+# ------------------------------------------------------------------------------------------------ formats (8f rank 2)
+def test_tracker_checkpoints_and_voc_cfg(tmp_path):
+    """Tracker heads from checkpoint files (BaseTracker.py:74-80 naming; .npz here, Keras .hdf5 through hdf5_lite) give
+    the same numbers as the same weights passed as a dict; the compat layer loads a yolov2-voc.cfg-shaped network
+    (20 classes, VOC anchors)."""
+    import ctypes as C
+    import copy
+    from object_tracking_b200.models_tracking.TinyTracker import TinyTracker
+    from object_tracking_b200.models_tracking.MultiObjDetTracker import MultiObjDetTracker
+    cfg = copy.deepcopy(TRACKER_CFG)
+    cfg["train"]["saved_model_dir"] = str(tmp_path) + "/"
+    wl = W.synthetic_lstm_weights(1028, 512, 4, seed=21)
+    W.save_tracker_checkpoint(str(tmp_path / "TinyTracker-CHKPNT-01-0.90.npz"), W.synthetic_lstm_weights(1028, 512, 4, seed=20))
+    W.save_tracker_checkpoint(str(tmp_path / "TinyTracker-CHKPNT-05-0.40.npz"), wl)
+    frames = torch.from_numpy(np.random.default_rng(2).integers(0, 256, (1, 4, 416, 416, 3), dtype=np.uint8)).cuda()
+    a = TinyTracker(cfg, tracker_weights=wl, max_streams=1)
+    ya = a.track_windows(frames, graph=False).clone()
+    b = TinyTracker(cfg, max_streams=1)
+    y0 = b.track_windows(frames, graph=False).clone()
+    assert b.load_weights().endswith("CHKPNT-05-0.40.npz")
+    yb = b.track_windows(frames, graph=False)
+    assert torch.equal(ya, yb) and not torch.equal(y0, yb)
+    del a, b
+    # MultiObjDetTracker.load_weights: ConvLSTM + head + detector layers out of one checkpoint
+    Cn, U = 2, 64
+    wd, wt = W.synthetic_yolo_weights(Cn, seed=5), W.synthetic_multiobj_weights(Cn, U, seed=6)
+    arrays = {f"/model_weights/tconv_lstm/tconv_lstm/{k}:0": wt[k] for k in ("kernel", "recurrent_kernel", "bias")}
+    arrays["/model_weights/timedist_tconv2/timedist_tconv2/kernel:0"] = wt["head_kernel"]
+    arrays["/model_weights/timedist_tconv2/timedist_tconv2/bias:0"] = wt["head_bias"]
+    for s in W.yolo_layer_table(Cn):
+        arrays[f"/model_weights/timedist_bbox/conv_{s.index}/kernel:0"] = wd[f"kernel_{s.index}"]
+        if s.bn:
+            for kn, ours in (("gamma", "gamma"), ("beta", "beta"), ("moving_mean", "mean"), ("moving_variance", "var")):
+                arrays[f"/model_weights/timedist_bbox/norm_{s.index}/{kn}:0"] = wd[f"{ours}_{s.index}"]
+        else:
+            arrays[f"/model_weights/timedist_bbox/conv_{s.index}/bias:0"] = wd[f"bias_{s.index}"]
+    ck = str(tmp_path / "MultiObjDetTracker-CHKPNT-03-0.55.npz")
+    np.savez(ck, **arrays)
+    fr4 = frames[0]
+    m1 = MultiObjDetTracker({"LABELS": ["a", "b"]}, detector_weights=wd, tracker_weights=wt, convlstm_units=U)
+    ref = m1.track_windows(fr4[None], graph=False)[0].clone()
+    m2 = MultiObjDetTracker({"LABELS": ["a", "b"]}, convlstm_units=U)
+    m2.load_weights(ck)
+    assert m2.INITIAL_EPOCH == 3
+    assert torch.equal(m2.track_windows(fr4[None], graph=False)[0], ref)
+    del m1, m2
+    # yolov2-voc.cfg: same graph, 20 classes, its own anchors
+    import test_gpu_darknet_abi as T
+    from oracle import darknet_ref
+    d = str(tmp_path)
+    cfgp, wts = os.path.join(d, "yolov2-voc.cfg"), os.path.join(d, "voc.weights")
+    darknet_ref.write_yolov2_cfg(cfgp, 20, 416)
+    txt = open(cfgp).read().replace("0.57273, 0.677385, 1.87446, 2.06253, 3.33843, 5.47434, 7.88282, 3.52778, 9.77052, 9.16828",
+                                    "1.3221, 1.73145, 3.19275, 4.00944, 5.05587, 8.09892, 9.47112, 4.84053, 11.2364, 10.0071")
+    assert "1.3221" in txt
+    open(cfgp, "w").write(txt)
+    W.write_darknet_weights(wts, W.synthetic_yolo_weights(20, seed=0), 20, major=0, minor=2, seen=12345)   # v0.2 header
+    lib = T.bind(C.CDLL(os.path.join(os.path.dirname(W.__file__), "libb200track.so")))
+    net = lib.load_network(cfgp.encode(), wts.encode(), 0)
+    assert net and lib.network_width(net) == 416
+    dd = lib.layer_dims(net, 31)
+    assert (dd.h, dd.w, dd.c) == (13, 13, 125)
+    if darknet_ref.available():
+        ref_lib = T.bind(C.CDLL(darknet_ref.LIB_PATH))
+        cwd = os.getcwd()
+        net_r = ref_lib.load_network(cfgp.encode(), wts.encode(), 0)
+        os.chdir(cwd)
+        names = os.path.join(d, "voc.names")
+        open(names, "w").write("\n".join(f"c{i}" for i in range(20)) + "\n")
+        data = os.path.join(d, "voc.data")
+        open(data, "w").write(f"classes= 20\nnames = {names}\n")
+        meta = lib.get_metadata(data.encode())
+        frame = np.random.default_rng(9).integers(0, 256, (416, 416, 3), dtype=np.uint8)
+        ra = T.detect(ref_lib, net_r, meta, T.as_image(frame), thresh=.3)
+        rb = T.detect(lib, net, meta, T.as_image(frame), thresh=.3)
+        assert [x[0] for x in ra] == [x[0] for x in rb]
+        for (n1, p1, b1), (n2, p2, b2) in zip(ra, rb):
+            assert abs(p1 - p2) < 2e-4 and np.abs(np.array(b1) - np.array(b2)).max() < 5e-2
