@@ -82,7 +82,9 @@ class MultiObjDetTracker:
         det = detector_weights_from_arrays(arrays, self.CLASS)
         if det is not None:
             self.model.set_weights(det) if self.model is not None else self.detector.model.set_weights(det)
-        self.INITIAL_EPOCH = int(path.split('-')[2]) if path.count('-') >= 2 and path.split('-')[2].isdigit() else 0
+        import re
+        m = re.search(r"-CHKPNT-(\d+)-", path)                # MultiObjDetTracker.py:293: int(path.split('-')[2])
+        self.INITIAL_EPOCH = int(m.group(1)) if m else 0
         return convlstm_weights_from_arrays(arrays)
 
     def load_weights(self, path: Optional[str] = None):
