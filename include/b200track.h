@@ -94,6 +94,12 @@ int  b2t_yolo_forward(b2t_ctx *ctx, const void *frames_dev, int frame_dtype, int
  * layers of step i+1 (BaseTracker.track_windows(pipeline=True)). */
 int  b2t_yolo_forward_range(b2t_ctx *ctx, const void *frames_dev, int frame_dtype, int batch, int conv_first,
                             int conv_last, float *logits_dev, void *stream);
+/* Frame ingest without a staging copy: the step's uint8 frames are n_seg segments of seg_frames consecutive frames,
+ * seg_stride_bytes apart (S streams x T frames of longer device-resident clips).  Fills the context's input buffer; a
+ * following b2t_yolo_forward[_range](frames_dev = NULL, B2T_FRAME_U8, batch = n_seg * seg_frames) starts at conv_1, so
+ * the forward pass can live in a CUDA graph while the input pointer changes every step. */
+int  b2t_ingest_frames(b2t_ctx *ctx, const unsigned char *frames_dev, int n_seg, int seg_frames,
+                       long long seg_stride_bytes, void *stream);
 const float *b2t_logits(const b2t_ctx *ctx);          /* device (max_batch,G,G,5*(5+C)) of the last forward */
 /* KerasYOLO.extract (KerasYOLO.py:509-520) / network_extract_feat (network.c:589-598): copy a layer's
  * post-activation output (pre-pool), NHWC float32, into out_dev.  name: "norm_1".."norm_22", "conv_23",

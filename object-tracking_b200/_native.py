@@ -44,6 +44,7 @@ SIGNATURES = {
     "b2t_finalize": (C.c_int, [_vp, C.c_int, _vp]),
     "b2t_yolo_forward": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp]),
     "b2t_yolo_forward_range": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "b2t_ingest_frames": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_longlong, _vp]),
     "b2t_logits": (_vp, [_vp]),
     "b2t_extract": (C.c_long, [_vp, C.c_char_p, C.c_int, _vp, _vp]),
     "b2t_layer_dims": (C.c_int, [_vp, C.c_char_p, _ip, _ip, _ip]),

@@ -1016,8 +1016,13 @@ static int run_conv1(b2t_ctx *c, const void *frames, int dtype, int B, cudaStrea
     ConvLayer &l = c->conv[1];
     if (l.pm && dtype == B2T_FRAME_U8) {
         // tensor-core path: frame -> fp16 integers (8 ch / pixel), then conv_pm_kernel mode 1
-        int rc = launch_frames_to_c8(frames, c->d_ws + c->off_c8, (long long)B * l.H * l.W, st);
-        if (rc) return fail(-2, "frames_to_c8 launch: %s", cudaGetErrorString((cudaError_t)rc));
+        int rc = 0;
+        if (frames) {                                     // NULL: b2t_ingest_frames already filled the fp16 frame copy
+            const long long npix = (long long)B * l.H * l.W;
+            rc = launch_frames_to_c8(frames, c->d_ws + c->off_c8, npix, npix, 0, st);
+            if (rc) return fail(-2, "frames_to_c8 launch: %s", cudaGetErrorString((cudaError_t)rc));
+            c->launches += 1;
+        }
         ConvParams p;
         memset(&p, 0, sizeof p);
         p.B = B; p.H = l.H; p.W = l.W; p.ksize = 3; p.cin_chunks = 1; p.Cout = 32; p.kbytes = 16;
@@ -1058,9 +1063,10 @@ static int run_conv1(b2t_ctx *c, const void *frames, int dtype, int B, cudaStrea
                         h[j * 16 + 7] - t0, h[j * 16 + 8] - t0);
         }
 #endif
-        c->launches += 2;
+        c->launches += 1;
         return 0;
     }
+    if (!frames) return fail(-1, "b2t_yolo_forward: frames == NULL needs uint8 frames ingested with b2t_ingest_frames");
     Conv1Params p;
     memset(&p, 0, sizeof p);
     p.frames = frames; p.dtype = dtype; p.B = B; p.H = l.H; p.W = l.W;
@@ -1080,7 +1086,8 @@ static int forward_impl(b2t_ctx *c, const void *frames, int dtype, int B, float 
                         cudaEvent_t *ev /* 24 events or NULL */, int first = 1, int last = 23) {
     if (!c || !c->finalized) return fail(-1, "b2t_yolo_forward: context not finalized");
     if (first < 1 || last > 23 || first > last) return fail(-1, "b2t_yolo_forward: bad layer range [%d, %d]", first, last);
-    if (first == 1 && !frames) return fail(-1, "b2t_yolo_forward: null frames");
+    if (first == 1 && !frames && !(c->conv[1].pm && dtype == B2T_FRAME_U8))
+        return fail(-1, "b2t_yolo_forward: null frames");
     if (B < 1 || B > c->cfg.max_batch) return fail(-1, "batch %d outside [1, max_batch=%d]", B, c->cfg.max_batch);
     if (dtype != B2T_FRAME_U8 && dtype != B2T_FRAME_F32) return fail(-1, "bad frame dtype %d", dtype);
     int rc;
@@ -1160,6 +1167,25 @@ extern "C" int b2t_yolo_forward(b2t_ctx *c, const void *frames, int dtype, int B
 extern "C" int b2t_yolo_forward_range(b2t_ctx *c, const void *frames, int dtype, int B, int first, int last,
                                       float *logits_dev, void *stream) {
     return forward_impl(c, frames, dtype, B, logits_dev, (cudaStream_t)stream, nullptr, first, last);
+}
+
+// Frame ingest without a staging copy: the uint8 frames of a step are n_seg segments of seg_frames consecutive frames,
+// seg_stride_bytes apart (S streams x T frames of longer device-resident clips).  Converts them into the context's fp16
+// frame buffer; a following b2t_yolo_forward[_range](frames_dev = NULL, B2T_FRAME_U8, batch = n_seg * seg_frames)
+// starts at conv_1.  Lets a host keep the forward pass in a CUDA graph while the input pointer changes every step.
+extern "C" int b2t_ingest_frames(b2t_ctx *c, const unsigned char *frames, int n_seg, int seg_frames, long long seg_stride_bytes,
+                                 void *stream) {
+    if (!c || !c->finalized || !frames) return fail(-1, "b2t_ingest_frames: bad arguments");
+    if (!c->conv[1].pm) return fail(-1, "b2t_ingest_frames: the tensor-core conv_1 path is not active");
+    const long long B = (long long)n_seg * seg_frames;
+    if (n_seg < 1 || seg_frames < 1 || B > c->cfg.max_batch) return fail(-1, "b2t_ingest_frames: %d x %d frames outside [1, max_batch=%d]", n_seg, seg_frames, c->cfg.max_batch);
+    const ConvLayer &l = c->conv[1];
+    const long long seg_pix = (long long)seg_frames * l.H * l.W;
+    if (n_seg > 1 && seg_stride_bytes < seg_pix * 3) return fail(-1, "b2t_ingest_frames: segments overlap");
+    const int rc = launch_frames_to_c8(frames, c->d_ws + c->off_c8, B * l.H * l.W, seg_pix, seg_stride_bytes, (cudaStream_t)stream);
+    if (rc) return fail(-2, "frames_to_c8 launch: %s", cudaGetErrorString((cudaError_t)rc));
+    c->launches += 1;
+    return 0;
 }
 
 extern "C" const float *b2t_logits(const b2t_ctx *c) {

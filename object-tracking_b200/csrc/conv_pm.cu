@@ -350,10 +350,14 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.pm_tmem_cols) : "memory");
 }
 
-// uint8 HWC3 frame -> fp16 [pixel][8] (channels 3..7 zero), the integer values 0..255 exactly
-__global__ void __launch_bounds__(256) frames_to_c8_kernel(const uint8_t *__restrict__ src, uint4 *__restrict__ dst, long long npix) {
+// uint8 HWC3 frame -> fp16 [pixel][8] (channels 3..7 zero), the integer values 0..255 exactly.  The source is n
+// segments of seg_pix pixels each, seg_stride bytes apart (S streams x T consecutive frames of longer clips: the
+// window is gathered by this kernel, no staging copy); dense input: seg_pix = npix.
+__global__ void __launch_bounds__(256) frames_to_c8_kernel(const uint8_t *__restrict__ src, uint4 *__restrict__ dst, long long npix,
+                                                           long long seg_pix, long long seg_stride) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
-        const uint8_t *s = src + 3 * i;
+        const long long seg = i / seg_pix;
+        const uint8_t *s = src + seg * seg_stride + 3 * (i - seg * seg_pix);
         const __half2 a = __floats2half2_rn((float)s[0], (float)s[1]);
         const __half2 b = __floats2half2_rn((float)s[2], 0.f);
         uint4 o;
@@ -386,9 +390,10 @@ int launch_conv_pm(int n_sm, const CUtensorMap &x_hi, const CUtensorMap &x_lo, c
     return (int)launch_pdl(conv_pm_kernel, dim3(grid), dim3(kPmThreads), smem, st, x_hi, x_lo, w_hi, w_lo, p);
 }
 
-int launch_frames_to_c8(const void *frames, void *dst, long long npix, cudaStream_t st) {
+int launch_frames_to_c8(const void *frames, void *dst, long long npix, long long seg_pix, long long seg_stride, cudaStream_t st) {
     const int blocks = (int)((npix + 255) / 256 < 148 * 16 ? (npix + 255) / 256 : 148 * 16);
-    frames_to_c8_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint8_t *>(frames), reinterpret_cast<uint4 *>(dst), npix);
+    frames_to_c8_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint8_t *>(frames), reinterpret_cast<uint4 *>(dst), npix,
+                                                seg_pix, seg_stride);
     return (int)cudaGetLastError();
 }
 

@@ -136,7 +136,7 @@ int conv_pm_init();
 int conv_pm_smem_bytes(const ConvParams &p);
 int launch_conv_pm(int n_sm, const CUtensorMap &x_hi, const CUtensorMap &x_lo, const CUtensorMap &w_hi,
                    const CUtensorMap &w_lo, const ConvParams &p, cudaStream_t st);
-int launch_frames_to_c8(const void *frames, void *dst, long long npix, cudaStream_t st);
+int launch_frames_to_c8(const void *frames, void *dst, long long npix, long long seg_pix, long long seg_stride, cudaStream_t st);
 int launch_splitk_epilogue(const ConvParams &p, cudaStream_t st);
 int launch_conv_simt(const SimtView &v, const ConvParams &p, cudaStream_t st);
 int launch_conv1(const Conv1Params &p, cudaStream_t st);

@@ -155,6 +155,36 @@ class DetectorEngine:
             raise ValueError("frames must be uint8 or float32")
         N.check(self.lib.b2t_yolo_forward_range(self.h, frames.data_ptr(), dt, frames.shape[0], first, last, None, _stream()))
 
+    # ---------------------------------------------------------------- ingest without a staging copy
+    def can_ingest(self, frames: torch.Tensor) -> bool:
+        """(S,T,H,W,3) uint8 windows whose per-stream blocks frames[s] are contiguous (views of longer clips are)."""
+        if frames.dim() != 5 or frames.dtype != torch.uint8 or frames.device != self.device:
+            return False
+        S, T, H, W, C3 = frames.shape
+        if (H, W, C3) != (self.image_size, self.image_size, 3) or S * T > self.max_batch:
+            return False
+        st = frames.stride()
+        return st[4] == 1 and st[3] == 3 and st[2] == 3 * W and st[1] == 3 * W * H and (S == 1 or st[0] >= T * H * W * 3)
+
+    def ingest_windows(self, frames: torch.Tensor) -> None:
+        """Gather S windows of T frames straight into the engine's input buffer (no staging copy); follow with
+        forward_ingested(S*T)."""
+        S, T = frames.shape[0], frames.shape[1]
+        N.check(self.lib.b2t_ingest_frames(self.h, frames.data_ptr(), S, T, frames.stride(0) if S > 1 else 0, _stream()))
+
+    def forward_ingested(self, B: int, first: int = 1, last: int = 23) -> torch.Tensor:
+        """conv_first..conv_last on the frames ingest_windows() placed in the input buffer.  Capturable in a CUDA graph
+        whose input changes every replay."""
+        ev = self.forward_events
+        if ev is not None:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+        N.check(self.lib.b2t_yolo_forward_range(self.h, None, N.FRAME_U8, B, first, last, None, _stream()))
+        if ev is not None:
+            b.record()
+            ev.append((a, b))
+        return self.logits(B)
+
     def logits(self, B: int) -> torch.Tensor:
         """Zero-copy view of the context's logits buffer (it lives inside the torch-owned workspace)."""
         if self._logits_view is None:

@@ -128,31 +128,44 @@ class BaseTracker(object):
         if getattr(self, "tail_done", None) is not None:       # a pipelined call may still be in its tail
             torch.cuda.current_stream().wait_event(self.tail_done)
             self.tail_done = None
-        key = (S, T, H, W, frames.dtype, bool(reset))
+        # uint8 windows whose per-stream blocks are contiguous are gathered by the ingest kernel itself (no staging
+        # copy; the graph starts at conv_1); anything else is copied into a static input tensor first
+        ingest = eng.can_ingest(frames)
+        key = (S, T, H, W, frames.dtype, bool(reset), ingest)
         g = self._graphs.get(key)
         if g is None:
-            static_in = torch.empty((S * T, H, W, 3), dtype=frames.dtype, device=frames.device)
-            static_in.view(S, T, H, W, 3).copy_(frames)
+            static_in = None
+            if not ingest:
+                static_in = torch.empty((S * T, H, W, 3), dtype=frames.dtype, device=frames.device)
+                static_in.view(S, T, H, W, 3).copy_(frames)
+            fwd = (lambda: eng.forward_ingested(S * T)) if ingest else (lambda: eng.forward(static_in))
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):                      # warm-up outside capture (allocations, lazy init)
-                eng.forward(static_in)
+                if ingest:
+                    eng.ingest_windows(frames)
+                fwd()
                 self._tail(S, T, W, H, reset)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
+            ev, eng.forward_events = eng.forward_events, None   # no event records inside a capture
             n0 = eng.lib.b2t_launch_count(eng.h)
             g_fwd, g_tail = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             with torch.cuda.graph(g_fwd):
-                eng.forward(static_in)
+                fwd()
             with torch.cuda.graph(g_tail):
                 static_out = self._tail(S, T, W, H, reset)
+            eng.forward_events = ev
             g = self._graphs[key] = (g_fwd, g_tail, static_in, static_out, eng.lib.b2t_launch_count(eng.h) - n0)
         g_fwd, g_tail, static_in, static_out, n_kernels = g
-        static_in.view(S, T, H, W, 3).copy_(frames, non_blocking=True)     # strided views welcome: one copy
         ev = eng.forward_events
         if ev is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
+        if ingest:
+            eng.ingest_windows(frames)
+        else:
+            static_in.view(S, T, H, W, 3).copy_(frames, non_blocking=True)
         g_fwd.replay()
         if ev is not None:
             e1.record()
@@ -166,37 +179,54 @@ class BaseTracker(object):
     def _track_windows_pipelined(self, frames: torch.Tensor, reset: bool) -> torch.Tensor:
         S, T, H, W = frames.shape[0], frames.shape[1], frames.shape[2], frames.shape[3]
         eng = self.model_detector.engine
-        key = ("pipe", S, T, H, W, frames.dtype, bool(reset))
+        ingest = eng.can_ingest(frames)
+        key = ("pipe", S, T, H, W, frames.dtype, bool(reset), ingest)
         g = self._graphs.get(key)
         if g is None:
-            static_in = torch.empty((S * T, H, W, 3), dtype=frames.dtype, device=frames.device)
-            static_in.view(S, T, H, W, 3).copy_(frames)
+            static_in = None
+            if not ingest:
+                static_in = torch.empty((S * T, H, W, 3), dtype=frames.dtype, device=frames.device)
+                static_in.view(S, T, H, W, 3).copy_(frames)
+            if ingest:
+                fwd_a = lambda: eng.forward_ingested(S * T, 1, self._SPLIT)
+                fwd_b = lambda: eng.forward_ingested(S * T, self._SPLIT + 1, 23)
+            else:
+                fwd_a = lambda: eng.forward_range(static_in, 1, self._SPLIT)
+                fwd_b = lambda: eng.forward_range(static_in, self._SPLIT + 1, 23)
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):                      # warm-up outside capture (allocations, lazy init)
-                eng.forward(static_in)
+                if ingest:
+                    eng.ingest_windows(frames)
+                fwd_a()
+                fwd_b()
                 self._tail(S, T, W, H, reset)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
+            ev, eng.forward_events = eng.forward_events, None
             n0 = eng.lib.b2t_launch_count(eng.h)
             g_a, g_b, g_tail = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             with torch.cuda.graph(g_a):
-                eng.forward_range(static_in, 1, self._SPLIT)
+                fwd_a()
             with torch.cuda.graph(g_b):
-                eng.forward_range(static_in, self._SPLIT + 1, 23)
+                fwd_b()
             with torch.cuda.graph(g_tail):
                 static_out = self._tail(S, T, W, H, reset)
+            eng.forward_events = ev
             g = self._graphs[key] = (g_a, g_b, g_tail, static_in, static_out, eng.lib.b2t_launch_count(eng.h) - n0)
             if getattr(self, "tail_stream", None) is None:
                 self.tail_stream = torch.cuda.Stream()
                 self.tail_done = None
         g_a, g_b, g_tail, static_in, static_out, n_kernels = g
         cur = torch.cuda.current_stream()
-        static_in.view(S, T, H, W, 3).copy_(frames, non_blocking=True)
         ev = eng.forward_events
         if ev is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
+        if ingest:
+            eng.ingest_windows(frames)
+        else:
+            static_in.view(S, T, H, W, 3).copy_(frames, non_blocking=True)
         g_a.replay()                                           # conv_1 .. conv_8: overlaps the previous call's tail
         if self.tail_done is not None:
             cur.wait_event(self.tail_done)                     # conv_9 .. 23 overwrite what that tail reads

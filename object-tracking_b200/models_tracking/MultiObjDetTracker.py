@@ -105,9 +105,10 @@ class MultiObjDetTracker:
             self._steps[stream] = 0
 
     # ------------------------------------------------------------------ batched device API
-    def _window_kernels(self, static_in: torch.Tensor, S: int, T: int, reset: bool, decode_detector: bool):
+    def _window_kernels(self, static_in: Optional[torch.Tensor], S: int, T: int, reset: bool, decode_detector: bool):
+        """static_in None: the frames were placed by eng.ingest_windows()."""
         eng = self.model
-        det_logits = eng.forward(static_in)
+        det_logits = eng.forward(static_in) if static_in is not None else eng.forward_ingested(S * T)
         trk_logits = eng.convlstm_sequence(S, T, 0, reset)
         boxes, counts = eng.decode(trk_logits, self.OBJ_THRESHOLD, self.NMS_THRESHOLD, self.ANCHORS, tag="trk")
         out = [trk_logits, boxes, counts]
@@ -121,35 +122,46 @@ class MultiObjDetTracker:
         -> (trk_logits (S*T,G,G,A,5+C), boxes (S*T,max,8), counts (S*T)) device tensors, frame index s*T + t:
         the tracker output decoded like MultiObjDetTracker.predict (:309-310).  One batched detector pass, one
         batched ConvLSTM input conv, T recurrent steps over the S streams, one batched head, one decode launch;
-        with graph=True the whole call replays as ONE CUDA graph captured on first use.  The tensors are reused."""
+        with graph=True the whole call replays as ONE CUDA graph captured on first use (uint8 windows are gathered by
+        the ingest kernel in front of it, no staging copy).  The tensors are reused."""
         S, T, H, W = frames.shape[0], frames.shape[1], frames.shape[2], frames.shape[3]
         if S * T > self.detector.BATCH_SIZE:
             raise ValueError(f"{S} streams x {T} frames > detector batch {self.detector.BATCH_SIZE}")
         eng = self.model
         if not graph:
             return tuple(self._window_kernels(frames.reshape(S * T, H, W, 3).contiguous(), S, T, reset, False))
-        key = (S, T, H, W, frames.dtype, bool(reset))
+        ingest = eng.can_ingest(frames)
+        key = (S, T, H, W, frames.dtype, bool(reset), ingest)
         g = self._graphs.get(key)
         if g is None:
-            static_in = torch.empty((S * T, H, W, 3), dtype=frames.dtype, device=frames.device)
-            static_in.view(S, T, H, W, 3).copy_(frames)
+            static_in = None
+            if not ingest:
+                static_in = torch.empty((S * T, H, W, 3), dtype=frames.dtype, device=frames.device)
+                static_in.view(S, T, H, W, 3).copy_(frames)
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):                      # warm-up outside capture (allocations, lazy init)
+                if ingest:
+                    eng.ingest_windows(frames)
                 self._window_kernels(static_in, S, T, reset, False)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
+            ev, eng.forward_events = eng.forward_events, None   # no event records inside a capture
             n0 = eng.lib.b2t_launch_count(eng.h)
             gr = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gr):
                 outs = self._window_kernels(static_in, S, T, reset, False)
+            eng.forward_events = ev
             g = self._graphs[key] = (gr, static_in, outs, eng.lib.b2t_launch_count(eng.h) - n0)
         gr, static_in, outs, n_kernels = g
-        static_in.view(S, T, H, W, 3).copy_(frames, non_blocking=True)
         ev = eng.forward_events
         if ev is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
+        if ingest:
+            eng.ingest_windows(frames)
+        else:
+            static_in.view(S, T, H, W, 3).copy_(frames, non_blocking=True)
         gr.replay()
         if ev is not None:
             e1.record()

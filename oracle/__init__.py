@@ -16,7 +16,14 @@ tensorflow).  What *is* pinned, by ``oracle/make_golden.py`` run in the build co
   ``.weights`` file and input (conv/BN/leaky/maxpool/reorg/route/region);
 * ``darknet_oracle`` box decode + ``do_nms_obj`` == the same library's outputs.
 
+* ``tracker_oracle.generate_heatmap_feat / generate_rectangle_from_heatmap`` == the reference's own
+  ``utility/utils.py:53-79`` exec'd from ``/root/reference`` (3 000 cases; 96 outputs committed);
+* ``ingest_oracle`` == the installed OpenCV's ``cv2.resize`` (bit-exact);
+* the JPEG decoder's fixtures == ``load_image_color`` of the reference C library (bit-exact).
+
 The Keras-only semantics (BN eps 1e-3, tf.space_to_depth ordering, LSTM / ConvLSTM2D gate
 equations) are restated from the published Keras 2 definitions: for those rows parity is
-"unpinned" in the sense of the task statement and DESIGN.md says so.
+"unpinned" in the sense of the task statement and DESIGN.md says so.  Their structure (gate order,
+weight layouts, state update) is cross-checked against independent implementations --
+``torch.nn.LSTMCell`` and a torch ``conv2d`` composition -- in ``tests/test_oracle_cpu.py``.
 """

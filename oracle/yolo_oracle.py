@@ -6,8 +6,9 @@ batchnorm_layer.c:135-155 -> blas.c:147-158 ``normalize_cpu``, activations.h:38 
 maxpool_layer.c:79-114, reorg_layer.c:91-110 -> blas.c:9-30 ``reorg_cpu``, route_layer.c:74-87).
 
 torch-CPU ``conv2d`` is the only non-numpy arithmetic; float64 is the primary oracle, float32
-quantifies the fp32 noise floor.  Pinned against ``oracle/_ref/libdarknet.so`` by
-``oracle/make_golden.py`` / ``tests/test_oracle_vs_darknet.py``.
+quantifies the fp32 noise floor.  Its darknet mode is pinned against ``oracle/_ref/libdarknet.so`` (the reference's C
+library): ``oracle/make_golden.py darknet`` asserts the agreement when it writes ``tests/golden/darknet_416.npz`` and
+``tests/test_oracle_cpu.py`` re-checks the oracle against those committed library outputs.
 """
 from __future__ import annotations
 

@@ -520,3 +520,31 @@ def test_tracker_checkpoints_and_voc_cfg(tmp_path):
         assert [x[0] for x in ra] == [x[0] for x in rb]
         for (n1, p1, b1), (n2, p2, b2) in zip(ra, rb):
             assert abs(p1 - p2) < 2e-4 and np.abs(np.array(b1) - np.array(b2)).max() < 5e-2
+
+
+def test_strided_window_ingest_equals_copy_path():
+    """Windows that are views of longer device-resident clips are gathered by the ingest kernel (b2t_ingest_frames), no
+    staging copy: same numbers as the eager path on a contiguous copy, serial and pipelined, TinyTracker and
+    MultiObjDetTracker."""
+    from object_tracking_b200.models_tracking.TinyTracker import TinyTracker
+    from object_tracking_b200.models_tracking.MultiObjDetTracker import MultiObjDetTracker
+    clip = torch.from_numpy(np.random.default_rng(31).integers(0, 256, (2, 12, 416, 416, 3), dtype=np.uint8)).cuda()
+    trk = TinyTracker(TRACKER_CFG, max_streams=2)
+    eng = trk.model_detector.engine
+    for j in (0, 4, 8):
+        win = clip[:, j:j + 4]
+        assert not win.is_contiguous() and eng.can_ingest(win)
+        ref = trk.track_windows(win.contiguous(), graph=False).clone()
+        assert torch.equal(trk.track_windows(win), ref)
+        y = trk.track_windows(win, pipeline=True)
+        with torch.cuda.stream(trk.tail_stream):
+            yp = y.clone()
+        torch.cuda.synchronize()
+        assert torch.equal(yp, ref)
+    assert not eng.can_ingest(clip[:, ::2][:, :4])              # frames of a stream must be consecutive in memory
+    del trk
+    mt = MultiObjDetTracker({"LABELS": ["a", "b"]}, convlstm_units=64, max_streams=2)
+    win = clip[:, 3:7]
+    ref = [t.clone() for t in mt.track_windows(win.contiguous(), graph=False)]
+    got = mt.track_windows(win)
+    assert torch.equal(got[0], ref[0]) and torch.equal(got[2], ref[2])
