@@ -808,7 +808,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_chain_kernel(const __gri
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (tr) trace[L * 8 + 5] = clock64();
             if (p.splits > 1) {                                   // every CTA's partials are written: finish a slice
-                splitk_finish_range(p, (long long)blockIdx.x * kEpiThreads + et, (long long)G * kEpiThreads);
+                // work items are dealt to WARPS round-robin over the CTAs (warp w of CTA b = global warp w*G + b), 32
+                // consecutive items per warp: a layer with fewer items than threads still loads every SM's L2 port
+                splitk_finish_range(p, ((long long)(et >> 5) * G + blockIdx.x) * 32 + (et & 31), (long long)G * kEpiThreads);
                 asm volatile("fence.acq_rel.gpu;" ::: "memory");
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 done += G;
