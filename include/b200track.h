@@ -188,6 +188,17 @@ int  b2t_convlstm_sequence(b2t_ctx *ctx, int n_streams, int n_steps, int slot0, 
                            int hard_sigmoid, void *stream);
 int  b2t_convlstm_window(b2t_ctx *ctx, int batch, float *trk_logits_dev, int hard_sigmoid, void *stream);
 
+/* ---- callers after the path ---------------------------------------------------- */
+/* draw_boxes (utils.py:190-206): cv2.rectangle(image, (xmin,ymin), (xmax,ymax), colour, 3) for the first counts[b] rows
+ * [x,y,w,h,...] (b2t_decode_nms layout, image-relative centre form) of every frame, in place on (B,H,W,3) uint8 frames;
+ * pixel-identical to OpenCV's thickness-3 rectangle.  The cv2.putText label stays on the host. */
+int  b2t_draw_boxes(b2t_ctx *ctx, unsigned char *frames_dev, int batch, int h, int w, const float *rows_dev,
+                    const int *counts_dev, int max_rows, int c0, int c1, int c2, void *stream);
+/* overlap_score / average_overlap_score (utils.py:82-110): n pairs of corner boxes (x1,y1,x2,y2), float64 like the
+ * reference's Python floats -> scores_dev (n) and their left-to-right mean (mean_dev, may be NULL), bit-identical. */
+int  b2t_overlap_scores(b2t_ctx *ctx, const double *y_true_dev, const double *y_pred_dev, int n, double *scores_dev,
+                        double *mean_dev, void *stream);
+
 /* ---- CUDA graphs: one launch per step for a plain-C host ---------------- */
 /* Capture every b2t_* call made on `stream` between begin and end (all entry points are stream-ordered; the ones that
  * synchronise -- b2t_finalize, b2t_lstm_set_weights, the first b2t_resize_frames of a geometry -- must precede the

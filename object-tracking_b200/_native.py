@@ -70,6 +70,8 @@ SIGNATURES = {
     "b2t_convlstm_window": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp]),
     "b2t_convlstm_reset_slots": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "b2t_convlstm_sequence": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp]),
+    "b2t_draw_boxes": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
+    "b2t_overlap_scores": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, _vp, _vp]),
     "b2t_graph_begin": (C.c_int, [_vp, _vp]),
     "b2t_graph_end": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
     "b2t_graph_launch": (C.c_int, [_vp, _vp]),

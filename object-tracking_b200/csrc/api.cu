@@ -1576,6 +1576,26 @@ extern "C" int b2t_select_detection(b2t_ctx *c, const float *dets, const int *co
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ callers after the path
+extern "C" int b2t_draw_boxes(b2t_ctx *c, unsigned char *frames_dev, int B, int H, int W, const float *rows_dev,
+                              const int *counts_dev, int max_rows, int c0, int c1, int c2, void *stream) {
+    if (!frames_dev || !rows_dev || !counts_dev || B < 1 || H < 1 || W < 1 || max_rows < 1) return fail(-1, "b2t_draw_boxes: bad arguments");
+    if (max_rows > 65535 || B > 65535) return fail(-1, "b2t_draw_boxes: more than 65535 boxes per frame / frames");
+    const int rc = launch_draw_boxes(frames_dev, B, H, W, rows_dev, counts_dev, max_rows, c0, c1, c2, (cudaStream_t)stream);
+    if (rc) return fail(-2, "draw_boxes launch: %s", cudaGetErrorString((cudaError_t)rc));
+    if (c) c->launches += 1;
+    return 0;
+}
+
+extern "C" int b2t_overlap_scores(b2t_ctx *c, const double *y_true_dev, const double *y_pred_dev, int n, double *scores_dev,
+                                  double *mean_dev, void *stream) {
+    if (!y_true_dev || !y_pred_dev || !scores_dev || n < 1) return fail(-1, "b2t_overlap_scores: bad arguments");
+    const int rc = launch_overlap_scores(y_true_dev, y_pred_dev, n, scores_dev, mean_dev, (cudaStream_t)stream);
+    if (rc) return fail(-2, "overlap_scores launch: %s", cudaGetErrorString((cudaError_t)rc));
+    if (c) c->launches += 1;
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ CUDA graphs
 // A step of this path is 30-45 kernel launches of a few microseconds each: replayed eagerly it is launch-latency
 // bound.  These four calls let a plain-C host capture any sequence of b2t_* calls made on `stream` (every entry point is

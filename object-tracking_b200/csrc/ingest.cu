@@ -71,6 +71,79 @@ __global__ void __launch_bounds__(256) letterbox_u8_kernel(const LetterboxParams
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Callers after the path.
+//
+// draw_boxes (utility/utils.py:190-206): cv2.rectangle(image, (xmin, ymin), (xmax, ymax), colour, 3) for every decoded
+// box, on the device, in place.  OpenCV rasterises a thickness-3 segment as the pixel set
+// { max(0, a - u, u - b) + |v - c| <= 2 }  (u along the segment [a, b], v across it at c): a 5-pixel band with
+// diamond-cut ends; a rectangle is the union of its four edges.  Pinned against cv2.rectangle itself
+// (tests/test_oracle_cpu.py for the rule, tests/test_gpu_parity_r2.py for the kernel).  The text label of
+// cv2.putText stays on the host.  Box corners follow the reference's arithmetic under numpy >= 2 (float32):
+// int((x -/+ w/2) * W), int((y -/+ h/2) * H), truncation toward zero.
+__global__ void draw_boxes_kernel(unsigned char *frames, int B, int H, int W, const float *rows, const int *counts, int max_rows,
+                                  unsigned char c0, unsigned char c1, unsigned char c2) {
+    const int b = blockIdx.y, k = blockIdx.x;
+    if (b >= B || k >= min(counts[b], max_rows)) return;
+    const float *r = rows + ((long long)b * max_rows + k) * 8;
+    const float hw = __fdiv_rn(r[2], 2.f), hh = __fdiv_rn(r[3], 2.f);
+    int xa = (int)__fmul_rn(__fsub_rn(r[0], hw), (float)W), xb = (int)__fmul_rn(__fadd_rn(r[0], hw), (float)W);
+    int ya = (int)__fmul_rn(__fsub_rn(r[1], hh), (float)H), yb = (int)__fmul_rn(__fadd_rn(r[1], hh), (float)H);
+    if (xa > xb) { const int t = xa; xa = xb; xb = t; }
+    if (ya > yb) { const int t = ya; ya = yb; yb = t; }
+    unsigned char *img = frames + (long long)b * H * W * 3;
+    auto put = [&](int x, int y) {
+        if (x >= 0 && x < W && y >= 0 && y < H) {
+            unsigned char *p = img + ((long long)y * W + x) * 3;
+            p[0] = c0; p[1] = c1; p[2] = c2;
+        }
+    };
+    // horizontal edges at y = ya, yb: u = x in [xa, xb]; vertical edges at x = xa, xb: u = y in [ya, yb]
+    const int lh = xb - xa + 5, lv = yb - ya + 5;
+    for (int i = threadIdx.x; i < 5 * lh; i += blockDim.x) {
+        const int dv = i / lh - 2, x = xa - 2 + i % lh;
+        const int out = max(0, max(xa - x, x - xb));
+        if (out + abs(dv) <= 2) { put(x, ya + dv); put(x, yb + dv); }
+    }
+    for (int i = threadIdx.x; i < 5 * lv; i += blockDim.x) {
+        const int dv = i / lv - 2, y = ya - 2 + i % lv;
+        const int out = max(0, max(ya - y, y - yb));
+        if (out + abs(dv) <= 2) { put(xa + dv, y); put(xb + dv, y); }
+    }
+}
+
+int launch_draw_boxes(unsigned char *frames, int B, int H, int W, const float *rows, const int *counts, int max_rows,
+                      int c0, int c1, int c2, cudaStream_t st) {
+    draw_boxes_kernel<<<dim3(max_rows, B), 128, 0, st>>>(frames, B, H, W, rows, counts, max_rows, (unsigned char)c0,
+                                                         (unsigned char)c1, (unsigned char)c2);
+    return (int)cudaGetLastError();
+}
+
+// overlap_score / average_overlap_score (utility/utils.py:82-110) for n pairs of corner boxes (x1, y1, x2, y2) in
+// float64, the reference's arithmetic (Python floats): |dx*dy| products without clamping an empty intersection, and
+// the mean accumulated left to right.  One thread per pair, then thread 0 sums in order (bit-identical to the loop).
+__global__ void overlap_scores_kernel(const double *t, const double *p, int n, double *scores, double *mean) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double *a = t + 4 * i, *b = p + 4 * i;
+        const double x1 = fmax(a[0], b[0]), y1 = fmax(a[1], b[1]), x2 = fmin(a[2], b[2]), y2 = fmin(a[3], b[3]);
+        const double inter = fabs(__dmul_rn(__dsub_rn(x1, x2), __dsub_rn(y1, y2)));
+        const double uni = __dsub_rn(__dadd_rn(fabs(__dmul_rn(__dsub_rn(a[0], a[2]), __dsub_rn(a[1], a[3]))),
+                                               fabs(__dmul_rn(__dsub_rn(b[0], b[2]), __dsub_rn(b[1], b[3])))), inter);
+        scores[i] = __ddiv_rn(inter, uni);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && mean) {
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) s = __dadd_rn(s, scores[i]);
+        *mean = __ddiv_rn(s, (double)n);
+    }
+}
+
+int launch_overlap_scores(const double *t, const double *p, int n, double *scores, double *mean, cudaStream_t st) {
+    overlap_scores_kernel<<<1, 256, 0, st>>>(t, p, n, scores, mean);
+    return (int)cudaGetLastError();
+}
+
 int launch_letterbox_u8(const LetterboxParams &p, cudaStream_t st) {
     const long long total = (long long)p.B * p.net_h * p.net_w * 3;
     const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);

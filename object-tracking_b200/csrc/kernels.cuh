@@ -155,5 +155,8 @@ int launch_box_from_heatmap(const float *heat, int n, int size, float thresh, in
 int launch_resize_bilinear_u8(const ResizeParams &p, cudaStream_t st);
 int launch_letterbox_u8(const LetterboxParams &p, cudaStream_t st);
 int launch_convlstm_gates(const ConvLstmGateParams &p, cudaStream_t st);
+int launch_draw_boxes(unsigned char *frames, int B, int H, int W, const float *rows, const int *counts, int max_rows,
+                      int c0, int c1, int c2, cudaStream_t st);
+int launch_overlap_scores(const double *t, const double *p, int n, double *scores, double *mean, cudaStream_t st);
 
 }  // namespace b2t

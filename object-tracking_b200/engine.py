@@ -303,6 +303,26 @@ class DetectorEngine:
         N.check(self.lib.b2t_box_from_heatmap(self.h, heat.data_ptr(), n, size, thresh, rect.data_ptr(), _stream()))
         return rect
 
+    # ---------------------------------------------------------------- callers after the path
+    def draw_boxes(self, frames: torch.Tensor, rows: torch.Tensor, counts: torch.Tensor, color=(0, 255, 0)) -> torch.Tensor:
+        """utils.draw_boxes' rectangles (cv2.rectangle, thickness 3) on (B,H,W,3) uint8 device frames, in place, for the
+        first counts[b] decode rows of each frame.  Pixel-identical to OpenCV; text labels are a host job."""
+        B, H, W, _ = frames.shape
+        if frames.dtype != torch.uint8 or not frames.is_contiguous():
+            raise ValueError("draw_boxes expects contiguous uint8 frames")
+        N.check(self.lib.b2t_draw_boxes(self.h, frames.data_ptr(), B, H, W, rows.data_ptr(), counts.data_ptr(), rows.shape[1],
+                                        int(color[0]), int(color[1]), int(color[2]), _stream()))
+        return frames
+
+    def overlap_scores(self, y_true: torch.Tensor, y_pred: torch.Tensor):
+        """utils.overlap_score for n pairs of (x1,y1,x2,y2) float64 rows + average_overlap_score -> (scores (n), mean)."""
+        n = y_true.shape[0]
+        scores = torch.empty(n, dtype=torch.float64, device=self.device)
+        mean = torch.empty(1, dtype=torch.float64, device=self.device)
+        N.check(self.lib.b2t_overlap_scores(self.h, y_true.contiguous().data_ptr(), y_pred.contiguous().data_ptr(), n,
+                                            scores.data_ptr(), mean.data_ptr(), _stream()))
+        return scores, mean
+
     # ---------------------------------------------------------------- ConvLSTM (MultiObjDetTracker)
     def convlstm_reset(self) -> None:
         N.check(self.lib.b2t_convlstm_reset(self.h, _stream()))

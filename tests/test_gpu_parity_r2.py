@@ -548,3 +548,38 @@ def test_strided_window_ingest_equals_copy_path():
     ref = [t.clone() for t in mt.track_windows(win.contiguous(), graph=False)]
     got = mt.track_windows(win)
     assert torch.equal(got[0], ref[0]) and torch.equal(got[2], ref[2])
+
+
+# ------------------------------------------------------------------------------------------------ callers after the path (8f rank 3)
+def test_device_overlay_and_overlap_metric():
+    """b2t_draw_boxes == cv2.rectangle(..., thickness 3) on decoded boxes (utils.draw_boxes without the text label),
+    b2t_overlap_scores == utils.overlap_score / average_overlap_score in float64, bit for bit."""
+    import cv2
+    from oracle import overlay_oracle
+    from object_tracking_b200.utility import utils as U
+    eng = _engine(n_class=2, max_batch=1)
+    rng = np.random.default_rng(12)
+    B, H, W, M = 3, 300, 420, 40
+    frames = rng.integers(0, 256, (B, H, W, 3), dtype=np.uint8)
+    rows = np.zeros((B, M, 8), np.float32)
+    rows[..., 0:2] = rng.uniform(-0.05, 1.05, (B, M, 2))
+    rows[..., 2:4] = rng.uniform(0.0, 0.6, (B, M, 2))
+    rows[0, 0, :4] = (0.5, 0.5, 0.0, 0.0)                              # degenerate: a point
+    rows[0, 1, :4] = (0.5, 0.5, 1.5, 1.5)                              # larger than the frame: nothing visible but clipping
+    counts = np.array([M, 7, 0], np.int32)
+    got = eng.draw_boxes(torch.from_numpy(frames.copy()).cuda(), torch.from_numpy(rows).cuda(),
+                         torch.from_numpy(counts).cuda()).cpu().numpy()
+    for b in range(B):
+        ref = frames[b].copy()
+        for r in rows[b, :counts[b]]:
+            xa, ya, xb, yb = overlay_oracle.box_corners(r, W, H)
+            cv2.rectangle(ref, (xa, ya), (xb, yb), (0, 255, 0), 3)
+        assert np.array_equal(got[b], ref), b
+    assert np.array_equal(got[2], frames[2])
+    n = 257
+    t = rng.uniform(0, 1, (n, 4)); p = rng.uniform(0, 1, (n, 4))
+    t[:, 2:] += t[:, :2]; p[:, 2:] += p[:, :2]
+    s, m = eng.overlap_scores(torch.from_numpy(t).cuda(), torch.from_numpy(p).cuda())
+    ref_s = np.array([U.overlap_score(t[i], p[i]) for i in range(n)])
+    assert np.array_equal(s.cpu().numpy(), ref_s)
+    assert float(m.cpu()[0]) == U.average_overlap_score(t, p)

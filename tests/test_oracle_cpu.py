@@ -232,3 +232,20 @@ def test_planted_synthetic_detector_emits_allowed_classes():
             assert np.array_equal(a[k], b[k]), k
     d = (b["bias_23"] - a["bias_23"]).reshape(5, 85)
     assert np.allclose(d[:, 5], 10.0) and np.allclose(d[:, 7], 9.0) and np.count_nonzero(d) == 10
+
+
+def test_overlay_oracle_matches_cv2_rectangle():
+    """draw_boxes' cv2.rectangle(..., thickness 3) restated as a pixel-set rule == the installed OpenCV, incl. clipped,
+    reversed and degenerate rectangles."""
+    import cv2
+    from oracle import overlay_oracle
+    rng = np.random.default_rng(0)
+    for _ in range(150):
+        H, W = int(rng.integers(20, 90)), int(rng.integers(20, 90))
+        a, b = np.zeros((H, W, 3), np.uint8), np.zeros((H, W, 3), np.uint8)
+        for _ in range(3):
+            x1, x2 = (int(v) for v in rng.integers(-15, W + 15, 2))
+            y1, y2 = (int(v) for v in rng.integers(-15, H + 15, 2))
+            cv2.rectangle(a, (x1, y1), (x2, y2), (0, 255, 0), 3)
+            overlay_oracle.rectangle3(b, x1, y1, x2, y2, (0, 255, 0))
+        assert np.array_equal(a, b)
