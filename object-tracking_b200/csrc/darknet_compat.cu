@@ -328,7 +328,7 @@ image load_image_color(char *filename, int w, int h) {
         }
         buf.assign(file.begin() + pos + 1, file.begin() + pos + 1 + (size_t)iw * ih * 3);
     } else {
-        err(std::string("load_image_color: ") + filename + ": the compat layer decodes JPEG (sequential DCT) and binary PPM; "
+        err(std::string("load_image_color: ") + filename + ": the compat layer decodes JPEG and binary PPM; "
             "decode other formats in the caller and use make_image()");
         return im;
     }

@@ -1,9 +1,10 @@
 // Host-side JPEG decoder behind the compat layer's load_image_color (darknet/src/image.c:1442-1482 decodes through
 // stb_image; models_detection/YOLO.py:141 always hands a .jpg path to it).
 //
-// Scope: Huffman-coded sequential DCT JPEG (SOF0 baseline / SOF1 extended, 8-bit), grey or 3 components, sampling
+// Scope: Huffman-coded DCT JPEG, 8-bit: sequential (SOF0 baseline / SOF1 extended) and progressive (SOF2: spectral
+// selection + successive approximation, DC/AC first and refinement scans, EOB runs), grey or 3 components, sampling
 // factors 1..4, interleaved and non-interleaved scans, restart intervals, JFIF / Adobe colour-transform markers.
-// Progressive (SOF2) and arithmetic-coded files are rejected with an error (decode them in the caller and use
+// Arithmetic-coded, lossless and 12-bit files are rejected with an error (decode them in the caller and use
 // make_image()).
 //
 // The reconstruction is bit-exact with the reference's decoder, which matters because the frame feeds a detector
@@ -43,6 +44,8 @@ struct Component {
     int w2 = 0, h2 = 0;          // allocated size (whole MCUs)
     int dc_pred = 0;
     std::vector<uint8_t> data;
+    std::vector<int16_t> coeff;  // progressive: every block's 64 coefficients (natural order), bw2 blocks per row
+    int bw2 = 0;
 };
 
 struct Decoder {
@@ -56,6 +59,8 @@ struct Decoder {
     int restart_interval = 0;
     bool jfif = false;
     int adobe_transform = -1;
+    bool progressive = false;
+    int ss = 0, se = 63, ah = 0, al = 0, eob_run = 0;     // progressive scan parameters
     // bit reader
     uint32_t bits = 0;
     int nbits = 0;
@@ -158,6 +163,102 @@ bool decode_block(Decoder &d, Component &c, int16_t blk[64]) {
     return true;
 }
 
+// ---- progressive scans (T.81 annex G): coefficients are accumulated in Component::coeff over several scans
+inline int get_bit(Decoder &d) {
+    if (d.nbits < 1) fill(d);
+    const int v = peek(d, 1);
+    skip(d, 1);
+    return v;
+}
+inline int get_bits(Decoder &d, int n) {
+    if (n == 0) return 0;
+    if (d.nbits < n) fill(d);
+    const int v = peek(d, n);
+    skip(d, n);
+    return v;
+}
+
+bool decode_block_prog_dc(Decoder &d, Component &c, int16_t *blk) {
+    if (d.se != 0) return d.fail("progressive DC scan with an AC band");
+    if (d.ah == 0) {                                   // first pass: the (point-transformed) DC difference
+        memset(blk, 0, 64 * sizeof(int16_t));
+        const int t = decode_symbol(d, d.dc[c.td]);
+        if (t < 0 || t > 15) return d.fail("bad huffman code");
+        c.dc_pred += receive_extend(d, t);
+        blk[0] = (int16_t)(c.dc_pred * (1 << d.al));
+    } else if (get_bit(d)) {                           // refinement: one more bit of precision
+        blk[0] = (int16_t)(blk[0] + (1 << d.al));
+    }
+    return true;
+}
+
+bool decode_block_prog_ac(Decoder &d, Component &c, int16_t *blk) {
+    if (d.ss == 0) return d.fail("progressive AC scan starting at the DC coefficient");
+    const Huff &h = d.ac[c.ta];
+    if (d.ah == 0) {                                   // first pass of the band [ss, se]
+        if (d.eob_run) { --d.eob_run; return true; }
+        int k = d.ss;
+        do {
+            const int rs = decode_symbol(d, h);
+            if (rs < 0) return d.fail("bad huffman code");
+            const int s = rs & 15, r = rs >> 4;
+            if (s == 0) {
+                if (r < 15) {                          // end-of-band run of 2^r + extra blocks (this one included)
+                    d.eob_run = 1 << r;
+                    if (r) d.eob_run += get_bits(d, r);
+                    --d.eob_run;
+                    break;
+                }
+                k += 16;
+            } else {
+                k += r;
+                const int z = kZigzag[k++];
+                blk[z] = (int16_t)(receive_extend(d, s) * (1 << d.al));
+            }
+        } while (k <= d.se);
+        return true;
+    }
+    // refinement pass: correction bits for the coefficients that are already non-zero, new +-1 coefficients between them
+    const int16_t bit = (int16_t)(1 << d.al);
+    auto refine = [&](int16_t *p) {
+        if (get_bit(d) && (*p & bit) == 0) *p = (int16_t)(*p > 0 ? *p + bit : *p - bit);
+    };
+    if (d.eob_run) {
+        --d.eob_run;
+        for (int k = d.ss; k <= d.se; ++k) {
+            int16_t *p = &blk[kZigzag[k]];
+            if (*p != 0) refine(p);
+        }
+        return true;
+    }
+    int k = d.ss;
+    do {
+        const int rs = decode_symbol(d, h);
+        if (rs < 0) return d.fail("bad huffman code");
+        int s = rs & 15, r = rs >> 4;
+        if (s == 0) {
+            if (r < 15) {
+                d.eob_run = (1 << r) - 1;
+                if (r) d.eob_run += get_bits(d, r);
+                r = 64;                                // run to the end of the band, refining on the way
+            }                                          // r == 15: sixteen zero coefficients to skip
+        } else {
+            if (s != 1) return d.fail("bad huffman code");
+            s = get_bit(d) ? bit : -bit;
+        }
+        while (k <= d.se) {
+            int16_t *p = &blk[kZigzag[k++]];
+            if (*p != 0) {
+                refine(p);
+            } else {
+                if (r == 0) { *p = (int16_t)s; break; }
+                --r;
+            }
+        }
+    } while (k <= d.se);
+    return true;
+}
+
 // ---- inverse DCT (see the header comment).  One 8-point pass on already scaled inputs; outputs the even part x[0..3]
 // and the odd part t[0..3] such that out[k] = x[k] + t[3-k], out[7-k] = x[k] - t[3-k].
 // The multipliers are the usual islow constants scaled by 2^12; each is the value (int)(c * 4096 + 0.5) of the SIGNED
@@ -252,12 +353,16 @@ bool read_sof(Decoder &d) {
         c.w = (d.width * c.h + d.hmax - 1) / d.hmax; c.hgt = (d.height * c.v + d.vmax - 1) / d.vmax;
         c.w2 = d.mcux * c.h * 8; c.h2 = d.mcuy * c.v * 8;
         c.data.assign((size_t)c.w2 * c.h2, 0);
+        if (d.progressive) {
+            c.bw2 = c.w2 / 8;
+            c.coeff.assign((size_t)c.w2 * c.h2, 0);
+        }
     }
     return true;
 }
 
 void restart(Decoder &d) {
-    d.bits = 0; d.nbits = 0; d.hit_marker = false; d.marker = 0;
+    d.bits = 0; d.nbits = 0; d.hit_marker = false; d.marker = 0; d.eob_run = 0;
     for (int i = 0; i < 4; ++i) d.comp[i].dc_pred = 0;
 }
 
@@ -272,11 +377,24 @@ bool read_scan(Decoder &d) {
         while (k < d.ncomp && d.comp[k].id != id) ++k;
         if (k == d.ncomp) return d.fail("bad SOS component");
         d.comp[k].td = tt >> 4; d.comp[k].ta = tt & 15;
-        if (d.comp[k].td > 3 || d.comp[k].ta > 3 || !d.dc[d.comp[k].td].defined || !d.ac[d.comp[k].ta].defined)
-            return d.fail("scan uses an undefined huffman table");
+        if (d.comp[k].td > 3 || d.comp[k].ta > 3) return d.fail("bad huffman table index");
         order[i] = k;
     }
-    d.u8(); d.u8(); d.u8();          // spectral selection / approximation: fixed for sequential JPEG
+    d.ss = d.u8(); d.se = d.u8();
+    const int a = d.u8();
+    d.ah = a >> 4; d.al = a & 15;
+    if (d.progressive) {
+        if (d.ss > 63 || d.se > 63 || d.ss > d.se || d.ah > 13 || d.al > 13) return d.fail("bad progressive scan parameters");
+        if (d.ss != 0 && ns != 1) return d.fail("interleaved progressive AC scan");
+    } else {
+        d.ss = 0; d.se = 63; d.ah = d.al = 0;
+    }
+    for (int i = 0; i < ns; ++i) {
+        const Component &c = d.comp[order[i]];
+        const bool need_dc = d.ss == 0, need_ac = d.se != 0;
+        if ((need_dc && !(d.progressive && d.ah) && !d.dc[c.td].defined) || (need_ac && !d.ac[c.ta].defined))
+            return d.fail("scan uses an undefined huffman table");
+    }
     restart(d);
     int16_t blk[64];
     int todo = d.restart_interval ? d.restart_interval : 0x7fffffff;
@@ -294,8 +412,13 @@ bool read_scan(Decoder &d) {
         const int bw = (c.w + 7) >> 3, bh = (c.hgt + 7) >> 3;
         for (int by = 0; by < bh; ++by)
             for (int bx = 0; bx < bw; ++bx) {
-                if (!decode_block(d, c, blk)) return false;
-                idct_block(c.data.data() + (size_t)by * 8 * c.w2 + bx * 8, c.w2, blk);
+                if (d.progressive) {
+                    int16_t *cb = c.coeff.data() + 64 * ((size_t)by * c.bw2 + bx);
+                    if (!(d.ss == 0 ? decode_block_prog_dc(d, c, cb) : decode_block_prog_ac(d, c, cb))) return false;
+                } else {
+                    if (!decode_block(d, c, blk)) return false;
+                    idct_block(c.data.data() + (size_t)by * 8 * c.w2 + bx * 8, c.w2, blk);
+                }
                 if (!after_unit()) return true;
             }
         return true;
@@ -306,6 +429,11 @@ bool read_scan(Decoder &d) {
                 Component &c = d.comp[order[i]];
                 for (int y = 0; y < c.v; ++y)
                     for (int x = 0; x < c.h; ++x) {
+                        if (d.progressive) {           // only DC scans may be interleaved
+                            int16_t *cb = c.coeff.data() + 64 * ((size_t)(my * c.v + y) * c.bw2 + (mx * c.h + x));
+                            if (!decode_block_prog_dc(d, c, cb)) return false;
+                            continue;
+                        }
                         if (!decode_block(d, c, blk)) return false;
                         idct_block(c.data.data() + (size_t)(my * c.v + y) * 8 * c.w2 + (mx * c.h + x) * 8, c.w2, blk);
                     }
@@ -375,14 +503,14 @@ bool jpeg_decode_rgb(const uint8_t *data, size_t size, std::vector<uint8_t> &rgb
         }
         if (m == 0xD9) break;                                   // EOI
         if (m == 0 || m == 0x01 || (m >= 0xD0 && m <= 0xD7)) continue;
-        if (m == 0xC0 || m == 0xC1) {
+        if (m == 0xC0 || m == 0xC1 || m == 0xC2) {
             if (have_frame) return bad("second frame header");
+            d.progressive = m == 0xC2;
             if (!read_sof(d)) return bad("bad frame header");
             have_frame = true;
             is_rgb_ids = d.ncomp == 3 && d.comp[0].id == 'R' && d.comp[1].id == 'G' && d.comp[2].id == 'B';
             continue;
         }
-        if (m == 0xC2) return bad("progressive JPEG is not decoded by the compat layer (decode it in the caller and use make_image())");
         if ((m >= 0xC3 && m <= 0xCF) && m != 0xC4 && m != 0xC8 && m != 0xCC) return bad("unsupported JPEG coding process");
         if (m == 0xDA) {
             if (!have_frame) return bad("scan before frame header");
@@ -402,6 +530,18 @@ bool jpeg_decode_rgb(const uint8_t *data, size_t size, std::vector<uint8_t> &rgb
         d.p = seg_end;
     }
     if (!have_frame || !have_scan) return bad("no image data");
+    if (d.progressive)                                  // all scans are in: dequantise and transform every block
+        for (int k = 0; k < d.ncomp; ++k) {
+            Component &c = d.comp[k];
+            const uint16_t *q = d.qt[c.tq];
+            const int bw = (c.w + 7) >> 3, bh = (c.hgt + 7) >> 3;
+            for (int by = 0; by < bh; ++by)
+                for (int bx = 0; bx < bw; ++bx) {
+                    int16_t *cb = c.coeff.data() + 64 * ((size_t)by * c.bw2 + bx);
+                    for (int i = 0; i < 64; ++i) cb[i] = (int16_t)(cb[i] * q[i]);
+                    idct_block(c.data.data() + (size_t)by * 8 * c.w2 + bx * 8, c.w2, cb);
+                }
+        }
 
     // resample + colour conversion, row by row
     width = d.width; height = d.height;

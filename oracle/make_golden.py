@@ -252,6 +252,12 @@ def make_jpeg_golden():
     p = os.path.join(d, "rst3.jpg"); cv2.imwrite(p, smooth, [cv2.IMWRITE_JPEG_RST_INTERVAL, 3, cv2.IMWRITE_JPEG_QUALITY, 75]); files.append(p)
     p = os.path.join(d, "grey.jpg"); cv2.imwrite(p, cv2.cvtColor(ramp, cv2.COLOR_BGR2GRAY)); files.append(p)
     p = os.path.join(d, "opt.jpg"); cv2.imwrite(p, noise, [cv2.IMWRITE_JPEG_OPTIMIZE, 1, cv2.IMWRITE_JPEG_QUALITY, 50]); files.append(p)
+    for name, img, extra in (("prog420", smooth, [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, sf["420"], cv2.IMWRITE_JPEG_QUALITY, 70]),
+                             ("prog444_rst", ramp, [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, sf["444"], cv2.IMWRITE_JPEG_RST_INTERVAL, 2]),
+                             ("prog_grey", cv2.cvtColor(noise, cv2.COLOR_BGR2GRAY), [cv2.IMWRITE_JPEG_QUALITY, 40])):
+        p = os.path.join(d, name + ".jpg")           # progressive: spectral selection + successive approximation scans
+        cv2.imwrite(p, img, [cv2.IMWRITE_JPEG_PROGRESSIVE, 1] + extra)
+        files.append(p)
     for w, h in ((1, 1), (7, 3), (16, 17)):
         p = os.path.join(d, f"tiny_{w}x{h}.jpg"); cv2.imwrite(p, rng.integers(0, 256, (h, w, 3), dtype=np.uint8)); files.append(p)
     # the frame the GPU side-by-side test feeds both libraries: non-square, letterboxed by network_predict_image
