@@ -50,7 +50,10 @@ typedef struct {
     int reserved[7];          /* reserved[0] = 1: also keep the pre-pool outputs of conv_1,2,5,8 (KerasYOLO.extract)
                                  reserved[1]: largest batch that runs conv_2..23 as ONE persistent cooperative launch
                                  (conv_chain_kernel, the batch-1 schedule); 0 = default (1: measured faster only
-                                 for a single frame, profiles/r2_batch_sweep_416.txt), -1 = never                        */
+                                 for a single frame, profiles/r2_batch_sweep_416.txt), -1 = never
+                                 reserved[2] = 1: the tiny graph of cfg/yolov2-tiny*.cfg (9 conv layers, sixth maxpool
+                                 stride 1) instead of cfg/yolov2.cfg's; reserved[3] = filters of its conv_8 (1024 voc,
+                                 512 coco; 0 = 1024).  Weights: b2t_load_darknet_weights or b2t_set_conv_weights(1..9). */
 } b2t_config;
 
 const char *b2t_last_error(void);

@@ -90,6 +90,7 @@ struct ConvLayer {
     bool flat1x1 = false;                         // 1x1 conv, plain destination, no pool: persistent kernel over the flat pixel list
     CUtensorMap tmXf_hi, tmXf_lo;                 // its patch view: [cin_pad][MB*H*W] with a box of 128 pixels
     bool have_weights = false;
+    int ps1_buf = -1;                             // tiny graph: a 2x2 stride-1 max-pool of out_buf follows (maxpool_layer.c:79-114)
 };
 
 struct b2t_ctx {
@@ -102,6 +103,8 @@ struct b2t_ctx {
     std::map<std::string, int> choff_by_name;
     std::vector<ConvLayer> conv;                  // [0] unused, 1..23, then convlstm layers
     int L_CIN = 0, L_CREC = 0, L_HEAD = 0;        // indices of the ConvLSTM layers (0 = absent)
+    int n_conv = 23;                              // conv layers of the detector graph: 23 (cfg/yolov2*.cfg) or 9 (cfg/yolov2-tiny*.cfg)
+    int conv1_cout = 32;                          // real output channels of conv_1 (the kernel computes 32; tiny: 16 + 16 zero)
     // conv_1
     size_t off_w1 = 0, off_s1 = 0, off_b1 = 0, off_lut = 0;
     size_t off_w1pm = 0, off_s1pm = 0;           // conv_1 on the tensor cores: packed fp16 (hi,lo) weights, scale / 255
@@ -279,7 +282,7 @@ static int choose_splits(int tiles, int chunks, int n_sm) {
 static ConvLayer &new_conv(b2t_ctx *c, int index, int k, int cin, int cout, bool act, bool pool, int H, int W) {
     ConvLayer l;
     l.index = index; l.k = k; l.cin = cin; l.cout = cout;
-    l.kchunk = (cin == 32 && c->cfg.engine != 2) ? 32 : 64;   // conv_2: 32 input channels, SWIZZLE_64B rows
+    l.kchunk = (cin <= 32 && index != 1 && c->cfg.engine != 2) ? 32 : 64;   // conv_2: <= 32 input channels, SWIZZLE_64B rows
     l.cin_pad = round_up(cin, l.kchunk);
     l.act = act; l.pool = pool; l.H = H; l.W = W;
     l.ldw = k * k * l.cin_pad;
@@ -328,12 +331,9 @@ extern "C" int b2t_create(const b2t_config *cfg, b2t_ctx **out) {
     const int H0 = cfg->image_h;
     c->conv.resize(24);
 
-    // conv_k table (KerasYOLO.py:277-400): k, cin, cout, pool-after
-    static const int T[20][4] = {{3, 3, 32, 1},     {3, 32, 64, 1},    {3, 64, 128, 0},    {1, 128, 64, 0},
-                                 {3, 64, 128, 1},   {3, 128, 256, 0},  {1, 256, 128, 0},   {3, 128, 256, 1},
-                                 {3, 256, 512, 0},  {1, 512, 256, 0},  {3, 256, 512, 0},   {1, 512, 256, 0},
-                                 {3, 256, 512, 1},  {3, 512, 1024, 0}, {1, 1024, 512, 0},  {3, 512, 1024, 0},
-                                 {1, 1024, 512, 0}, {3, 512, 1024, 0}, {3, 1024, 1024, 0}, {3, 1024, 1024, 0}};
+    const int Gs = c->G;
+    const bool lstm = cfg->convlstm_units > 0;
+    const bool tiny = cfg->reserved[2] == 1;
     // conv_1 blob: fp32 [27][32], scale, bias, LUT
     c->off_w1 = 0;
     c->off_s1 = align_up(27 * 32 * 4, 256);
@@ -342,9 +342,50 @@ extern "C" int b2t_create(const b2t_config *cfg, b2t_ctx **out) {
     c->off_w1pm = c->off_lut + 1024;
     c->off_s1pm = c->off_w1pm + 3 * 4096;
     c->weight_bytes = c->off_s1pm + 512;
+    if (tiny) {
+        // cfg/yolov2-tiny-voc.cfg / yolov2-tiny.cfg: conv 16, 32, 64, 128, 256 (each 3x3 + BN + leaky + maxpool 2/2), 512
+        // (+ maxpool size 2 STRIDE 1), 1024, F8 (1024 voc / 512 coco), 1x1 head.  conv_1's kernel computes 32 channels:
+        // the upper 16 carry zero weights, and conv_2 reads 32 input channels with zero weights on them.
+        if (cfg->convlstm_units) { delete c; return fail(-1, "b2t_create: the tiny graph has no ConvLSTM head"); }
+        const int f8 = cfg->reserved[3] > 0 ? cfg->reserved[3] : 1024;
+        const int TT[8][3] = {{3, 32, 1}, {16, 32, 1}, {32, 64, 1}, {64, 128, 1}, {128, 256, 1}, {256, 512, 2}, {512, 1024, 0}, {1024, f8, 0}};
+        c->n_conv = 9;
+        c->conv1_cout = 16;
+        c->conv.resize(10);
+        int H = H0, prev = -1;
+        for (int i = 1; i <= 8; ++i) {
+            const int *t = TT[i - 1];
+            char nm[32];
+            snprintf(nm, sizeof nm, "norm_%d", i);
+            ConvLayer &l = new_conv(c, i, 3, t[0], t[1], true, t[2] == 1, H, H);
+            l.in_buf = prev;
+            if (t[2] == 1) {
+                if (c->keep_prepool) l.out_buf = add_buf(c, nm, H, H, round_up(l.cout, 64));
+                l.pout_buf = add_buf(c, std::string("pool_") + std::to_string(i), H / 2, H / 2, i == 1 ? 32 : round_up(l.cout, 64));
+                prev = l.pout_buf;
+                H /= 2;
+            } else {
+                l.out_buf = add_buf(c, nm, H, H, round_up(l.cout, 64));
+                prev = l.out_buf;
+                if (t[2] == 2) { l.ps1_buf = add_buf(c, std::string("pool_") + std::to_string(i), H, H, round_up(l.cout, 64)); prev = l.ps1_buf; }
+            }
+            c->cout_by_name[nm] = i == 1 ? 16 : l.cout;
+            c->cout_by_name[std::string("pool_") + std::to_string(i)] = i == 1 ? 16 : l.cout;
+            if (i > 1) blob_reserve(c, l);
+        }
+        c->buf_by_name["conv_feat"] = c->conv[8].out_buf; c->cout_by_name["conv_feat"] = f8;
+        ConvLayer &l = new_conv(c, 9, 1, f8, AD, false, false, Gs, Gs);
+        l.in_buf = prev;
+        l.f32_out = 1;
+        blob_reserve(c, l);
+    } else {
+    // conv_k table (KerasYOLO.py:277-400): k, cin, cout, pool-after
+    static const int T[20][4] = {{3, 3, 32, 1},     {3, 32, 64, 1},    {3, 64, 128, 0},    {1, 128, 64, 0},
+                                 {3, 64, 128, 1},   {3, 128, 256, 0},  {1, 256, 128, 0},   {3, 128, 256, 1},
+                                 {3, 256, 512, 0},  {1, 512, 256, 0},  {3, 256, 512, 0},   {1, 512, 256, 0},
+                                 {3, 256, 512, 1},  {3, 512, 1024, 0}, {1, 1024, 512, 0},  {3, 512, 1024, 0},
+                                 {1, 1024, 512, 0}, {3, 512, 1024, 0}, {3, 1024, 1024, 0}, {3, 1024, 1024, 0}};
 
-    const int Gs = c->G;
-    const bool lstm = cfg->convlstm_units > 0;
     const int zc = lstm ? 1024 + round_up(AD, 64) : 1024;        // channels of the conv_22 output buffer
     const int concat = add_buf(c, "concat", Gs, Gs, 1280);
     const int featz = add_buf(c, "norm_22", Gs, Gs, zc);
@@ -415,6 +456,7 @@ extern "C" int b2t_create(const b2t_config *cfg, b2t_ctx **out) {
         ConvLayer &h = new_conv(c, 26, 1, u, AD, false, false, Gs, Gs);
         h.in_buf = c->buf_hseq; h.f32_out = 3;
         blob_reserve(c, h);
+    }
     }
     c->host_blob.assign(c->weight_bytes, 0);
     {   // LUT[u] = float(u / 255.)  (utils.py:150-153: numpy true division in float64, cast to fp32 by Keras)
@@ -546,11 +588,21 @@ static void fold_bn(const b2t_ctx *c, int n, const float *gamma, const float *be
 
 extern "C" int b2t_set_conv_weights(b2t_ctx *c, int idx, const float *ker, const float *gamma, const float *beta,
                                     const float *mean, const float *var, const float *bias) {
-    if (!c || idx < 1 || idx > 23 || !ker) return fail(-1, "b2t_set_conv_weights: bad arguments (conv_%d)", idx);
+    if (!c || idx < 1 || idx > c->n_conv || !ker) return fail(-1, "b2t_set_conv_weights: bad arguments (conv_%d)", idx);
     ConvLayer &l = c->conv[idx];
-    const bool bn = idx != 23;
+    const bool bn = idx != c->n_conv;
     if (bn && !(gamma && beta && mean && var)) return fail(-1, "conv_%d needs gamma/beta/mean/var", idx);
-    if (!bn && !bias) return fail(-1, "conv_23 needs a bias");
+    if (!bn && !bias) return fail(-1, "the head conv needs a bias");
+    std::vector<float> k1, g1, b1v, m1, v1;
+    if (idx == 1 && c->conv1_cout != 32) {
+        // conv_1 with fewer than 32 real output channels: pad with zero weights and an identity BatchNorm (output 0)
+        const int rc1 = c->conv1_cout;
+        k1.assign(27 * 32, 0.f); g1.assign(32, 1.f); b1v.assign(32, 0.f); m1.assign(32, 0.f); v1.assign(32, 1.f);
+        for (int t = 0; t < 27; ++t)
+            for (int co = 0; co < rc1; ++co) k1[t * 32 + co] = ker[t * rc1 + co];
+        for (int co = 0; co < rc1; ++co) { g1[co] = gamma[co]; b1v[co] = beta[co]; m1[co] = mean[co]; v1[co] = var[co]; }
+        ker = k1.data(); gamma = g1.data(); beta = b1v.data(); mean = m1.data(); var = v1.data();
+    }
     if (idx == 1) {
         float *w = reinterpret_cast<float *>(c->host_blob.data() + c->off_w1);
         memcpy(w, ker, 27 * 32 * 4);   // (kh,kw,cin,cout) is already [tap*3+cin][32]
@@ -608,12 +660,11 @@ extern "C" int b2t_load_darknet_weights(b2t_ctx *c, const char *path) {
     // parser.c:1220-1226: "seen" is size_t from v0.2 on, int32 before
     const bool wide = (hdr[0] * 10 + hdr[1] >= 2) && hdr[0] < 1000 && hdr[1] < 1000;
     if (fseek(f, wide ? 8 : 4, SEEK_CUR)) { fclose(f); return fail(-3, "%s: truncated header", path); }
-    static const int order[23] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23};
     std::vector<float> bn, raw, hwio;
-    for (int oi = 0; oi < 23; ++oi) {
-        const int idx = order[oi];
-        const ConvLayer &l = c->conv[idx];
-        const bool isbn = idx != 23;
+    for (int idx = 1; idx <= c->n_conv; ++idx) {          // file order = cfg order (conv_21's skip conv precedes conv_22)
+        ConvLayer l = c->conv[idx];
+        if (idx == 1) l.cout = c->conv1_cout;             // the file holds the real channel count
+        const bool isbn = idx != c->n_conv;
         const size_t nb = isbn ? 4 * (size_t)l.cout : (size_t)l.cout, nw = (size_t)l.cout * l.cin * l.k * l.k;
         bn.resize(nb);
         raw.resize(nw);
@@ -638,7 +689,7 @@ extern "C" int b2t_load_darknet_weights(b2t_ctx *c, const char *path) {
     float extra;
     const bool trailing = fread(&extra, 4, 1, f) == 1;
     fclose(f);
-    if (trailing) return fail(-3, "%s: trailing data after conv_23 (wrong class count?)", path);
+    if (trailing) return fail(-3, "%s: trailing data after the last conv layer (wrong class count?)", path);
     return 0;
 }
 
@@ -866,7 +917,7 @@ static int halo_geometry(b2t_ctx *c, ConvLayer &l, int B, ConvParams &p, bool ch
 
 // Small batches: can this layer run inside conv_chain_kernel (the big resource shape of the halo engine)?
 static bool chain_eligible(const b2t_ctx *c, const ConvLayer &l) {
-    return c->cfg.engine == B2T_ENGINE_TCGEN05 && l.index >= 2 && l.index <= 23 && l.h_rows * l.hP <= 256 && l.hN <= 256 &&
+    return c->cfg.engine == B2T_ENGINE_TCGEN05 && l.index >= 2 && l.index <= c->n_conv && l.h_rows * l.hP <= 256 && l.hN <= 256 &&
            2 * l.h_plane_bytes <= 65536;
 }
 
@@ -1082,10 +1133,22 @@ static int run_conv1(b2t_ctx *c, const void *frames, int dtype, int B, cudaStrea
     return 0;
 }
 
+// tiny graph: maxpool size 2 stride 1 (parser.c:471-486: padding 0; maxpool_layer.c:79-114: window [i, i+1] x [j, j+1]
+// clipped at the border) of layer l's output into its ps1 buffer, on split planes
+static int run_pool_s1(b2t_ctx *c, const ConvLayer &l, int B, cudaStream_t st) {
+    const ActBuf &in = c->bufs[l.out_buf], &out = c->bufs[l.ps1_buf];
+    const int rc = launch_pool_s1(in.hi, in.plane, out.hi, out.plane, B, l.H, l.W, in.C, st);
+    if (rc) return fail(-2, "pool_s1 launch: %s", cudaGetErrorString((cudaError_t)rc));
+    c->launches += 1;
+    return 0;
+}
+
 static int forward_impl(b2t_ctx *c, const void *frames, int dtype, int B, float *logits_user, cudaStream_t st,
-                        cudaEvent_t *ev /* 24 events or NULL */, int first = 1, int last = 23) {
+                        cudaEvent_t *ev /* 24 events or NULL */, int first = 1, int last = -1) {
     if (!c || !c->finalized) return fail(-1, "b2t_yolo_forward: context not finalized");
-    if (first < 1 || last > 23 || first > last) return fail(-1, "b2t_yolo_forward: bad layer range [%d, %d]", first, last);
+    const int NC = c->n_conv;
+    if (last < 0 || last == 23) last = last < 0 || NC < 23 ? NC : 23;      // 23 = "to the head" for callers written against the YOLOv2 graph
+    if (first < 1 || last > NC || first > last) return fail(-1, "b2t_yolo_forward: bad layer range [%d, %d]", first, last);
     if (first == 1 && !frames && !(c->conv[1].pm && dtype == B2T_FRAME_U8))
         return fail(-1, "b2t_yolo_forward: null frames");
     if (B < 1 || B > c->cfg.max_batch) return fail(-1, "batch %d outside [1, max_batch=%d]", B, c->cfg.max_batch);
@@ -1133,7 +1196,7 @@ static int forward_impl(b2t_ctx *c, const void *frames, int dtype, int B, float 
         ConvLayer &l = c->conv[i];
         if (chain && chain_eligible(c, l)) {
             ConvParams p;
-            base_params(c, l, B, i == 23 ? logits : nullptr, 0, 0, p);
+            base_params(c, l, B, i == NC ? logits : nullptr, 0, 0, p);
             const int ctas = halo_geometry(c, l, B, p, true);
             if (ctas < 0) { if (cb) chain_free(cb); return ctas; }
             if (!cb) cb = chain_new(c->d_chain_counter);
@@ -1146,14 +1209,19 @@ static int forward_impl(b2t_ctx *c, const void *frames, int dtype, int B, float 
                 cb = chain_new(c->d_chain_counter);
                 chain_add(cb, l.tmX_hi, l.tmX_lo, l.tmW_hi, l.tmW_lo, p);
             }
+            if (l.ps1_buf >= 0) {                          // the stride-1 pool is its own kernel: the chain ends here
+                if ((rc = flush_chain())) return rc;
+                if ((rc = run_pool_s1(c, l, B, st))) return rc;
+            }
             continue;
         }
         if ((rc = flush_chain())) return rc;
-        if ((rc = run_conv(c, l, B, i == 23 ? logits : nullptr, st))) return rc;
+        if ((rc = run_conv(c, l, B, i == NC ? logits : nullptr, st))) return rc;
+        if (l.ps1_buf >= 0 && (rc = run_pool_s1(c, l, B, st))) return rc;
         if (ev) cudaEventRecord(ev[i], st);
     }
     if ((rc = flush_chain())) return rc;
-    if (last == 23 && logits_user && logits_user != logits)
+    if (last == NC && logits_user && logits_user != logits)
         CK(cudaMemcpyAsync(logits_user, logits, (size_t)B * c->G * c->G * c->A * c->D * 4, cudaMemcpyDeviceToDevice, st));
     return 0;
 }
@@ -1201,6 +1269,7 @@ extern "C" int b2t_profile_forward(b2t_ctx *c, const void *frames, int dtype, in
     if (!rc) {
         CK(cudaStreamSynchronize(st));
         for (int i = 1; i <= 23; ++i) {
+            if (i > c->n_conv) { ms[i - 1] = 0.f; if (bytes) bytes[i - 1] = 0.0; continue; }
             CK(cudaEventElapsedTime(&ms[i - 1], ev[i - 1], ev[i]));
             if (bytes) {
                 const ConvLayer &l = c->conv[i];
@@ -1229,7 +1298,7 @@ static int lookup(const b2t_ctx *c, const char *name, int *buf, int *choff, int 
 }
 
 extern "C" int b2t_layer_dims(const b2t_ctx *c, const char *name, int *h, int *w, int *ch) {
-    if (name && !strcmp(name, "conv_23")) {
+    if (name && c && (!strcmp(name, "conv_23") || !strcmp(name, ("conv_" + std::to_string(c->n_conv)).c_str()))) {
         if (h) *h = c->G; if (w) *w = c->G; if (ch) *ch = c->A * c->D;
         return 0;
     }
@@ -1246,7 +1315,7 @@ extern "C" long b2t_extract(b2t_ctx *c, const char *name, int B, float *out, voi
     if (!c || !c->finalized || !out) return fail(-1, "b2t_extract: bad arguments");
     if (B < 1 || B > c->cfg.max_batch) return fail(-1, "bad batch");
     cudaStream_t st = (cudaStream_t)stream;
-    if (!strcmp(name, "conv_23")) {
+    if (!strcmp(name, "conv_23") || !strcmp(name, ("conv_" + std::to_string(c->n_conv)).c_str())) {
         const size_t n = (size_t)c->G * c->G * c->A * c->D;
         CK(cudaMemcpyAsync(out, c->d_ws + c->off_logits, n * B * 4, cudaMemcpyDeviceToDevice, st));
         return (long)n;

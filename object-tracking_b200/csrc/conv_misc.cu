@@ -130,7 +130,45 @@ __global__ void planes_to_f32_kernel(const op_t *hi, long long plane, int pix_st
     }
 }
 
+// maxpool size 2, stride 1 of the tiny graph (darknet/src/parser.c:471-486: padding (size-1)/2 = 0;
+// maxpool_layer.c:79-114: out[i][j] = max over in[i..i+1][j..j+1] inside the image) on split planes.  hi + lo is an
+// exact fp32 value (22 significant bits), so joining, comparing and re-splitting is lossless.
+__global__ void __launch_bounds__(256) pool_s1_kernel(const op_t *in, long long in_plane, op_t *out, long long out_plane, int B, int H,
+                                                      int W, int C) {
+    const int groups = C / 8;
+    const long long total = (long long)B * H * W * groups;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int g = int(t % groups);
+        const long long pix = t / groups;
+        const int x = int(pix % W), y = int((pix / W) % H);
+        float m[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
+        for (int dy = 0; dy < 2; ++dy)
+            for (int dx = 0; dx < 2; ++dx) {
+                if (y + dy >= H || x + dx >= W) continue;
+                const op_t *q = in + (pix + (long long)dy * W + dx) * C + g * 8;
+                const uint4 h4 = *reinterpret_cast<const uint4 *>(q), l4 = *reinterpret_cast<const uint4 *>(q + in_plane);
+                const op_t *hh = reinterpret_cast<const op_t *>(&h4), *ll = reinterpret_cast<const op_t *>(&l4);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], join_f16(hh[i], ll[i]));
+            }
+        __align__(16) op_t oh[8], ol[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) split_f16(m[i], oh[i], ol[i]);
+        op_t *d = out + pix * C + g * 8;
+        *reinterpret_cast<uint4 *>(d) = *reinterpret_cast<const uint4 *>(oh);
+        *reinterpret_cast<uint4 *>(d + out_plane) = *reinterpret_cast<const uint4 *>(ol);
+    }
+}
+
 // ---------------------------------------------------------------- host-side launchers (used by api.cu)
+int launch_pool_s1(const op_t *in, long long in_plane, op_t *out, long long out_plane, int B, int H, int W, int C, cudaStream_t st) {
+    const long long total = (long long)B * H * W * (C / 8);
+    const int blocks = (int)min((long long)148 * 8, (total + 255) / 256);
+    pool_s1_kernel<<<blocks, 256, 0, st>>>(in, in_plane, out, out_plane, B, H, W, C);
+    return (int)cudaGetLastError();
+}
 int launch_splitk_epilogue(const ConvParams &p, cudaStream_t st) {
     const int cgroups = (p.Cout + 7) / 8;
     const long long total = (long long)p.B * (p.pool ? p.H / 2 : p.H) * (p.pool ? p.W / 2 : p.W) * cgroups;

@@ -40,6 +40,8 @@ struct Net {
     std::vector<float> h_region, h_feat, h_tmp;
     float thresh = 0.5f;
     int det_w = 0, det_h = 0;
+    bool tiny = false;            // cfg/yolov2-tiny*.cfg: 9 conv layers, region layer = darknet layer 15 (31 for yolov2)
+    int region_idx = 31;
 };
 
 std::mutex g_mu;
@@ -150,6 +152,13 @@ int geti(const Section &s, const char *k, int d) {
 const int kFilters[22] = {32, 64, 128, 64, 128, 256, 128, 256, 512, 256, 512, 256, 512, 1024, 512, 1024, 512, 1024, 1024, 1024, 64, 1024};
 const int kSizes[22] = {3, 3, 3, 1, 3, 3, 1, 3, 3, 1, 3, 1, 3, 3, 1, 3, 1, 3, 3, 3, 1, 3};
 
+// cfg/yolov2-tiny-voc.cfg / yolov2-tiny.cfg: darknet layer index -> engine tensor
+const char *tiny_layer_name(int idx) {
+    static const char *names[15] = {"norm_1", "pool_1", "norm_2", "pool_2", "norm_3", "pool_3", "norm_4", "pool_4",
+                                    "norm_5", "pool_5", "norm_6", "pool_6", "norm_7", "norm_8", "conv_9"};
+    return (idx >= 0 && idx < 15) ? names[idx] : nullptr;
+}
+
 const char *layer_name(int idx) {      // darknet layer index -> engine tensor
     static const char *names[31] = {"norm_1", "pool_1", "norm_2", "pool_2", "norm_3", "norm_4", "norm_5", "pool_5",
                                     "norm_6", "norm_7", "norm_8", "pool_8", "norm_9", "norm_10", "norm_11", "norm_12",
@@ -181,13 +190,21 @@ network *load_network(char *cfg, char *weights, int clear) {
     std::vector<Section> secs;
     if (!cfg || !read_sections(cfg, secs)) { err(std::string("load_network: cannot read cfg ") + (cfg ? cfg : "(null)")); return nullptr; }
     Net *n = new Net();
-    int conv = 0, bad = 0;
+    int conv = 0, bad = 0, bad_tiny = 0, pools = 0, pool_s1 = 0, tiny_f8 = 0;
+    static const int kTinyFilters[7] = {16, 32, 64, 128, 256, 512, 1024};
     for (const Section &s : secs) {
         if (s.name == "[net]" || s.name == "[network]") { n->w = geti(s, "width", 416); n->h = geti(s, "height", 416); }
         if (s.name == "[convolutional]") {
             const int f = geti(s, "filters", 1), k = geti(s, "size", 1);
             if (conv < 22 && (f != kFilters[conv] || k != kSizes[conv])) bad = 1;
+            if (conv < 7 && (f != kTinyFilters[conv] || k != 3)) bad_tiny = 1;
+            if (conv == 7) { tiny_f8 = f; if (k != 3) bad_tiny = 1; }
+            if (conv == 8 && k != 1) bad_tiny = 1;
             ++conv;
+        }
+        if (s.name == "[maxpool]") {
+            ++pools;
+            if (geti(s, "stride", 1) == 1) { ++pool_s1; if (pools != 6 || geti(s, "size", 2) != 2) bad_tiny = 1; }
         }
         if (s.name == "[region]") {
             n->classes = geti(s, "classes", 20);
@@ -205,14 +222,18 @@ network *load_network(char *cfg, char *weights, int clear) {
             }
         }
     }
-    if (conv != 23 || bad || n->n_box != 5 || n->classes < 1 || n->w != n->h || n->w % 32) {
-        err("load_network: only the YOLOv2 graph of cfg/yolov2.cfg is supported (23 conv layers, 5 anchors, square input multiple of 32)");
+    n->tiny = conv == 9 && !bad_tiny && pools == 6 && pool_s1 == 1;
+    if ((!(conv == 23 && !bad) && !n->tiny) || n->n_box != 5 || n->classes < 1 || n->w != n->h || n->w % 32) {
+        err("load_network: supported graphs are cfg/yolov2.cfg / yolov2-voc.cfg (23 conv layers) and cfg/yolov2-tiny.cfg / "
+            "yolov2-tiny-voc.cfg (9 conv layers, sixth maxpool stride 1); 5 anchors, square input multiple of 32");
         delete n;
         return nullptr;
     }
     n->grid = n->w / 32;
+    n->region_idx = n->tiny ? 15 : 31;
     b2t_config c;
     memset(&c, 0, sizeof c);
+    if (n->tiny) { c.reserved[2] = 1; c.reserved[3] = tiny_f8; }
     c.image_h = n->h; c.image_w = n->w; c.n_class = n->classes; c.max_batch = 1;
     c.semantics = B2T_SEM_DARKNET; c.bn_eps = 1e-3f; c.engine = B2T_ENGINE_TCGEN05; c.device = g_device;
     if (b2t_create(&c, &n->ctx)) { delete n; return nullptr; }
@@ -464,9 +485,9 @@ void free_ptrs(void **ptrs, int n) {
 dims layer_dims(network *net, int idx) {
     dims d = {0, 0, 0};
     Net *n = reinterpret_cast<Net *>(net);
-    const char *name = layer_name(idx - 1);
     if (!n) return d;
-    if (idx - 1 == 31 || idx - 1 == 30) { d.w = d.h = n->grid; d.c = n->n_box * (5 + n->classes); return d; }
+    const char *name = n->tiny ? tiny_layer_name(idx - 1) : layer_name(idx - 1);
+    if (idx - 1 == n->region_idx || idx - 1 == n->region_idx - 1) { d.w = d.h = n->grid; d.c = n->n_box * (5 + n->classes); return d; }
     if (!name) { err("layer_dims: layer is not kept by the B200 engine"); return d; }
     b2t_layer_dims(n->ctx, name, &d.h, &d.w, &d.c);
     return d;
@@ -476,12 +497,12 @@ feature network_extract_feat(network *net, int idx) {
     feature f = {0, nullptr};
     Net *n = reinterpret_cast<Net *>(net);
     if (!n) return f;
-    if (idx - 1 == 31) {               // the region layer's output
+    if (idx - 1 == n->region_idx) {    // the region layer's output
         f.size = (int)n->h_region.size();
         f.feat = n->h_region.data();
         return f;
     }
-    const char *name = layer_name(idx - 1);
+    const char *name = n->tiny ? tiny_layer_name(idx - 1) : layer_name(idx - 1);
     int h = 0, w = 0, c = 0;
     if (!name || b2t_layer_dims(n->ctx, name, &h, &w, &c)) { err("network_extract_feat: layer is not kept by the B200 engine"); return f; }
     const size_t cnt = (size_t)h * w * c;

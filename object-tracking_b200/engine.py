@@ -49,8 +49,10 @@ def rows_to_host(rows: torch.Tensor, counts: torch.Tensor):
 class DetectorEngine:
     def __init__(self, n_class: int = 80, image_size: int = 416, max_batch: int = 4, semantics: str = "keras",
                  bn_eps: float = 1e-3, engine: str = "tcgen05", device: int = 0, convlstm_units: int = 0,
-                 keep_prepool: bool = False, chain_max_batch: int = 0):
-        """chain_max_batch: largest batch whose conv_2..23 run as one persistent cooperative launch (the small-batch
+                 keep_prepool: bool = False, chain_max_batch: int = 0, graph: str = "yolov2", tiny_filters: int = 1024):
+        """graph: "yolov2" (cfg/yolov2.cfg, yolov2-voc.cfg: 23 conv layers) or "tiny" (cfg/yolov2-tiny*.cfg: 9 conv
+        layers; tiny_filters = filters of its conv_8, 1024 voc / 512 coco; weights through load_darknet_weights).
+        chain_max_batch: largest batch whose conv_2..23 run as one persistent cooperative launch (the small-batch
         schedule, conv_chain_kernel); 0 = library default (1), -1 = never."""
         if not torch.cuda.is_available():
             raise N.B2TError("no CUDA device: the B200 path has no CPU fallback")
@@ -69,6 +71,11 @@ class DetectorEngine:
         cfg.convlstm_units = convlstm_units
         cfg.reserved[0] = 1 if keep_prepool else 0
         cfg.reserved[1] = chain_max_batch
+        if graph not in ("yolov2", "tiny"):
+            raise ValueError(f"unknown graph '{graph}'")
+        if graph == "tiny":
+            cfg.reserved[2], cfg.reserved[3] = 1, tiny_filters
+        self.graph = graph
         self.semantics, self.convlstm_units = semantics, convlstm_units
         h = C.c_void_p()
         N.check(self.lib.b2t_create(C.byref(cfg), C.byref(h)))

@@ -125,3 +125,48 @@ class DarknetRef:
             prob[j] = np.ctypeslib.as_array(d.prob, shape=(n_class,))
         self.lib.free_detections(dets, n)
         return boxes, obj, prob
+
+
+TINY_VOC_ANCHORS = "1.08,1.19,  3.42,4.41,  6.63,11.38,  9.42,5.11,  16.62,10.52"
+COCO_ANCHORS = "0.57273, 0.677385, 1.87446, 2.06253, 3.33843, 5.47434, 7.88282, 3.52778, 9.77052, 9.16828"
+
+
+def write_tiny_cfg(path: str, n_class: int, size: int = 416, f8: int = 1024, anchors: str = TINY_VOC_ANCHORS) -> None:
+    """The layer list of darknet/cfg/yolov2-tiny-voc.cfg (f8 = 1024, 20 classes) / yolov2-tiny.cfg (f8 = 512, 80
+    classes): six conv + maxpool pairs (the sixth pool has stride 1), two more 3x3 convs, the 1x1 head, region."""
+    conv = "[convolutional]\nbatch_normalize=1\nfilters={f}\nsize=3\nstride=1\npad=1\nactivation=leaky\n"
+    s = [f"[net]\nbatch=1\nsubdivisions=1\nwidth={size}\nheight={size}\nchannels=3\nmomentum=0.9\ndecay=0.0005\n"]
+    for i, f in enumerate((16, 32, 64, 128, 256, 512)):
+        s.append(conv.format(f=f))
+        s.append("[maxpool]\nsize=2\nstride=%d\n" % (1 if i == 5 else 2))
+    s.append(conv.format(f=1024))
+    s.append(conv.format(f=f8))
+    s.append(f"[convolutional]\nsize=1\nstride=1\npad=1\nfilters={5 * (5 + n_class)}\nactivation=linear\n")
+    s.append(f"[region]\nanchors = {anchors}\nbias_match=1\nclasses={n_class}\ncoords=4\nnum=5\nsoftmax=1\njitter=.2\n"
+             "rescore=1\nobject_scale=5\nnoobject_scale=1\nclass_scale=1\ncoord_scale=1\nabsolute=1\nthresh = .6\nrandom=1\n")
+    with open(path, "w") as f:
+        f.write("\n".join(s))
+
+
+def write_tiny_weights(path: str, n_class: int, f8: int = 1024, seed: int = 0) -> None:
+    """Seeded random-init weights for the tiny graph in darknet's file order (parser.c:1149-1198): per conv
+    biases(beta) [scales(gamma) rolling_mean rolling_variance] weights[Cout][Cin][kh][kw]; v0.1 header."""
+    import struct
+    rng = np.random.default_rng(seed)
+    chans = [(3, 16, 3), (16, 32, 3), (32, 64, 3), (64, 128, 3), (128, 256, 3), (256, 512, 3), (512, 1024, 3), (1024, f8, 3),
+             (f8, 5 * (5 + n_class), 1)]
+    with open(path, "wb") as f:
+        f.write(struct.pack("<iiii", 0, 1, 0, 0))
+        for i, (ci, co, k) in enumerate(chans):
+            last = i == len(chans) - 1
+            if last:
+                b = (0.1 * rng.standard_normal(co)).astype("<f4")
+                b.reshape(5, 5 + n_class)[:, 4] -= 1.0
+                f.write(b.tobytes())
+            else:
+                f.write((0.1 * rng.standard_normal(co)).astype("<f4").tobytes())          # beta
+                f.write(rng.uniform(0.5, 1.5, co).astype("<f4").tobytes())                # gamma
+                f.write((0.1 * rng.standard_normal(co)).astype("<f4").tobytes())          # mean
+                f.write(rng.uniform(0.5, 1.5, co).astype("<f4").tobytes())                # var
+            gain = (0.3 if last else 1.0) * np.sqrt(2.0 / (k * k * ci))
+            f.write((rng.standard_normal((co, ci, k, k)) * gain).astype("<f4").tobytes())

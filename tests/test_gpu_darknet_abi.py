@@ -217,3 +217,57 @@ def test_yolo_detect_on_a_jpeg_path_side_by_side(files):
                 hits += 1
                 break
     assert hits >= len(c) - 2, (hits, len(c), len(a))
+
+
+@pytest.mark.skipif(not darknet_ref.available(), reason="oracle/_ref/libdarknet.so not present")
+@pytest.mark.parametrize("variant", ["voc", "coco"])
+def test_tiny_yolov2_graph_side_by_side(tmp_path, variant):
+    """cfg/yolov2-tiny-voc.cfg (20 classes, conv_8 = 1024) and cfg/yolov2-tiny.cfg (80 classes, conv_8 = 512): nine conv
+    layers, conv_1 with 16 channels, the sixth maxpool with stride 1 -- through the reference's C library and through
+    libb200track.so (compat ABI: one frame = the chain schedule; engine API: batch 3 = one kernel per layer)."""
+    import torch
+    from object_tracking_b200.engine import DetectorEngine
+    n_class, f8, anchors = (20, 1024, darknet_ref.TINY_VOC_ANCHORS) if variant == "voc" else (80, 512, darknet_ref.COCO_ANCHORS)
+    d = str(tmp_path)
+    cfg, wts = os.path.join(d, "tiny.cfg"), os.path.join(d, "tiny.weights")
+    darknet_ref.write_tiny_cfg(cfg, n_class, 416, f8, anchors)
+    darknet_ref.write_tiny_weights(wts, n_class, f8, seed=3)
+    names = os.path.join(d, "n.names")
+    open(names, "w").write("\n".join(f"c{i}" for i in range(n_class)) + "\n")
+    data = os.path.join(d, "n.data")
+    open(data, "w").write(f"classes= {n_class}\nnames = {names}\n")
+    ref = bind(C.CDLL(darknet_ref.LIB_PATH))
+    ours = bind(C.CDLL(_native.LIB_PATH))
+    cwd = os.getcwd()
+    net_r = ref.load_network(cfg.encode(), wts.encode(), 0)
+    net_o = ours.load_network(cfg.encode(), wts.encode(), 0)
+    os.chdir(cwd)
+    assert net_o, _native.lib().b2t_last_error()
+    meta = ours.get_metadata(data.encode())
+    rng = np.random.default_rng(5)
+    frames = rng.integers(0, 256, (3, 416, 416, 3), dtype=np.uint8)
+    for k, n_layer in enumerate((13, 14, 15)):                        # darknet layers 12, 13 (features) and 14 (head)
+        do, dr = ours.layer_dims(net_o, n_layer), ref.layer_dims(net_r, n_layer)
+        assert (do.w, do.h, do.c) == (dr.w, dr.h, dr.c), n_layer
+    thr = .2 if variant == "voc" else .05
+    a = detect(ref, net_r, meta, as_image(frames[0]), thresh=thr)
+    b = detect(ours, net_o, meta, as_image(frames[0]), thresh=thr)
+    for n_layer, tol in ((12, 2e-3), (14, 3e-3), (15, 3e-3)):         # pool_6 (the stride-1 max-pool), conv_8, head logits
+        fr, fo = ref.network_extract_feat(net_r, n_layer), ours.network_extract_feat(net_o, n_layer)
+        assert fr.size == fo.size, n_layer
+        fa = np.ctypeslib.as_array(fr.feat, shape=(fr.size,)).copy()
+        fb = np.ctypeslib.as_array(fo.feat, shape=(fo.size,)).copy()
+        assert np.abs(fa - fb).max() < tol * max(1.0, np.abs(fa).max() / 10), (n_layer, np.abs(fa - fb).max(), np.abs(fa).max())
+    logits_ref = fa.reshape(5 * (5 + n_class), 13, 13)
+    assert (len(a) >= 3 or variant == "coco") and [x[0] for x in a] == [x[0] for x in b]
+    for (n1, p1, b1), (n2, p2, b2) in zip(a, b):
+        assert abs(p1 - p2) < 3e-4 and np.abs(np.array(b1) - np.array(b2)).max() < 5e-2
+    # the engine API at batch 3 (one kernel per layer) gives the same logits for frame 0 as the library
+    e = DetectorEngine(n_class=n_class, max_batch=3, semantics="darknet", graph="tiny", tiny_filters=f8)
+    e.load_darknet_weights(wts)
+    e.finalize()
+    lg = e.forward(torch.from_numpy(frames).cuda()).cpu().numpy()
+    got = lg[0].reshape(13, 13, -1).transpose(2, 0, 1)
+    assert np.abs(got - logits_ref).max() < 3e-3 * max(1.0, np.abs(logits_ref).max() / 10)
+    one = e.forward(torch.from_numpy(frames[:1]).cuda()).cpu().numpy()   # batch 1: chain schedule
+    assert np.abs(one[0] - lg[0]).max() < 5e-4
