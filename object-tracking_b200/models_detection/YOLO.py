@@ -55,11 +55,19 @@ class YOLO:
             self.cpu_mode, self.gpu_id = argvs[0], argvs[1]
 
     def load_detection_model(self):
-        """YOLO.py:128-134 (load_network + get_metadata).  cpu_mode is ignored: this build has no CPU path."""
+        """YOLO.py:128-134 (load_network + get_metadata).  cpu_mode is ignored: this build has no CPU path.
+        ``config.model_detector.config_file`` selects the graph by name like the cfg files it points at:
+        ``yolov2-tiny-voc.cfg`` / ``yolov2-tiny.cfg`` -> the 9-conv tiny graph (weights file required), anything else
+        -> the 23-conv YOLOv2 graph."""
         dev = self.gpu_id if self.gpu_id < torch.cuda.device_count() else 0
+        cfg_name = os.path.basename(str(self.CONFIG)).lower()
+        tiny = "tiny" in cfg_name
         self.engine = DetectorEngine(n_class=self.n_class, image_size=self.image_size, max_batch=self.max_batch,
-                                     semantics="darknet", device=dev)
+                                     semantics="darknet", device=dev, graph="tiny" if tiny else "yolov2",
+                                     tiny_filters=1024 if "voc" in cfg_name else 512)
         wpath = os.path.join("darknet", self.WEIGHTS)
+        if tiny and self._weights is None and not os.path.exists(wpath) and not (self._broadcast and self._rank != 0):
+            raise FileNotFoundError(f"{wpath}: the tiny graph has no synthetic weights; provide the darknet weights file")
         if self._broadcast and self._rank != 0:
             # multi-GPU: rank 0 packs and uploads, everyone else receives the packed blob over NCCL/NVLink
             self.synthetic_weights = self._weights is None and not os.path.exists(wpath)
