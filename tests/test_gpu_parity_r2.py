@@ -583,3 +583,22 @@ def test_device_overlay_and_overlap_metric():
     ref_s = np.array([U.overlap_score(t[i], p[i]) for i in range(n)])
     assert np.array_equal(s.cpu().numpy(), ref_s)
     assert float(m.cpu()[0]) == U.average_overlap_score(t, p)
+
+
+def test_decode_overflow_raises_everywhere():
+    """the decode kernel reports a candidate-table overflow (thresholds far below 0.5: several classes per
+    anchor pass) as count = -1; every host path must raise instead of slicing rows[:-1]."""
+    from object_tracking_b200._native import B2TError
+    from object_tracking_b200.engine import rows_to_host
+    from object_tracking_b200.utility import utils as U
+    eng = _engine(n_class=20, max_batch=1)
+    net = np.zeros((13, 13, 5, 25), np.float32)
+    net[..., 4] = 8.0                                             # conf ~ 1, uniform classes: p = 0.05 for 845 x 20 pairs
+    boxes, counts = eng.decode(torch.from_numpy(net[None]).cuda(), 0.01, 0.45)
+    assert int(counts.cpu()[0]) == -1
+    with pytest.raises(B2TError):
+        rows_to_host(boxes, counts)
+    with pytest.raises(B2TError):
+        U.decode_netout(net, 0.01, 0.45, W.ANCHORS, 20, engine=eng)
+    ok = U.decode_netout(net, 0.5, 0.45, W.ANCHORS, 20, engine=eng)   # the reference's own threshold: nothing passes
+    assert ok == []
