@@ -121,6 +121,7 @@ struct b2t_ctx {
     long launches = 0;
     int n_sm = 148;
     int chain_max_batch = 1;                      // batches up to this size run conv_2..23 in conv_chain_kernel (0 = never)
+    bool chain_forced = false;                    // reserved[1] given explicitly: no image-size condition
     unsigned int *d_chain_counter = nullptr;      // its grid-barrier arrival counter
     long capture_launches0 = 0;                   // b2t_graph_begin: launch counter at the start of the capture
     PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
@@ -213,7 +214,7 @@ static void choose_pm_tile(int H, int W, int ksize, bool pool, int row_bytes, bo
 
 static unsigned magic_for(int d) { return d <= 1 ? 0u : (unsigned)((0x100000000ull + (unsigned)d - 1) / (unsigned)d); }
 
-static int choose_splits_halo(int ctas, int cin_chunks, int taps, int n_sm) {
+static int choose_splits_halo(int ctas, int cin_chunks, int taps, int n_sm, int batch) {
     const int force = dev_env("B2T_SPLITS", 0);
     int best_s = 1;
     double best_cost = 1e30;
@@ -226,7 +227,10 @@ static int choose_splits_halo(int ctas, int cin_chunks, int taps, int n_sm) {
         static const int chain_cap = dev_env("B2T_CHAIN", 320);
         if (per * taps * 4 > chain_cap && s < max_s) continue;
         const long waves = ((long)ctas * s + n_sm - 1) / n_sm;
-        const double cost = (double)waves * (per * taps + 10.0) + (s > 1 ? 3.0 * s : 0.0);
+        // split-K finish = a second kernel + one write and s reads of the partials: its bytes grow with the batch (3 units
+        // per split fits 36 frames; at <= 8 frames the partials are a few MB and stay in L2)
+        const double red = s > 1 ? (batch <= 8 ? 1.0 + 0.25 * s : 3.0 * s) : 0.0;
+        const double cost = (double)waves * (per * taps + 10.0) + red;
         if (cost < best_cost - 1e-9) { best_cost = cost; best_s = s; }
     }
     return best_s;
@@ -324,7 +328,7 @@ extern "C" int b2t_create(const b2t_config *cfg, b2t_ctx **out) {
     b2t_ctx *c = new b2t_ctx();
     c->cfg = *cfg;
     c->keep_prepool = cfg->reserved[0];
-    if (cfg->reserved[1]) c->chain_max_batch = cfg->reserved[1] < 0 ? 0 : cfg->reserved[1];
+    if (cfg->reserved[1]) { c->chain_max_batch = cfg->reserved[1] < 0 ? 0 : cfg->reserved[1]; c->chain_forced = true; }
     c->G = cfg->image_h / 32;
     c->D = 5 + cfg->n_class;
     const int AD = c->A * c->D;
@@ -493,7 +497,7 @@ extern "C" int b2t_create(const b2t_config *cfg, b2t_ctx **out) {
 #endif
             if (cfg->engine == B2T_ENGINE_TCGEN05) {
                 const int ctas = ((l.W + l.hC - 1) / l.hC) * ((l.H + l.hR - 1) / l.hR) * ((l.cout + 127) / 128) * bsz;
-                s = choose_splits_halo(ctas, l.cin_pad / l.kchunk, l.k * l.k, 148);
+                s = choose_splits_halo(ctas, l.cin_pad / l.kchunk, l.k * l.k, 148, bsz);
                 if (bsz <= c->chain_max_batch) {
                     const size_t s2 = choose_splits_chain(ctas, l.cin_pad / l.kchunk * l.k * l.k, 148);
                     if (s2 > s) s = s2;
@@ -908,7 +912,7 @@ static int halo_geometry(b2t_ctx *c, ConvLayer &l, int B, ConvParams &p, bool ch
         p.splits = choose_splits_chain(ctas, units, c->n_sm);
         p.k_per_units = (units + p.splits - 1) / p.splits;
     } else {
-        p.splits = choose_splits_halo(ctas, p.cin_chunks, l.k * l.k, c->n_sm);
+        p.splits = choose_splits_halo(ctas, p.cin_chunks, l.k * l.k, c->n_sm, B);
     }
     if (p.splits > 1 && (size_t)p.splits * B * l.H * l.W * p.ldp * 4 > c->partial_bytes)
         return fail(-2, "internal: split-K workspace too small for conv %d", l.index);
@@ -1162,7 +1166,10 @@ static int forward_impl(b2t_ctx *c, const void *frames, int dtype, int B, float 
     float *logits = reinterpret_cast<float *>(c->d_ws + c->off_logits);
     // small batches: consecutive layers run inside ONE persistent cooperative launch (conv_chain_kernel); per-layer
     // event timing (b2t_profile_forward) keeps the one-kernel-per-layer schedule
-    const bool chain = !ev && c->chain_max_batch > 0 && B <= c->chain_max_batch && c->d_chain_counter;
+    // (measured, profiles/r2_batch_sweep_*.txt: the chain wins for one 416x416 frame; at 608x608 the layers have enough
+    // items for the per-layer kernels even at batch 1)
+    const bool chain = !ev && c->chain_max_batch > 0 && B <= c->chain_max_batch && c->d_chain_counter &&
+                       (c->cfg.image_h <= 448 || c->chain_forced);
     ChainBuilder *cb = nullptr;
 #ifdef B2T_DEV
     static long long *chain_trace = nullptr;
