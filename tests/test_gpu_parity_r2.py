@@ -602,3 +602,52 @@ def test_decode_overflow_raises_everywhere():
         U.decode_netout(net, 0.01, 0.45, W.ANCHORS, 20, engine=eng)
     ok = U.decode_netout(net, 0.5, 0.45, W.ANCHORS, 20, engine=eng)   # the reference's own threshold: nothing passes
     assert ok == []
+
+
+def _wide_bn_weights(C, seed=77):
+    """He-initialised kernels with BatchNorm statistics spread over orders of magnitude per channel: gamma log-uniform
+    in [0.05, 20], variance in [0.01, 100] (folded scale 5e-3 .. 2e2 before normalisation); each layer's folded scales
+    are then normalised to unit rms so that, like in a trained network, the activations stay O(1)..O(100) layer after
+    layer while single channels sit three decades below or one above."""
+    w = W.synthetic_yolo_weights(C, seed=3)
+    rng = np.random.default_rng(seed)
+    for s in W.yolo_layer_table(C):
+        if s.bn:
+            g = np.exp(rng.uniform(np.log(0.05), np.log(20.0), s.cout))
+            v = np.exp(rng.uniform(np.log(0.01), np.log(100.0), s.cout))
+            g /= np.sqrt(np.mean((g / np.sqrt(v + 1e-3)) ** 2))
+            w[f"gamma_{s.index}"] = g.astype(np.float32)
+            w[f"var_{s.index}"] = v.astype(np.float32)
+            w[f"mean_{s.index}"] = (rng.standard_normal(s.cout) * 0.5).astype(np.float32)
+    return w
+
+
+def test_wide_batchnorm_spread_weights():
+    """parity was only measured on He-initialised weights with tame BatchNorm statistics; trained YOLOv2
+    weights have BN scales spread over orders of magnitude.  With _wide_bn_weights the fp16 (hi, lo) planes must keep
+    their 22 bits through that spread: every checked layer within 5e-5 of the fp64 oracle relative to its own magnitude,
+    logits within 1e-4 of theirs, darknet and Keras BatchNorm folding."""
+    C, B = 2, 2
+    w = _wide_bn_weights(C)
+    frames = np.random.default_rng(5).integers(0, 256, (B, 416, 416, 3), dtype=np.uint8)
+    names = [f"norm_{i}" for i in (3, 6, 9, 13, 14, 18, 20)] + ["concat"]
+    for sem in ("keras", "darknet"):
+        o = yolo_oracle.yolo_forward(yolo_oracle.normalize(frames), w, C, dtype=np.float64, want=names, mode=sem)
+        eng = _engine(n_class=C, max_batch=B, semantics=sem)
+        eng.set_weights(w)
+        eng.finalize()
+        lg = eng.forward(torch.from_numpy(frames).cuda()).cpu().numpy()
+        stats = {}
+        for n in names + ["conv_feat"]:
+            got = eng.extract(n, B).cpu().numpy()
+            ref = o[n] if n != "conv_feat" else o["feat"]
+            assert np.isfinite(got).all(), (sem, n)
+            ch = np.abs(ref).reshape(-1, ref.shape[-1]).max(axis=0)
+            stats[n] = (float(np.abs(ref).max()), float(np.abs(got - ref).max() / np.abs(ref).max()),
+                        float(ch.max() / max(ch[ch > 0].min(), 1e-30)))
+        assert max(v[1] for v in stats.values()) < 5e-5, (sem, stats)
+        assert max(v[0] for v in stats.values()) < 6e4, (sem, stats)                 # inside the fp16 planes' range
+        assert max(v[2] for v in stats.values()) > 100, (sem, stats)                  # the per-channel spread is real
+        err = np.abs(lg - o["logits"]).max()
+        assert err < 1e-4 * max(1.0, np.abs(o["logits"]).max()), (sem, err, np.abs(o["logits"]).max())
+        del eng
