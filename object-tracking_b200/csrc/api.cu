@@ -214,7 +214,7 @@ static void choose_pm_tile(int H, int W, int ksize, bool pool, int row_bytes, bo
 
 static unsigned magic_for(int d) { return d <= 1 ? 0u : (unsigned)((0x100000000ull + (unsigned)d - 1) / (unsigned)d); }
 
-static int choose_splits_halo(int ctas, int cin_chunks, int taps, int n_sm, int batch) {
+static int choose_splits_halo(int ctas, int cin_chunks, int taps, int n_sm, int batch, bool capped = true) {
     const int force = dev_env("B2T_SPLITS", 0);
     int best_s = 1;
     double best_cost = 1e30;
@@ -225,7 +225,7 @@ static int choose_splits_halo(int ctas, int cin_chunks, int taps, int n_sm, int 
         if (force > 0 && s != force && s != max_s) continue;
         // the tensor core truncates addends to the accumulator's exponent: keep one accumulation chain short
         static const int chain_cap = dev_env("B2T_CHAIN", 320);
-        if (per * taps * 4 > chain_cap && s < max_s) continue;
+        if (capped && per * taps * 4 > chain_cap && s < max_s) continue;
         const long waves = ((long)ctas * s + n_sm - 1) / n_sm;
         // split-K finish = a second kernel + one write and s reads of the partials: its bytes grow with the batch (3 units
         // per split fits 36 frames; at <= 8 frames the partials are a few MB and stay in L2)
@@ -911,6 +911,13 @@ static int halo_geometry(b2t_ctx *c, ConvLayer &l, int B, ConvParams &p, bool ch
         const int units = p.cin_chunks * l.k * l.k;
         p.splits = choose_splits_chain(ctas, units, c->n_sm);
         p.k_per_units = (units + p.splits - 1) / p.splits;
+    } else if (!l.h_small && l.hN <= 192) {
+        // long accumulation chains are cut into passes INSIDE the CTA (conv_halo_kernel<big>: the running sums are
+        // parked in spare TMEM columns / registers), so the K split is chosen for parallelism only
+        static const int chain_cap = dev_env("B2T_CHAIN", 320);
+        p.splits = choose_splits_halo(ctas, p.cin_chunks, l.k * l.k, c->n_sm, B, false);
+        const int per = (p.cin_chunks + p.splits - 1) / p.splits;
+        p.k_passes = (per * l.k * l.k * 4 + chain_cap - 1) / chain_cap;
     } else {
         p.splits = choose_splits_halo(ctas, p.cin_chunks, l.k * l.k, c->n_sm, B);
     }

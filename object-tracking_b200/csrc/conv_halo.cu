@@ -86,6 +86,67 @@ __device__ __forceinline__ void halo_epilogue(const ConvParams &p, float *stage,
     epilogue_store(p, stage, kStageLd, 4, b, y0, x0, cout0, zsplit, et, kEpiThreads);
 }
 
+// Multi-pass variant (conv_halo_kernel<big>, p.k_passes > 1, N <= 192): the K range of an item is accumulated in
+// k_passes separate tensor-core chains (the tensor core truncates every addend to the accumulator's exponent, so one
+// chain must stay short: DESIGN.md section 4).  After each pass but the last the epilogue threads read the accumulators
+// and PARK the running fp32 sums while the MMA warp restarts the accumulators: pixel columns [0, 128) in the 128 TMEM
+// columns the two accumulators (2 x N <= 384) leave free (tcgen05.st), columns [128, 192) in 32 registers per thread.
+// After the last pass the sums are added in pass order -- the same arithmetic as the split-K partial buffers + finish
+// kernel this replaces, without their HBM round trip and second launch.
+constexpr int kPassMaxN = 192, kPassTmemCols = 128;
+template <bool kLast>
+__device__ __forceinline__ void halo_pass_accumulate(const ConvParams &p, float (&keep)[2][16], float *stage, uint32_t tmem_acc,
+                                                     int N, int cout0, bool first_pass) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int ch_local = q * 32 + lane, ch = cout0 + ch_local;
+    const bool finish = p.splits == 1;                           // a K-split item stages its raw sum (split-K partial)
+    const float sc = (kLast && finish && ch < p.Cout) ? __ldg(p.scale + ch) : 0.f;
+    const float bi = (kLast && finish && ch < p.Cout) ? __ldg(p.bias + ch) : 0.f;
+    const uint32_t lane_addr = tmem_acc + (uint32_t(q * 32) << 16);
+    const uint32_t park = lane_addr + 2 * N;                     // first spare column
+#pragma unroll
+    for (int j = 0; j < kPassMaxN / 32; ++j) {
+        const int n0 = half * 16 + 32 * j;                       // this thread's j-th group of 16 columns
+        if (n0 < N) {
+            uint32_t a[16], c2[16];
+            tmem_ld16(lane_addr + n0, a);                        // main accumulator
+            tmem_ld16(lane_addr + N + n0, c2);                   // correction accumulator
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a[i] = __float_as_uint(__uint_as_float(a[i]) + __uint_as_float(c2[i]));
+            if (!first_pass) {                                   // + the parked sum of the earlier passes, pass order
+                if (j < kPassTmemCols / 32) {
+                    tmem_ld16(park + n0, c2);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) a[i] = __float_as_uint(__uint_as_float(c2[i]) + __uint_as_float(a[i]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) a[i] = __float_as_uint(keep[j - kPassTmemCols / 32][i] + __uint_as_float(a[i]));
+                }
+            }
+            if (kLast) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float tv = __uint_as_float(a[i]);
+                    if (finish) {
+                        tv = fmaf(tv, sc, bi);
+                        tv = p.act ? fmaxf(tv, 0.1f * tv) : tv;
+                    }
+                    stage[(n0 + i) * kStageLd + ch_local] = tv;
+                }
+            } else if (j < kPassTmemCols / 32) {
+                tmem_st16(park + n0, a);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) keep[j - kPassTmemCols / 32][i] = __uint_as_float(a[i]);
+            }
+        }
+    }
+    if (!kLast) tmem_st_wait();
+}
+
 // Two resource shapes of the same kernel:
 //  * big   -- one CTA per SM: two 64 KB patch buffers (double-buffered over channel chunks), 3 weight stages, all
 //             512 TMEM columns (N up to 256).  For the long-K layers (26x26 and 13x13 grids, ConvLSTM).
@@ -228,20 +289,28 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_consta
         const uint32_t w16_0 = umma_desc_lo(smem_u32(s_w)), h16_0 = umma_desc_lo(smem_u32(s_halo));
         const uint32_t xl_off = p.h_plane_bytes >> 4;
         const bool k128 = p.kbytes == 128, issue = !(B2T_DBG_BITS(p) & 8);
-        int ws = 0, g_it = 0, k = 0;
+        int ws = 0, g_it = 0, k = 0, acc_seq = 0;
         uint32_t wphase = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
             int b, y0, x0, cout0, z, c_begin, n_chunks;
             decode_item(item, b, y0, x0, cout0, z, c_begin, n_chunks);
-            const int n_main = max(1, min(min(p.n_main, Cfg::kTmemCols / N - 1), n_chunks * taps));
+            // accumulation passes: chunks [j*pc, (j+1)*pc) of the item form chain j (k_passes = 1: the whole item)
+            const int passes = kSmall ? 1 : max(1, min(p.k_passes, n_chunks));
+            const int pc = (n_chunks + passes - 1) / passes;
+            // (several passes: one main accumulator, the spare TMEM columns hold the parked sums)
+            const int n_main = passes > 1 ? 1 : max(1, min(min(p.n_main, Cfg::kTmemCols / N - 1), n_chunks * taps));
             const uint32_t t_corr = tmem_base + n_main * N;
             const bool tr = B2T_TRACE_PTR(p) && blockIdx.x == 0 && k < 64 && lane == 0;
             if (tr) B2T_TRACE_PTR(p)[k * 8 + 1] = clock64();
-            if (k > 0) { mbar_wait(acc_empty, (k - 1) & 1); tc_fence_after(); }   // the epilogue has read the accumulators
-            if (tr) B2T_TRACE_PTR(p)[k * 8 + 2] = clock64();
             int mi = 0;
             uint32_t first = 1, am = 0;
             for (int it = 0; it < n_chunks; ++it, ++g_it) {
+                if (it % pc == 0) {                              // a new chain: the epilogue has read the accumulators
+                    if (acc_seq > 0) { mbar_wait(acc_empty, (acc_seq - 1) & 1); tc_fence_after(); }
+                    if (tr && it == 0) B2T_TRACE_PTR(p)[k * 8 + 2] = clock64();
+                    mi = 0; first = 1; am = 0;
+                }
+                const bool pass_end = (it % pc == pc - 1) || it == n_chunks - 1;
                 const int hb = g_it % kHaloBufs;
                 mbar_wait(&halo_full[hb], (g_it / kHaloBufs) & 1);
                 if (tr && it == 0) B2T_TRACE_PTR(p)[k * 8 + 3] = clock64();
@@ -266,7 +335,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_consta
                         }
                         umma_commit(&w_empty[ws]);
                         if (last_tap) umma_commit(&halo_empty[hb]);
-                        if (last_tap && it == n_chunks - 1) umma_commit(accum_bar);
+                        if (last_tap && pass_end) umma_commit(accum_bar);
                     }
                     __syncwarp();
                     first = 0;
@@ -274,22 +343,50 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_consta
                     if (++kw == p.ksize) { kw = 0; xh += row16; } else xh += kb16;   // next tap: patch start shifted by (kh*hP + kw) rows
                     if (++ws == kWStages) { ws = 0; wphase ^= 1; }
                 }
+                if (pass_end) ++acc_seq;
             }
             if (tr) B2T_TRACE_PTR(p)[k * 8 + 7] = clock64();
         }
     } else {
         // ===================== epilogue (the patch buffers are dead once accum_bar fires) =====================
-        int k = 0;
+        int k = 0, acc_seq = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
             int b, y0, x0, cout0, z, c_begin, n_chunks;
             decode_item(item, b, y0, x0, cout0, z, c_begin, n_chunks);
-            const int n_main = max(1, min(min(p.n_main, Cfg::kTmemCols / N - 1), n_chunks * taps));
+            const int passes = kSmall ? 1 : max(1, min(p.k_passes, n_chunks));
+            const int pc = (n_chunks + passes - 1) / passes;
+            const int n_pass = (n_chunks + pc - 1) / pc;
+            const int n_main = passes > 1 ? 1 : max(1, min(min(p.n_main, Cfg::kTmemCols / N - 1), n_chunks * taps));
             const bool tr = B2T_TRACE_PTR(p) && blockIdx.x == 0 && k < 64 && threadIdx.x == 64;
             if (tr) B2T_TRACE_PTR(p)[k * 8 + 4] = clock64();
-            mbar_wait(accum_bar, k & 1);
-            tc_fence_after();
-            if (tr) B2T_TRACE_PTR(p)[k * 8 + 5] = clock64();
-            halo_epilogue(p, reinterpret_cast<float *>(smem), tmem_base, n_main + 1, N, b, y0, x0, cout0, z, acc_empty);
+            if (kSmall || n_pass == 1) {
+                mbar_wait(accum_bar, acc_seq & 1);
+                ++acc_seq;
+                tc_fence_after();
+                if (tr) B2T_TRACE_PTR(p)[k * 8 + 5] = clock64();
+                halo_epilogue(p, reinterpret_cast<float *>(smem), tmem_base, n_main + 1, N, b, y0, x0, cout0, z, acc_empty);
+            } else if constexpr (!kSmall) {
+                float keep[2][16];
+                float *stage = reinterpret_cast<float *>(smem);
+                for (int ps = 0; ps < n_pass; ++ps) {
+                    mbar_wait(accum_bar, acc_seq & 1);
+                    ++acc_seq;
+                    tc_fence_after();
+                    if (ps + 1 < n_pass) {
+                        halo_pass_accumulate<false>(p, keep, stage, tmem_base, N, cout0, ps == 0);
+                        tc_fence_before();
+                        asm volatile("bar.sync 1, 256;" ::: "memory");
+                        if (threadIdx.x == 64) mbar_arrive(acc_empty);          // the next chain may restart the accumulators
+                    } else {
+                        if (tr) B2T_TRACE_PTR(p)[k * 8 + 5] = clock64();
+                        halo_pass_accumulate<true>(p, keep, stage, tmem_base, N, cout0, false);
+                        tc_fence_before();
+                        asm volatile("bar.sync 1, 256;" ::: "memory");
+                        if (threadIdx.x == 64) mbar_arrive(acc_empty);
+                        epilogue_store(p, stage, kStageLd, 4, b, y0, x0, cout0, z, threadIdx.x - 64, kEpiThreads);
+                    }
+                }
+            }
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (threadIdx.x == 64) mbar_arrive(stage_free);
             if (tr) B2T_TRACE_PTR(p)[k * 8 + 6] = clock64();

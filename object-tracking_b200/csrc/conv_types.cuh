@@ -66,6 +66,8 @@ struct ConvParams {
     int pm_w_bytes;
     unsigned int magic_tx, magic_ty;   // ceil(2^32 / h_tiles_x), ceil(2^32 / h_tiles_y) (0 when the divisor is 1): fast item decode
     int b_in_off;           // added to the image index of the INPUT view only (state slot of the first stream)
+    int k_passes;           // conv_halo_kernel<big>: accumulation passes per item (>= 1): the K range of an item is cut into
+                            // k_passes chains, their fp32 sums are added in registers (no split-K partials in HBM)
     int k_per_units;        // conv_chain_kernel: (chunk, tap) units per K split, chunk-major (finer than whole chunks)
 #ifdef B2T_DEV              // developer builds only (make DEV=1); the release library has neither field nor the code behind them
     int dbg;                // experiments: 1 = weight TMA only for the first ring pass, 2 = patch TMA only for the

@@ -28,6 +28,11 @@ e.finalize()
 for b in (1, 2, 3):
     lg = e.forward(frames(b))
 done += ["frames_to_c8", "conv_pm(mode 0,1)", "conv_chain", "conv_halo_persist", "conv_halo<big>", "conv_halo<small>", "splitk_epilogue"]
+big = DetectorEngine(n_class=C, max_batch=20)                               # 20 frames: conv_19/20/22 run unsplit with two / three
+big.set_weights(w); big.finalize()                                          # in-CTA accumulation passes (TMEM-parked sums)
+big.forward(frames(20))
+done.append("conv_halo<big> multi-pass")
+del big
 e.forward(torch.rand((1, 416, 416, 3), device="cuda"))                      # conv1_direct_kernel (float frames)
 done.append("conv1_direct")
 e.extract("norm_5", 3); e.extract("concat", 3)
@@ -45,6 +50,11 @@ e.select_detection(dets, counts, 416, 416, mask, 32)
 e.heatmap_from_box(torch.rand((5, 4), device="cuda"), 32)
 e.box_from_heatmap(torch.rand((5, 1024), device="cuda"), 32, 0.75)
 done += ["select_detection", "heatmap_from_box", "box_from_heatmap"]
+e.draw_boxes(frames(2), *e.decode(e.logits(2), 0.5, 0.45))
+e.overlap_scores(torch.rand((9, 4), dtype=torch.float64, device="cuda"), torch.rand((9, 4), dtype=torch.float64, device="cuda"))
+clip = torch.from_numpy(rng.integers(0, 256, (2, 3, 416, 416, 3), dtype=np.uint8)).cuda()
+e.ingest_windows(clip[:, 1:2]); e.forward_ingested(2)
+done += ["draw_boxes", "overlap_scores", "frames_to_c8 (strided ingest)"]
 e.resize_frames(torch.from_numpy(rng.integers(0, 256, (2, 300, 400, 3), dtype=np.uint8)).cuda(), 416)
 e.letterbox_frames(torch.from_numpy(rng.integers(0, 256, (2, 300, 400, 3), dtype=np.uint8)).cuda(), bgr=True)
 done += ["resize_bilinear_u8", "letterbox_u8"]
