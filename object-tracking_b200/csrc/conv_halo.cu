@@ -295,22 +295,23 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_consta
             int b, y0, x0, cout0, z, c_begin, n_chunks;
             decode_item(item, b, y0, x0, cout0, z, c_begin, n_chunks);
             // accumulation passes: chunks [j*pc, (j+1)*pc) of the item form chain j (k_passes = 1: the whole item)
-            const int passes = kSmall ? 1 : max(1, min(p.k_passes, n_chunks));
-            const int pc = (n_chunks + passes - 1) / passes;
+            int passes = 1, pc = n_chunks;
+            if (!kSmall && p.k_passes > 1) { passes = min(p.k_passes, n_chunks); pc = (n_chunks + passes - 1) / passes; }
             // (several passes: one main accumulator, the spare TMEM columns hold the parked sums)
             const int n_main = passes > 1 ? 1 : max(1, min(min(p.n_main, Cfg::kTmemCols / N - 1), n_chunks * taps));
             const uint32_t t_corr = tmem_base + n_main * N;
             const bool tr = B2T_TRACE_PTR(p) && blockIdx.x == 0 && k < 64 && lane == 0;
             if (tr) B2T_TRACE_PTR(p)[k * 8 + 1] = clock64();
-            int mi = 0;
-            uint32_t first = 1, am = 0;
+            int mi = 0, pass_left = 0;                            // chunks left in the current chain (no division in this loop:
+            uint32_t first = 1, am = 0;                           //  one thread issues every MMA of the CTA)
             for (int it = 0; it < n_chunks; ++it, ++g_it) {
-                if (it % pc == 0) {                              // a new chain: the epilogue has read the accumulators
+                if (pass_left == 0) {                            // a new chain: the epilogue has read the accumulators
                     if (acc_seq > 0) { mbar_wait(acc_empty, (acc_seq - 1) & 1); tc_fence_after(); }
                     if (tr && it == 0) B2T_TRACE_PTR(p)[k * 8 + 2] = clock64();
                     mi = 0; first = 1; am = 0;
+                    pass_left = min(pc, n_chunks - it);
                 }
-                const bool pass_end = (it % pc == pc - 1) || it == n_chunks - 1;
+                const bool pass_end = --pass_left == 0;
                 const int hb = g_it % kHaloBufs;
                 mbar_wait(&halo_full[hb], (g_it / kHaloBufs) & 1);
                 if (tr && it == 0) B2T_TRACE_PTR(p)[k * 8 + 3] = clock64();
@@ -353,9 +354,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_consta
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
             int b, y0, x0, cout0, z, c_begin, n_chunks;
             decode_item(item, b, y0, x0, cout0, z, c_begin, n_chunks);
-            const int passes = kSmall ? 1 : max(1, min(p.k_passes, n_chunks));
-            const int pc = (n_chunks + passes - 1) / passes;
-            const int n_pass = (n_chunks + pc - 1) / pc;
+            int passes = 1, pc = n_chunks, n_pass = 1;
+            if (!kSmall && p.k_passes > 1) {
+                passes = min(p.k_passes, n_chunks);
+                pc = (n_chunks + passes - 1) / passes;
+                n_pass = (n_chunks + pc - 1) / pc;
+            }
             const int n_main = passes > 1 ? 1 : max(1, min(min(p.n_main, Cfg::kTmemCols / N - 1), n_chunks * taps));
             const bool tr = B2T_TRACE_PTR(p) && blockIdx.x == 0 && k < 64 && threadIdx.x == 64;
             if (tr) B2T_TRACE_PTR(p)[k * 8 + 4] = clock64();
