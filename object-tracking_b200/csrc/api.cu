@@ -1,5 +1,5 @@
 // C-ABI of libb200track.so (include/b200track.h): context, weight packing, TMA descriptors, launch plan.
-// Host code only orchestrates; every numeric step runs in the kernels of conv_umma.cu / decode_nms.cu /
+// Host code only orchestrates; every numeric step runs in the kernels of conv_halo.cu / conv_pm.cu / decode_nms.cu /
 // tracker.cu.  There is no CPU fallback: without a device every compute entry point fails with an error.
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -77,7 +77,7 @@ struct ConvLayer {
     size_t off_whi = 0, off_wlo = 0, off_scale = 0, off_bias = 0;
     int ldw = 0;
     int TW = 16, TH = 8, BN = 128;
-    CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;      // tile engine (conv_umma.cu)
+    CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;      // developer tile engine (dev_engines.cu)
     int hC = 0, hP = 0, hR = 0, hN = 0, h_rows = 0, h_plane_bytes = 0;   // halo engine tile (conv_halo.cu)
     bool h_small = false;                         // two-CTAs-per-SM resource shape
     CUtensorMap tmX_hi, tmX_lo, tmW_hi, tmW_lo;
@@ -91,6 +91,8 @@ struct ConvLayer {
     CUtensorMap tmXf_hi, tmXf_lo;                 // its patch view: [cin_pad][MB*H*W] with a box of 128 pixels
     bool have_weights = false;
     int ps1_buf = -1;                             // tiny graph: a 2x2 stride-1 max-pool of out_buf follows (maxpool_layer.c:79-114)
+    int reorg_buf = -1;                           // darknet semantics, conv_21: out_buf is a plain tensor, reorg_gather_kernel
+                                                  // permutes it into channels [0, 4*cout) of this buffer (blas.c:9-30)
 };
 
 struct b2t_ctx {
@@ -169,9 +171,6 @@ static void choose_halo_tile(int H, int W, int ksize, bool pool, ConvLayer &l) {
         if (pool && (P & 1)) continue;
         for (int R = 1; R <= H; ++R) {
             if (pool && (R & 1)) continue;
-            // the reorg layer's epilogue is a per-element scatter (2-byte stores): keep its tiles small so that even one
-            // frame spreads over many SMs -- its MMA time is negligible (0.04 GFLOP)
-            if (l.index == 21 && R > 2) break;
             const int rows = R + 2 * pad + (wrap ? 1 : 0);
             const int N = round_up(R * P, 16);
             if (rows * P > max_rows || N > max_n || (pool && N > 240)) break;
@@ -424,8 +423,16 @@ extern "C" int b2t_create(const b2t_config *cfg, b2t_ctx **out) {
     {   // conv_21 on the 26x26 skip, space_to_depth into concat[0:256]
         ConvLayer &l = new_conv(c, 21, 1, 512, 64, true, false, 2 * Gs, 2 * Gs);
         l.in_buf = skip_buf;
-        l.out_buf = concat; l.out_ch_off = 0;
-        l.out_mode = cfg->semantics == B2T_SEM_DARKNET ? DEST_REORG_DARKNET : DEST_S2D_TF;
+        if (cfg->semantics == B2T_SEM_DARKNET) {
+            // darknet's reorg is a permutation that mixes positions and channels: as a per-element scatter in the conv
+            // epilogue it was 54 us per 36 frames; conv_21 now writes a plain tensor (coalesced) and a gather kernel with
+            // coalesced stores permutes it into the concat buffer
+            l.out_buf = add_buf(c, "reorg_src", 2 * Gs, 2 * Gs, 64);
+            l.reorg_buf = concat;
+        } else {
+            l.out_buf = concat; l.out_ch_off = 0;
+            l.out_mode = DEST_S2D_TF;
+        }
         blob_reserve(c, l);
         c->cout_by_name["norm_21"] = 64;
     }
@@ -804,7 +811,8 @@ extern "C" int b2t_finalize(b2t_ctx *c, int upload, void *stream) {
         static const int flat_mode = dev_env("B2T_FLAT", 1);
         // (measured: a win up to K = 512; longer K re-streams too many weight bytes per 128-pixel tile -- the
         // shared-memory port saturates -- and the N = 192 whole-image tiles of conv_halo_kernel stay faster)
-        l.flat1x1 = flat_mode && l.k == 1 && !l.pool && l.out_mode == DEST_PLAIN && l.kchunk == 64 && nb == MB &&
+        // (cout > 64: the persistent kernel's weight box is w_rows = 64 rows for narrower layers, its MMA reads 128)
+        l.flat1x1 = flat_mode && l.k == 1 && !l.pool && l.out_mode == DEST_PLAIN && l.kchunk == 64 && nb == MB && l.cout > 64 &&
                     l.cin_pad <= 512 && c->cfg.engine == B2T_ENGINE_TCGEN05;
         if (l.flat1x1) {
             const cuuint64_t npx = (cuuint64_t)MB * l.H * l.W;
@@ -1154,6 +1162,16 @@ static int run_pool_s1(b2t_ctx *c, const ConvLayer &l, int B, cudaStream_t st) {
     return 0;
 }
 
+// darknet reorg (reorg_layer.c:91-110 -> blas.c:9-30, stride 2, forward = 0) of conv_21's plain output into channels
+// [0, 4*cout) of the concat buffer
+static int run_reorg(b2t_ctx *c, const ConvLayer &l, int B, cudaStream_t st) {
+    const ActBuf &in = c->bufs[l.out_buf], &out = c->bufs[l.reorg_buf];
+    const int rc = launch_reorg_gather(in.hi, in.plane, in.C, out.hi, out.plane, out.C, B, l.H, l.W, l.cout, st);
+    if (rc) return fail(-2, "reorg launch: %s", cudaGetErrorString((cudaError_t)rc));
+    c->launches += 1;
+    return 0;
+}
+
 static int forward_impl(b2t_ctx *c, const void *frames, int dtype, int B, float *logits_user, cudaStream_t st,
                         cudaEvent_t *ev /* 24 events or NULL */, int first = 1, int last = -1) {
     if (!c || !c->finalized) return fail(-1, "b2t_yolo_forward: context not finalized");
@@ -1223,15 +1241,17 @@ static int forward_impl(b2t_ctx *c, const void *frames, int dtype, int B, float 
                 cb = chain_new(c->d_chain_counter);
                 chain_add(cb, l.tmX_hi, l.tmX_lo, l.tmW_hi, l.tmW_lo, p);
             }
-            if (l.ps1_buf >= 0) {                          // the stride-1 pool is its own kernel: the chain ends here
+            if (l.ps1_buf >= 0 || l.reorg_buf >= 0) {      // a stride-1 pool / reorg is its own kernel: the chain ends here
                 if ((rc = flush_chain())) return rc;
-                if ((rc = run_pool_s1(c, l, B, st))) return rc;
+                if (l.ps1_buf >= 0 && (rc = run_pool_s1(c, l, B, st))) return rc;
+                if (l.reorg_buf >= 0 && (rc = run_reorg(c, l, B, st))) return rc;
             }
             continue;
         }
         if ((rc = flush_chain())) return rc;
         if ((rc = run_conv(c, l, B, i == NC ? logits : nullptr, st))) return rc;
         if (l.ps1_buf >= 0 && (rc = run_pool_s1(c, l, B, st))) return rc;
+        if (l.reorg_buf >= 0 && (rc = run_reorg(c, l, B, st))) return rc;
         if (ev) cudaEventRecord(ev[i], st);
     }
     if ((rc = flush_chain())) return rc;

@@ -162,7 +162,50 @@ __global__ void __launch_bounds__(256) pool_s1_kernel(const op_t *in, long long 
     }
 }
 
+// darknet's reorg layer (reorg_layer.c:91-110 -> reorg_cpu(x, w, h, c, batch, stride = 2, forward = 0, out), blas.c:9-30) as
+// a GATHER: the (C, H, W) source viewed flat; destination flat index d = i + W*(j + H*k) (k < C, j < H, i < W) takes
+// source flat index s = w2 + 2W*(h2 + 2H*c2) with c2 = k % (C/4), off = k / (C/4), w2 = 2i + off % 2, h2 = 2j + off / 2;
+// the destination buffer is then read as (4C, H/2, W/2).  One thread = 8 consecutive destination channels of one
+// destination pixel (NHWC planes): 16-byte stores, 2-byte gathered loads out of an L2-resident tensor.
+__global__ void __launch_bounds__(256) reorg_gather_kernel(const op_t *in, long long in_plane, int in_stride, op_t *out,
+                                                           long long out_plane, int out_stride, int B, int H, int W, int C) {
+    const int Hd = H / 2, Wd = W / 2, Cd = 4 * C, groups = Cd / 8, out_c = C / 4;
+    const long long total = (long long)B * Hd * Wd * groups;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int g = int(t % groups);
+        const int pix = int(t / groups);                    // (b, yd, xd)
+        const int b = small_div(pix, Hd * Wd), rem = pix - b * Hd * Wd;
+        const int yd = small_div(rem, Wd), xd = rem - yd * Wd;
+        __align__(16) op_t oh[8], ol[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int cd = g * 8 + e;
+            const int d = (cd * Hd + yd) * Wd + xd;         // flat index in the (4C, H/2, W/2) destination = (C, H, W) loop space
+            const int row = small_div(d, W), i = d - row * W;
+            const int k = small_div(row, H), j = row - k * H;
+            const int off = small_div(k, out_c), c2 = k - off * out_c;
+            const int w2 = 2 * i + (off & 1), h2 = 2 * j + (off >> 1);
+            const int s = w2 + 2 * W * (h2 + 2 * H * c2);   // flat index in the (C, H, W) source
+            const int sr = small_div(s, W), xs = s - sr * W;
+            const int cs = small_div(sr, H), ys = sr - cs * H;
+            const op_t *q = in + (((long long)b * H + ys) * W + xs) * in_stride + cs;
+            oh[e] = q[0];
+            ol[e] = q[in_plane];
+        }
+        op_t *dst = out + (long long)pix * out_stride + g * 8;
+        *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(oh);
+        *reinterpret_cast<uint4 *>(dst + out_plane) = *reinterpret_cast<const uint4 *>(ol);
+    }
+}
+
 // ---------------------------------------------------------------- host-side launchers (used by api.cu)
+int launch_reorg_gather(const op_t *in, long long in_plane, int in_stride, op_t *out, long long out_plane, int out_stride, int B,
+                        int H, int W, int C, cudaStream_t st) {
+    const long long total = (long long)B * (H / 2) * (W / 2) * (4 * C / 8);
+    const int blocks = (int)min((long long)148 * 8, (total + 255) / 256);
+    reorg_gather_kernel<<<blocks, 256, 0, st>>>(in, in_plane, in_stride, out, out_plane, out_stride, B, H, W, C);
+    return (int)cudaGetLastError();
+}
 int launch_pool_s1(const op_t *in, long long in_plane, op_t *out, long long out_plane, int B, int H, int W, int C, cudaStream_t st) {
     const long long total = (long long)B * H * W * (C / 8);
     const int blocks = (int)min((long long)148 * 8, (total + 255) / 256);

@@ -9,7 +9,7 @@
 
 namespace b2t {
 
-enum { DEST_PLAIN = 0, DEST_S2D_TF = 1, DEST_REORG_DARKNET = 2 };
+enum { DEST_PLAIN = 0, DEST_S2D_TF = 1 };   // darknet's reorg ordering is a separate gather kernel (conv_misc.cu)
 
 struct Dest {
     op_t *hi;      // fp16 hi plane base (NULL = none)
@@ -90,47 +90,10 @@ __device__ __forceinline__ float leaky(float v) { return v > 0.f ? v : 0.1f * v;
 // far more than the error of the approximate fp32 division
 __device__ __forceinline__ int small_div(int n, int d) { return __float2int_rz(__fdividef((float)n + 0.5f, (float)d)); }
 
-// darknet/src/blas.c:9-30 reorg_cpu(stride 2, forward = 0) as a scatter of source element (c, y, x) of a (C, H, W)
-// tensor: the CHW source is read as if shaped (C/4, 2H, 2W).  With q = c*H + y (row of the (C*H) x W matrix) the flat
-// source index is s = q*W + x, so  w2 = s % 2W = (q & 1)*W + x,  h2 = (s / 2W) % 2H = (q >> 1) % 2H,
-// c2 = s / 4WH = (q >> 1) / 2H;  out channel k = ((h2 & 1)*2 + (w2 & 1))*(C/4) + c2 and the element lands at flat index
-// o = (w2 >> 1) + W*((h2 >> 1) + H*k) of the (4C, H/2, W/2) destination: row R = o / (W/2), column o % (W/2).
-__device__ __forceinline__ void reorg_darknet_dest(int c, int y, int x, int H, int W, int Cout, int &cd, int &yd, int &xd) {
-    const int q = c * H + y, qh = q >> 1;
-    const int c2 = small_div(qh, 2 * H), h2 = qh - c2 * 2 * H, w2 = (q & 1) * W + x;
-    const int k = ((h2 & 1) * 2 + (w2 & 1)) * (Cout >> 2) + c2;
-    const int Wd = W >> 1, Hd = H >> 1, wh = w2 >> 1;
-    const int a = wh >= Wd ? 1 : 0;
-    xd = wh - a * Wd;
-    const int R = a + 2 * ((h2 >> 1) + H * k);
-    cd = small_div(R, Hd);
-    yd = R - cd * Hd;
-}
-
 // Write up to 8 consecutive channels [c, c+8) of source pixel (b,y,x).  Cout = channels of the source tensor.
 __device__ __forceinline__ void emit8(const Dest &d, int b, int y, int x, int c, int Cout, const float (&v)[8]) {
     const int nvalid = min(8, Cout - c);
     if (nvalid <= 0) return;
-    if (d.mode == DEST_REORG_DARKNET) {
-        // darknet/src/blas.c:9-30 reorg_cpu(forward=0) expressed as a scatter of source element (c,y,x):
-        // the CHW source is read as if shaped (C/4, 2H, 2W); see DESIGN.md section 3.
-        const int H = d.H, W = d.W;                 // source dims (26x26), dest is (4C, H/2, W/2)
-        const int Hd = H / 2, Wd = W / 2;
-        for (int i = 0; i < nvalid; ++i) {
-            int cd, yd, xd;
-            reorg_darknet_dest(c + i, y, x, H, W, Cout, cd, yd, xd);
-            const long long pix = ((long long)b * Hd + yd) * Wd + xd;
-            if (d.hi) {
-                op_t h, l;
-                split_f16(v[i], h, l);
-                op_t *p = d.hi + pix * d.pix_stride_b + d.ch_off_b + cd;
-                p[0] = h;
-                p[d.plane_stride] = l;
-            }
-            if (d.f32) d.f32[pix * d.pix_stride_f + d.ch_off_f + cd] = v[i];
-        }
-        return;
-    }
     long long pix;
     int cc = c;
     if (d.mode == DEST_S2D_TF) {  // tf.space_to_depth(2): out[b,y/2,x/2,((y&1)*2+(x&1))*C + c]
@@ -239,11 +202,7 @@ __device__ __forceinline__ void epilogue_store(const ConvParams &p, const float 
 __device__ __forceinline__ void emit1(const Dest &d, int b, int y, int x, int c, int Cout, float v) {
     long long pix;
     int cc = c;
-    if (d.mode == DEST_REORG_DARKNET) {
-        int yd, xd;
-        reorg_darknet_dest(c, y, x, d.H, d.W, Cout, cc, yd, xd);
-        pix = ((long long)b * (d.H / 2) + yd) * (d.W / 2) + xd;
-    } else if (d.mode == DEST_S2D_TF) {
+    if (d.mode == DEST_S2D_TF) {
         pix = ((long long)b * (d.H / 2) + (y >> 1)) * (d.W / 2) + (x >> 1);
         cc = ((y & 1) * 2 + (x & 1)) * Cout + c;
     } else {

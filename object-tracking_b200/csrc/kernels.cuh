@@ -142,6 +142,8 @@ int launch_conv_simt(const SimtView &v, const ConvParams &p, cudaStream_t st);
 int launch_conv1(const Conv1Params &p, cudaStream_t st);
 int launch_planes_to_f32(const op_t *hi, long long plane, int pix_stride, int ch_off, int C, long long npix,
                          float *out, cudaStream_t st);
+int launch_reorg_gather(const op_t *in, long long in_plane, int in_stride, op_t *out, long long out_plane, int out_stride, int B,
+                        int H, int W, int C, cudaStream_t st);
 int launch_pool_s1(const op_t *in, long long in_plane, op_t *out, long long out_plane, int B, int H, int W, int C, cudaStream_t st);
 int launch_decode(bool darknet, const DecodeParams &p, cudaStream_t st);
 int launch_lstm_gates(const LstmParams &p, cudaStream_t st);
