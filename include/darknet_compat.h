@@ -12,9 +12,10 @@
  * Differences from darknet, all deliberate:
  *  - errors never exit() the process: load_network returns NULL, the others return empty results, and the text is
  *    available from b2t_last_error() (darknet: error()/file_error() print and exit, utils.c:253-285);
- *  - only the YOLOv2 graph of cfg/yolov2.cfg (any class count / input size multiple of 32) is accepted;
- *  - load_image_color decodes binary PPM (P6) only -- JPEG/PNG decoding is stb_image inside darknet and is
- *    frame ingest, outside this path; callers that hold pixels use make_image()/network_predict.
+ *  - accepted graphs: cfg/yolov2.cfg, cfg/yolov2-voc.cfg (23 conv layers) and cfg/yolov2-tiny.cfg, cfg/yolov2-tiny-voc.cfg
+ *    (9 conv layers, sixth max-pool with stride 1); any class count, anchors and square input multiple of 32;
+ *  - load_image_color decodes Huffman-coded JPEG (sequential and progressive; bit-exact with darknet's stb_image path,
+ *    csrc/jpeg_decode.cu) and binary PPM (P6); PNG / BMP callers hold pixels and use make_image()/network_predict.
  */
 #ifndef B200_DARKNET_COMPAT_H
 #define B200_DARKNET_COMPAT_H
@@ -43,7 +44,7 @@ network *load_network(char *cfg, char *weights, int clear);            /* networ
 void free_network(network *net);
 metadata get_metadata(char *file);                                     /* option_list.c:35-50 */
 image make_image(int w, int h, int c);
-image load_image_color(char *filename, int w, int h);                  /* image.c:1482 (PPM only here) */
+image load_image_color(char *filename, int w, int h);                  /* image.c:1482 (JPEG, PPM) */
 void rgbgr_image(image im);                                            /* image.c:515-525   */
 void free_image(image m);
 float *network_predict(network *net, float *input);                    /* network.c:507-518; CHW float, net-sized */
