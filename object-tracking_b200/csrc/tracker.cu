@@ -360,23 +360,37 @@ __global__ void pool_features_kernel(const PoolParams p) {
     }
 }
 
-// Global max, natural layout: one CTA per (frame, 64 channels), 4 pixel lanes per channel (coalesced 128-byte rows)
+// Global max, natural layout: one CTA per (frame, 64 channels).  A thread owns 8 consecutive channels (one 16-byte load
+// per plane and pixel) and one of 32 pixel lanes; a warp reads 4 pixels x 128 contiguous bytes per load instruction and
+// every thread has all its loads in flight at once (13x13 grid: 6 pixels x 2 planes).  max() is exact in any order.
 __global__ void __launch_bounds__(256) pool_global_kernel(const PoolParams p) {
-    __shared__ float red[4][64];
-    const int b = blockIdx.x, c = blockIdx.y * 64 + (threadIdx.x & 63), pl = threadIdx.x >> 6;
-    float m = -INFINITY;
+    __shared__ float red[32][64 + 1];
+    const int b = blockIdx.x, cg = threadIdx.x & 7, pl = threadIdx.x >> 3;
+    const int c = blockIdx.y * 64 + cg * 8;
+    float m[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
     if (c < p.C) {
         const op_t *q = p.hi + (long long)b * p.H * p.W * p.pix_stride + p.ch_off + c;
-        for (int px = pl; px < p.H * p.W; px += 4) {
+#pragma unroll 4
+        for (int px = pl; px < p.H * p.W; px += 32) {
             const op_t *e = q + (long long)px * p.pix_stride;
-            m = fmaxf(m, join_f16(e[0], e[p.plane]));
+            const uint4 h4 = *reinterpret_cast<const uint4 *>(e), l4 = *reinterpret_cast<const uint4 *>(e + p.plane);
+            const op_t *h = reinterpret_cast<const op_t *>(&h4), *l = reinterpret_cast<const op_t *>(&l4);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], join_f16(h[i], l[i]));
         }
     }
-    red[pl][threadIdx.x & 63] = m;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[pl][cg * 8 + i] = m[i];
     __syncthreads();
-    if (threadIdx.x < 64 && c < p.C)
-        p.out[(long long)b * p.C + c] = fmaxf(fmaxf(red[0][threadIdx.x], red[1][threadIdx.x]),
-                                              fmaxf(red[2][threadIdx.x], red[3][threadIdx.x]));
+    if (threadIdx.x < 64) {
+        const int ch = blockIdx.y * 64 + threadIdx.x;
+        float v = red[0][threadIdx.x];
+#pragma unroll
+        for (int r = 1; r < 32; ++r) v = fmaxf(v, red[r][threadIdx.x]);
+        if (ch < p.C) p.out[(long long)b * p.C + ch] = v;
+    }
 }
 
 // ---------------------------------------------------------------- heat maps (utils.py:53-79)
@@ -523,7 +537,11 @@ int launch_dense_sigmoid(const float *h, const float *wd, const float *bd, int u
     return (int)cudaGetLastError();
 }
 int launch_pool_features(const PoolParams &p, cudaStream_t st) {
-    if (p.mode == 0 && !p.chw_view) {
+    // 16-byte loads: 8-channel groups aligned in both planes (every activation buffer of the engine is; anything else
+    // takes the element-wise kernel below)
+    const bool vec = (p.C & 7) == 0 && (p.pix_stride & 7) == 0 && (p.ch_off & 7) == 0 && (p.plane & 7) == 0 &&
+                     (reinterpret_cast<uintptr_t>(p.hi) & 15) == 0;
+    if (p.mode == 0 && !p.chw_view && vec) {
         pool_global_kernel<<<dim3(p.B, (p.C + 63) / 64), 256, 0, st>>>(p);
         return (int)cudaGetLastError();
     }

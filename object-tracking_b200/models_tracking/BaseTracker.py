@@ -95,9 +95,18 @@ class BaseTracker(object):
     def _decode_and_pool(self, B: int, W: int, H: int, heat_size: int = 0):
         """Everything after the conv stack, on the engine's current logits / feature buffers."""
         det = self.model_detector
+        # the feature pooling does not depend on the detections: it runs on a side stream beside decode + selection
+        # (two parallel branches when the tail is captured into a CUDA graph)
+        cur = torch.cuda.current_stream()
+        side = self.__dict__.get("_pool_stream")
+        if side is None:
+            side = self._pool_stream = torch.cuda.Stream(device=det.engine.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            fv = det.engine.pool_features(self._fv_name, B, self.pool, self.ref_layout_bug)
         dets, counts = det.engine.region_detect(det.engine.logits(B), det.THRESH, det.NMS, W, H)
         det_in, heat, chosen = det.engine.select_detection(dets, counts, W, H, det.class_mask, heat_size)
-        fv = det.engine.pool_features(self._fv_name, B, self.pool, self.ref_layout_bug)
+        cur.wait_stream(side)
         return fv, det_in, heat, chosen
 
     def _tail(self, S: int, T: int, W: int, H: int, reset: bool) -> torch.Tensor:

@@ -85,6 +85,13 @@ lib.do_nms_obj(dd, num.value, 80, 0.45)
 lib.network_extract_feat(net, 25)
 lib.free_detections(dd, num.value)
 lib.free_image(im)
-done += ["compat: letterbox, chw_to_hwc, hwc_to_chw, region_activate"]
+done += ["compat: letterbox, chw_to_hwc, hwc_to_chw, region_activate", "reorg_gather (darknet semantics)"]
+# the tiny graph (cfg/yolov2-tiny-voc.cfg): stride-1 max-pool kernel, 16-channel conv_1
+tcfg, twts = os.path.join(d, "tiny.cfg"), os.path.join(d, "tiny.weights")
+darknet_ref.write_tiny_weights(twts, 20, 1024, seed=3)
+te = DetectorEngine(n_class=20, max_batch=2, semantics="darknet", graph="tiny", tiny_filters=1024)
+te.load_darknet_weights(twts); te.finalize()
+te.forward(frames(2)); te.forward(frames(1))
+done += ["pool_s1 (tiny graph)"]
 torch.cuda.synchronize()
 print("exercised:", ", ".join(done))
