@@ -461,6 +461,35 @@ def roofline_block(r, fwd_ms, timed_ms, kernel_desc):
 TRAFFIC_NCU = {("tiny", 36): 2.140e9}
 
 
+def plugin_call_leg(r, n: int = 60):
+    """The reference's own per-frame call of the TinyTracker flow, unchanged: a JPEG on disk ->
+    ``model_detector.extract_spatio_info(frame_path, fv_layer)`` -> (class-filtered detections, 13x13x1024 feature) on
+    the host (preprocessing.py:412-418, YOLO.py:172-180).  Host JPEG decode, letterbox ingest, one-frame forward, region
+    decode + NMS, 173 056-float feature read-back: wall clock per call, every call synchronous like the reference's."""
+    import cv2
+    import torch
+    tmp = tempfile.mkdtemp()
+    rng = np.random.default_rng(7)
+    paths = []
+    for i in range(4):                                           # 640x480 frames: smooth ramps + noise, not net-sized
+        yy, xx = np.mgrid[0:480, 0:640]
+        img = np.stack([(xx * (i + 1)) % 256, (yy * 2 + 40 * i) % 256, ((xx + yy) // 2) % 256], -1).astype(np.float32)
+        img = np.clip(img + rng.normal(0, 12, img.shape), 0, 255).astype(np.uint8)
+        paths.append(os.path.join(tmp, f"f{i}.jpg"))
+        cv2.imwrite(paths[-1], img)
+    det = r.obj.model_detector
+    for i in range(4):
+        det.extract_spatio_info(paths[i % 4], r.obj.detection_fv_layer)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(n):
+        dets, feat = det.extract_spatio_info(paths[i % 4], r.obj.detection_fv_layer)
+    dt = (time.perf_counter() - t0) / n
+    return {"c2_plugin_call": "YOLO.extract_spatio_info(640x480 JPEG path, fv_layer): host decode + letterbox + forward + "
+                              "region/NMS + feature read-back, synchronous",
+            "c2_plugin_call_ms": 1e3 * dt, "c2_plugin_call_fps": 1.0 / dt, "c2_plugin_call_feat_floats": int(feat.size)}
+
+
 def main_b200(args):
     import torch
     import torch.distributed as dist
@@ -536,6 +565,8 @@ def main_b200(args):
                     line[key + "_conv_ms"] = f
                     line[key + "_hbm_frac"] = rr.bytes_per_step / (f * 1e-3) / 1e9 / pk["hbm"]
                     line[key + "_tensor_frac"] = rr.flops_per_step / (f * 1e-3) / 1e12 / pk["tflops_burst"]
+                    if name == "c2":
+                        line.update(plugin_call_leg(rr))
                     del rr
                     torch.cuda.empty_cache()
                 except Exception as e:                          # a secondary config must not lose the headline

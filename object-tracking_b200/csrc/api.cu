@@ -620,7 +620,9 @@ extern "C" int b2t_set_conv_weights(b2t_ctx *c, int idx, const float *ker, const
         float *s1 = reinterpret_cast<float *>(c->host_blob.data() + c->off_s1);
         fold_bn(c, 32, gamma, beta, mean, var, s1, reinterpret_cast<float *>(c->host_blob.data() + c->off_b1));
         // tensor-core path (conv_pm.cu mode 1): per kernel row kh a [32 cout][32 k] fp16 tile, k = kw*8 + cin, stored
-        // as 128-byte core matrices [cout/8][k/8][cout%8][k%8]; hi plane then lo plane; 1/255 goes into the scale
+        // as 128-byte core matrices [cout/8][k/8][cout%8][k%8]; the three tiles of the hi plane in DESCENDING kernel-row
+        // order (kh = 2, 1, 0), then the lo plane: two consecutive tiles [W_kh ; W_kh-1] form the 64-row operand that
+        // serves both output rows of a row pair from one patch row; 1/255 goes into the scale
         op_t *wp = reinterpret_cast<op_t *>(c->host_blob.data() + c->off_w1pm);
         float *s1pm = reinterpret_cast<float *>(c->host_blob.data() + c->off_s1pm);
         memset(wp, 0, 3 * 4096);
@@ -641,8 +643,8 @@ extern "C" int b2t_set_conv_weights(b2t_ctx *c, int idx, const float *ker, const
             for (int kh = 0; kh < 3; ++kh)
                 for (int kw = 0; kw < 3; ++kw)
                     for (int ci = 0; ci < 3; ++ci) {
-                        const size_t d = (size_t)kh * 2048 + (size_t)((co / 8) * 4 + kw) * 64 + (co % 8) * 8 + ci;   // fp16 elements
-                        split_f16(ker[((kh * 3 + kw) * 3 + ci) * 32 + co] * up, wp[d], wp[d + 1024]);
+                        const size_t d = (size_t)(2 - kh) * 1024 + (size_t)((co / 8) * 4 + kw) * 64 + (co % 8) * 8 + ci;   // fp16 elements
+                        split_f16(ker[((kh * 3 + kw) * 3 + ci) * 32 + co] * up, wp[d], wp[d + 3072]);
                     }
             s1pm[co] = (float)(fabs((double)s1[co]) * (double)ldexpf(1.f, -shift) / 255.0);
         }

@@ -39,6 +39,19 @@ __device__ __forceinline__ void umma_pm3(uint32_t t_main, uint32_t t_corr, uint3
     umma_f16(t_main, dxh, dwh, idesc, acc);
 }
 
+// The same three products in TWO instructions when the lo weight tile directly follows the hi tile in shared memory
+// (w_rows == N): B = [w_hi ; w_lo] is then one K-major operand of 2N rows, and x_hi * [w_hi ; w_lo] fills the adjacent
+// accumulators [main | corr] at once; x_lo * w_hi follows into corr.  Same addends in the same order per accumulator
+// (bit-identical), but x_hi and w_hi are read from shared memory once instead of twice: 14 KB instead of 18 KB per K step
+// at N = 64, where the kernel is bound by the tensor core's shared-memory reads (ncu: l1tex data pipe 66-72 % of peak
+// with the tensor pipe 48 % active).
+__device__ __forceinline__ void umma_pm2(uint32_t t_main, uint32_t N, uint32_t xh, uint32_t xl, uint32_t wh, uint32_t hi,
+                                         uint32_t idesc_2n, uint32_t idesc_n, uint32_t acc) {
+    const uint64_t dxh = umma_desc_make(xh, hi), dxl = umma_desc_make(xl, hi), dwh = umma_desc_make(wh, hi);
+    umma_f16(t_main, dxh, dwh, idesc_2n, acc);
+    umma_f16(t_main + N, dxl, dwh, idesc_n, 1u);
+}
+
 __global__ void __launch_bounds__(kPmThreads, 2)
 conv_pm_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
                const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
@@ -168,25 +181,37 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant
                 const uint32_t a_hi = (128u >> 4) | (1u << 14), b_hi = (512u >> 4) | (1u << 14);
                 const uint32_t xa = p16_0 + hb * pb16;                       // LBO field = 1 (16 B) from umma_desc_lo
                 const uint32_t wb = w16 | ((128u >> 4) << 16);
-                // the item is a pair of image rows (one pooled row): output row r uses patch rows r + kh and
-                // accumulates into columns [r*N, r*N + N) of the item's TMEM buffer.  u*w_hi and u*w_lo share the
-                // accumulator here: the chain is 12 MMAs short, so the w_lo terms (2^-11 of the sum) keep 13 bits
+                // The item is a pair of image rows (one pooled row): output row r uses patch rows r + kh and accumulates
+                // into columns [r*N, r*N + N) of the item's TMEM buffer.  Patch rows 1 and 2 feed BOTH output rows (with
+                // kernel rows j and j-1), so they are read once: the packed weights keep the kernel rows in DESCENDING
+                // order per plane, and the N = 64 operand that starts at kernel row j is [W_j ; W_j-1] = the columns of
+                // row 0 and row 1.  Patch rows 0 / 3 feed one output row each (N = 32).  16 MMAs and 88 KB of shared-memory
+                // operand reads per item instead of 24 and 120 KB -- the kernel is bound by those reads (ncu: tensor
+                // data pipe 72 % of peak with the tensor pipe 30 % active).  u*w_hi and u*w_lo share the accumulator: the
+                // chain is 12 MMAs short, so the w_lo terms (2^-11 of the sum) keep 13 bits.
                 const uint32_t t_buf = tmem_base + ab * 2 * N;
+                const uint32_t idesc2 = umma_idesc_f16(128, 2 * N);
+                auto wdesc = [&](int kh, int plane, int ks) {
+                    return umma_desc_make(wb + plane * (6144 >> 4) + (2 - kh) * (2048 >> 4) + ks * (256 >> 4), b_hi);
+                };
                 if (elect_one()) {
+                    if (!(B2T_DBG_BITS(p) & 8)) {
 #pragma unroll
-                    for (int r = 0; r < 2; ++r) {
-#pragma unroll
-                        for (int kh = 0; kh < 3; ++kh) {
+                        for (int pr = 1; pr <= 2; ++pr) {
 #pragma unroll
                             for (int ks = 0; ks < 2; ++ks) {
-                                const uint64_t da = umma_desc_make(xa + (r + kh) * p.hP + 2 * ks, a_hi);
-                                const uint64_t dwh = umma_desc_make(wb + kh * (4096 >> 4) + ks * (256 >> 4), b_hi);
-                                const uint64_t dwl = umma_desc_make(wb + kh * (4096 >> 4) + (2048 >> 4) + ks * (256 >> 4), b_hi);
-                                const uint32_t acc = (kh | ks) ? 1u : 0u;
-                                if (B2T_DBG_BITS(p) & 8) continue;
-                                umma_f16(t_buf + r * N, da, dwh, idesc, acc);
-                                umma_f16(t_buf + r * N, da, dwl, idesc, 1u);
+                                const uint64_t da = umma_desc_make(xa + pr * p.hP + 2 * ks, a_hi);
+                                umma_f16(t_buf, da, wdesc(pr, 0, ks), idesc2, (pr == 1 && ks == 0) ? 0u : 1u);
+                                umma_f16(t_buf, da, wdesc(pr, 1, ks), idesc2, 1u);
                             }
+                        }
+#pragma unroll
+                        for (int ks = 0; ks < 2; ++ks) {
+                            const uint64_t d0 = umma_desc_make(xa + 2 * ks, a_hi), d3 = umma_desc_make(xa + 3 * p.hP + 2 * ks, a_hi);
+                            umma_f16(t_buf, d0, wdesc(0, 0, ks), idesc, 1u);          // patch row 0 -> output row 0, kernel row 0
+                            umma_f16(t_buf, d0, wdesc(0, 1, ks), idesc, 1u);
+                            umma_f16(t_buf + N, d3, wdesc(2, 0, ks), idesc, 1u);      // patch row 3 -> output row 1, kernel row 2
+                            umma_f16(t_buf + N, d3, wdesc(2, 1, ks), idesc, 1u);
                         }
                     }
                     umma_commit(&patch_empty[hb]);
@@ -201,6 +226,9 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant
             const uint32_t kb16 = p.kbytes >> 4, row16 = p.hP * kb16 - (p.ksize - 1) * kb16;
             const uint32_t xl_off = p.h_plane_bytes >> 4, wl_off = p.pw_tile_bytes >> 5, wt16 = p.pw_tile_bytes >> 4;
             const bool k128 = p.kbytes == 128;
+            // hi and lo weight tiles adjacent and 2N accumulator columns in one instruction: merged issue (umma_pm2)
+            const bool merged = p.pw_tile_bytes == 2 * N * p.kbytes && 2 * N <= 256;
+            const uint32_t idesc_2n = umma_idesc_f16(128, 2 * N);
             uint32_t acc = 0, wh = w16 | (1u << 16);
             for (int ci = 0; ci < p.cin_chunks; ++ci, ++g_chunk) {
                 const int hb = g_chunk & 1;
@@ -212,13 +240,21 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant
                     const uint32_t xl = xh + xl_off, wl = wh + wl_off;
                     const bool last_tap = tap == taps - 1;
                     if (elect_one()) {
-                        if (!(B2T_DBG_BITS(p) & 8)) {
-                        umma_pm3(t_main, t_corr, xh, xl, wh, wl, dhi, idesc, acc);
-                        umma_pm3(t_main, t_corr, xh + 2, xl + 2, wh + 2, wl + 2, dhi, idesc, 1u);
-                        }
-                        if (k128 && !(B2T_DBG_BITS(p) & 8)) {
-                            umma_pm3(t_main, t_corr, xh + 4, xl + 4, wh + 4, wl + 4, dhi, idesc, 1u);
-                            umma_pm3(t_main, t_corr, xh + 6, xl + 6, wh + 6, wl + 6, dhi, idesc, 1u);
+                        if (B2T_DBG_BITS(p) & 8) {
+                        } else if (merged) {
+                            umma_pm2(t_main, N, xh, xl, wh, dhi, idesc_2n, idesc, acc);
+                            umma_pm2(t_main, N, xh + 2, xl + 2, wh + 2, dhi, idesc_2n, idesc, 1u);
+                            if (k128) {
+                                umma_pm2(t_main, N, xh + 4, xl + 4, wh + 4, dhi, idesc_2n, idesc, 1u);
+                                umma_pm2(t_main, N, xh + 6, xl + 6, wh + 6, dhi, idesc_2n, idesc, 1u);
+                            }
+                        } else {
+                            umma_pm3(t_main, t_corr, xh, xl, wh, wl, dhi, idesc, acc);
+                            umma_pm3(t_main, t_corr, xh + 2, xl + 2, wh + 2, wl + 2, dhi, idesc, 1u);
+                            if (k128) {
+                                umma_pm3(t_main, t_corr, xh + 4, xl + 4, wh + 4, wl + 4, dhi, idesc, 1u);
+                                umma_pm3(t_main, t_corr, xh + 6, xl + 6, wh + 6, wl + 6, dhi, idesc, 1u);
+                            }
                         }
                         if (last_tap) umma_commit(&patch_empty[hb]);
                         if (last_tap && ci == p.cin_chunks - 1) umma_commit(&acc_full[ab]);
