@@ -651,3 +651,31 @@ def test_wide_batchnorm_spread_weights():
         err = np.abs(lg - o["logits"]).max()
         assert err < 1e-4 * max(1.0, np.abs(o["logits"]).max()), (sem, err, np.abs(o["logits"]).max())
         del eng
+
+
+@pytest.mark.parametrize("size,B", [(320, 3), (352, 1), (512, 2), (544, 1)])
+def test_other_network_sizes_against_fp64_oracle(size, B):
+    """darknet accepts any width/height that is a multiple of 32 (cfg `width=`/`height=`, parser.c:611-623; its multi-scale
+    training uses 320..608): grids 10, 11, 16 and 17 exercise other tile geometries (odd grids, partial tiles) and, at one
+    frame, the chain schedule's image-size condition.  Logits against the fp64 oracle, every kept layer of frame 0."""
+    from object_tracking_b200.engine import DetectorEngine
+    w = W.synthetic_yolo_weights(20, seed=4)
+    frames = np.random.default_rng(size).integers(0, 256, (B, size, size, 3), dtype=np.uint8)
+    e = DetectorEngine(n_class=20, image_size=size, max_batch=B, semantics="darknet")
+    e.set_weights(w)
+    e.finalize()
+    lg = e.forward(torch.from_numpy(frames).cuda()).cpu().numpy()
+    G = size // 32
+    assert lg.shape == (B, G, G, 5, 25)
+    names = ["norm_3", "norm_7", "norm_13", "norm_20", "concat"]
+    o = yolo_oracle.yolo_forward(yolo_oracle.normalize(frames), w, 20, dtype=np.float64, mode="darknet", want=names)
+    assert np.abs(lg - o["logits"]).max() < 1e-3 * max(1.0, np.abs(o["logits"]).max() / 10), np.abs(lg - o["logits"]).max()
+    for n in names:
+        got, ref = e.extract(n, B).cpu().numpy(), o[n]
+        assert got.shape == ref.shape, n
+        assert np.abs(got - ref).max() / np.abs(ref).max() < 3e-5, (n, size)
+    dets, counts = e.region_detect(torch.from_numpy(lg).cuda(), 0.3, 0.45, size, size)
+    region = darknet_oracle.region_forward(np.transpose(o["logits"][0].reshape(G, G, -1), (2, 0, 1)).astype(np.float32), 20)
+    boxes, obj, prob = darknet_oracle.detect(region, size, size, size, size, 0.3, 0.45, 20)
+    kept = int((prob > 0).sum())                                                    # rows = (box, class) pairs above the threshold
+    assert abs(int(counts.cpu()[0]) - kept) <= 1, (int(counts.cpu()[0]), kept)     # a score on the threshold may flip
