@@ -125,6 +125,13 @@ WORKLOADS = {
     # configs[3]: 32 streams over 8 GPUs = 4 streams per GPU advancing frame by frame (batch 4 per step)
     "c4": dict(cls="TinyTracker", n_class=80, image=416, S=4, T=1,
                what="TinyTracker YOLOv2-416 C=80 + LSTM(512), %d streams per GPU, one frame of each per step"),
+    # configs[3] / configs[4] with each stream's clip cut into 4-frame windows like the headline (the trackers are stateless
+    # across windows): 4 x 4 = 16 and 8 x 4 = 32 frames per step -- the throughput regime of the same streams
+    "c4w": dict(cls="TinyTracker", n_class=80, image=416, S=4, T=4,
+                what="TinyTracker YOLOv2-416 C=80 + LSTM(512), %d streams per GPU, one 4-frame window of each per step"),
+    "c5w": dict(cls="TinyHeatmapTracker", n_class=80, image=608, S=8, T=4,
+                what="TinyHeatmapTracker YOLOv2-608 C=80 + LSTM(512) heat-map head, %d streams per GPU, one 4-frame window "
+                     "of each per step"),
     # configs[2]: MultiObjDetTracker, 20 classes, ConvLSTM2D(512) + 1x1 head + decode_netout of the tracker output
     "multiobj": dict(cls="MultiObjDetTracker", n_class=20, image=416, S=9, T=4,
                      what="MultiObjDetTracker YOLOv2-416 C=20 (Keras semantics) + ConvLSTM2D(512) + 1x1 head + "
@@ -552,10 +559,11 @@ def main_b200(args):
         torch.cuda.empty_cache()
         if world == 1 and not args.no_extra and args.workload == "tiny":
             # the other BASELINE configs that fit one GPU, short runs, reported as scalar keys beside the headline
-            for name, key in (("c2", "c2_b1"), ("c4", "c4_b4"), ("multiobj", "c3_multiobj_b36"), ("c5", "c5_608_b8")):
+            for name, key in (("c2", "c2_b1"), ("c4", "c4_b4"), ("multiobj", "c3_multiobj_b36"), ("c5", "c5_608_b8"),
+                              ("c4w", "c4_w16"), ("c5w", "c5_608_w32")):
                 try:
-                    rr = Runner(name, WORKLOADS[name]["S"], 0, 1, local, PIPE, clip_windows=32)
-                    k = 100 if name in ("c2", "c4", "c5") else 40
+                    rr = Runner(name, WORKLOADS[name]["S"], 0, 1, local, PIPE, clip_windows=32 if name not in ("c4w", "c5w") else 8)
+                    k = 100 if name in ("c2", "c4", "c5") else 40 if name != "c5w" else 20
                     m, f, _ = timed_loop(rr, k, 5, barrier)
                     B = rr.S * rr.T
                     pk = measured_peaks()
@@ -588,7 +596,8 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="tiny", choices=sorted(WORKLOADS),
                     help="BASELINE.json config: tiny = configs[1] batched over 9 windows (headline), c2 = configs[1] "
-                         "frame by frame, multiobj = configs[2], c4 = configs[3] per GPU, c5 = configs[4] per GPU")
+                         "frame by frame, multiobj = configs[2], c4 = configs[3] per GPU, c5 = configs[4] per GPU "
+                         "(c4w / c5w: the same streams in 4-frame windows)")
     ap.add_argument("--windows", type=int, default=0,
                     help="windows / streams per GPU per step (default: the workload's; tiny: 9 x 4 = 36 frames: 36 "
                          "images x 8 cout tiles = 288 work items ~ 2 x 148 SMs for the 13x13 layers)")
