@@ -1534,6 +1534,9 @@ extern "C" int b2t_lstm_sequence(b2t_lstm *l, const float *fv, const float *det,
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
     if (reset && (rc = b2t_lstm_reset(l, -1, stream))) return rc;
+    // one step per stream (streams advancing frame by frame): the full-step kernel does projection + recurrence in one
+    // pass over the weights -- two launches instead of three, none of them cooperative
+    if (T == 1) return b2t_lstm_step_slots(l, 0, fv, l->n_feat, det, l->n_det, S, y, l->n_out, hard_sigmoid, stream);
     const int u = l->units, R = S * T;
     LstmParams p;
     memset(&p, 0, sizeof p);
