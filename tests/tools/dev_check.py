@@ -1,6 +1,6 @@
 """Developer check run under gpurun: per-layer error of both conv engines against the fp64 oracle."""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np, torch
 from object_tracking_b200 import weights as W

@@ -1,6 +1,6 @@
 """gpurun helper: per-layer error of the engines vs the fp64 oracle + per-conv timings at a given batch."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np, torch
 from object_tracking_b200 import weights as W

@@ -9,7 +9,7 @@ schemes:  xh    = drop the x_lo term (activations rounded to fp16)
           hh    = one term (both rounded)
           f8    = corrections computed from e4m3-rounded factors: xh*wh + q8(xh)*q8(wl) + q8(xl)*q8(wh)
 
-usage: python scripts/precision_budget_cpu.py [B] [n_class]
+usage: python tests/tools/precision_budget_cpu.py [B] [n_class]
 """
 import os
 import sys
@@ -18,7 +18,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from object_tracking_b200 import weights as W  # noqa: E402
 from oracle import yolo_oracle as Y  # noqa: E402
 

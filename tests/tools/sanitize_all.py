@@ -1,12 +1,12 @@
 """One small-shape call of every kernel of libb200track.so, to be run under compute-sanitizer:
 
-  compute-sanitizer --tool memcheck  python scripts/sanitize_all.py
-  compute-sanitizer --tool racecheck python scripts/sanitize_all.py
-  compute-sanitizer --tool synccheck python scripts/sanitize_all.py
+  compute-sanitizer --tool memcheck  python tests/tools/sanitize_all.py
+  compute-sanitizer --tool racecheck python tests/tools/sanitize_all.py
+  compute-sanitizer --tool synccheck python tests/tools/sanitize_all.py
 
 Prints the list of kernels it exercised; the sanitizer's own summary follows on stderr."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np, torch
 from object_tracking_b200 import weights as W
